@@ -1,0 +1,315 @@
+"""oracle/pem_oracle.py -- CPU restatement of the PEM geometric hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this file;
+it is used by tests/, by ``__graft_entry__.smoke()`` as the checker, and by the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+
+Two halves:
+
+* the pointnet2 ops are the plain-C restatement in ``pointnet2_oracle.c``
+  (built by ``oracle/Makefile`` into ``oracle/_build/libpem_oracle.so``) called
+  through ctypes on numpy arrays;
+* the dense geometric functions are restated with torch *CPU* ops, because the
+  reference itself is torch CPU code whose third-party arithmetic (ATen
+  softmax/cumsum, LAPACK gesdd through ``torch.svd``, ``torch.det``,
+  ``torch.topk``) cannot be re-derived bit-for-bit in numpy.  The restatement
+  is staged (every intermediate the parity plan S1..S5 needs is returned) and
+  takes the random draw as an explicit argument.
+
+Pinning: validated against the live, unmodified reference
+(``oracle/ref_live.py``, this container only) by ``tests/test_oracle_cpu.py``
+and against the committed fixtures in ``tests/golden/`` written by
+``oracle/make_golden.py`` from that live reference.
+
+Reference citations are relative to
+/root/reference/SAM-6D/Pose_Estimation_Model/ (``MU`` = utils/model_utils.py).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+# --------------------------------------------------------------------------
+# pointnet2 ops: C oracle through ctypes
+# --------------------------------------------------------------------------
+def lib_path():
+    return os.path.join(_HERE, "_build", "libpem_oracle.so")
+
+
+def build_c_oracle():
+    """gcc the C restatement (idempotent)."""
+    src = os.path.join(_HERE, "pointnet2_oracle.c")
+    out = lib_path()
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(
+        ["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build_c_oracle())
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def fps(xyz, npoint, skip_near_origin=True):
+    """(B,N,3) f32 -> (B,npoint) i32.  sampling.cpp:76-118 (CPU semantics)."""
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    idx = np.zeros((B, npoint), np.int32)
+    scratch = np.empty((B, N), np.float32)
+    _lib().oracle_fps(_p(xyz), B, N, npoint, int(skip_near_origin), _p(scratch), _p(idx))
+    return idx
+
+
+def gather(feat, idx):
+    """(B,C,N) f32, (B,M) i32 -> (B,C,M).  sampling.cpp:23-44."""
+    feat, idx = _f32(feat), _i32(idx)
+    B, C, N = feat.shape
+    M = idx.shape[1]
+    out = np.zeros((B, C, M), np.float32)
+    _lib().oracle_gather(_p(feat), _p(idx), B, C, N, M, _p(out))
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    """(B,M,3),(B,N,3) -> (B,M,nsample) i32.  ball_query.cpp:16-62."""
+    new_xyz, xyz = _f32(new_xyz), _f32(xyz)
+    B, M, _ = new_xyz.shape
+    N = xyz.shape[1]
+    idx = np.zeros((B, M, nsample), np.int32)
+    _lib().oracle_ball_query(_p(new_xyz), _p(xyz), B, M, N,
+                             ctypes.c_float(radius), nsample, _p(idx))
+    return idx
+
+
+def group(feat, idx):
+    """(B,C,N) f32, (B,M,ns) i32 -> (B,C,M,ns).  group_points.cpp:20-45."""
+    feat, idx = _f32(feat), _i32(idx)
+    B, C, N = feat.shape
+    _, M, ns = idx.shape
+    out = np.zeros((B, C, M, ns), np.float32)
+    _lib().oracle_group(_p(feat), _p(idx), B, C, N, M, ns, _p(out))
+    return out
+
+
+def query_and_group(xyz, new_xyz, features, radius, nsample):
+    """QueryAndGroup.forward, use_xyz=True (pointnet2_utils.py:326-403).
+
+    xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) -> (B,3+C,M,ns), idx.
+    """
+    xyz, new_xyz, features = _f32(xyz), _f32(new_xyz), _f32(features)
+    idx = ball_query(new_xyz, xyz, radius, nsample)
+    g_xyz = group(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx)
+    g_xyz = g_xyz - new_xyz.transpose(0, 2, 1)[:, :, :, None]
+    g_feat = group(features, idx)
+    return np.concatenate([g_xyz, g_feat], axis=1), idx
+
+
+def sample_pts_feats(pts, feats, npoint):
+    """MU:70-84.  pts (B,N,3), feats (B,N,C) -> (B,npoint,3), (B,npoint,C), idx."""
+    pts, feats = _f32(pts), _f32(feats)
+    idx = fps(pts, npoint)
+    p = gather(np.ascontiguousarray(pts.transpose(0, 2, 1)), idx).transpose(0, 2, 1)
+    f = gather(np.ascontiguousarray(feats.transpose(0, 2, 1)), idx).transpose(0, 2, 1)
+    return p, f, idx
+
+
+# --------------------------------------------------------------------------
+# dense geometric functions: torch CPU restatement
+# --------------------------------------------------------------------------
+def _t(a):
+    return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+
+
+def feature_similarity(feat1, feat2, temp=1.0, normalize=True):
+    """Cosine similarity / temp.  MU:131-153 ('cosine' branch; F.normalize eps=1e-12)."""
+    a, b = _t(feat1).float(), _t(feat2).float()
+    if normalize:
+        a = a / a.norm(dim=2, keepdim=True).clamp_min(1e-12)
+        b = b / b.norm(dim=2, keepdim=True).clamp_min(1e-12)
+    return torch.bmm(a, b.transpose(1, 2)) / temp
+
+
+def sq_pairwise(x, y):
+    """x2 - 2xy + y2 clamped at 0 (MU:101-128, expanded form, not sum((x-y)^2))."""
+    xy = x @ y.transpose(-1, -2)
+    x2 = (x ** 2).sum(-1).unsqueeze(-1)
+    y2 = (y ** 2).sum(-1).unsqueeze(-2)
+    return (x2 - 2 * xy + y2).clamp(min=0.0)
+
+
+def dual_softmax(atten):
+    """softmax over columns times softmax over rows (MU:230 / MU:320)."""
+    atten = _t(atten).float()
+    return torch.softmax(atten, dim=2) * torch.softmax(atten, dim=1)
+
+
+def fg_masks(P):
+    """label>0 masks (MU:231-234 / MU:321-322): argmax over the full row (col) for
+    rows (cols) 1.., foreground iff the first maximum is not at index 0."""
+    lab1 = P[:, 1:, :].max(dim=2)[1]
+    lab2 = P[:, :, 1:].max(dim=1)[1]
+    return (lab1 > 0).float(), (lab2 > 0).float()
+
+
+def coarse_assignment(atten):
+    """MU:230-242.  Returns w1 (B,N1), w2 (B,N2) and the normalised CDF (B,N1*N2) f32."""
+    P = dual_softmax(atten)
+    w1, w2 = fg_masks(P)
+    B = P.shape[0]
+    S = P[:, 1:, 1:].contiguous() * w1.unsqueeze(2) * w2.unsqueeze(1)
+    S = S.reshape(B, -1) ** 1.5
+    cdf = torch.cumsum(S, dim=1)
+    cdf = cdf / (cdf[:, -1].unsqueeze(1).contiguous() + 1e-8)
+    return {"w1": w1, "w2": w2, "score": S, "cdf": cdf}
+
+
+def inverse_cdf(cdf, rand, faithful=False):
+    """First index i with cdf[i] >= r, and 0 when there is none (MU:277-305).
+
+    faithful=True materialises the (B,S,N) comparison exactly like the reference
+    (used for the CPU baseline timing); the default is the equivalent
+    lower-bound search (cdf is non-decreasing), patched for the "none" case.
+    """
+    cdf, rand = _t(cdf), _t(rand)
+    if faithful:
+        return torch.argmax((cdf.unsqueeze(1) >= rand.unsqueeze(2)).float(), dim=2)
+    idx = torch.searchsorted(cdf.contiguous(), rand.contiguous(), right=False)
+    return torch.where(idx >= cdf.shape[1], torch.zeros_like(idx), idx)
+
+
+def procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5):
+    """Weighted Kabsch, ref ~ R src + t.  MU:343-436."""
+    src, ref = _t(src).float(), _t(ref).float()
+    n = src.shape[0]
+    w = torch.ones_like(src[:, :, 0]) if weights is None else _t(weights).float()
+    w = torch.where(w < weight_thresh, torch.zeros_like(w), w)
+    w = (w / (w.sum(dim=1, keepdim=True) + eps)).unsqueeze(2)
+    cs = (src * w).sum(dim=1, keepdim=True)
+    cr = (ref * w).sum(dim=1, keepdim=True)
+    H = (src - cs).permute(0, 2, 1) @ (w * (ref - cr))
+    U, _, V = torch.svd(H)
+    Ut = U.transpose(1, 2)
+    D = torch.eye(3).unsqueeze(0).repeat(n, 1, 1)
+    D[:, 2, 2] = torch.sign(torch.det(V @ Ut))
+    R = V @ D @ Ut
+    t = (cr.permute(0, 2, 1) - R @ cs.permute(0, 2, 1)).squeeze(2)
+    return R, t, H
+
+
+def coarse_hypotheses(cdf, rand, pts1, pts2, n_proposal1, faithful=False):
+    """MU:248-261: draw 3*P1 correspondences, solve P1 three-point Procrustes, residual."""
+    pts1, pts2 = _t(pts1).float(), _t(pts2).float()
+    B, N1, _ = pts1.shape
+    N2 = pts2.shape[1]
+    idx = inverse_cdf(cdf, rand, faithful)
+    i1 = torch.clamp(idx.div(N2, rounding_mode="floor"), max=N1 - 1)
+    i2 = torch.clamp(idx % N2, max=N2 - 1)
+    p1 = torch.gather(pts1, 1, i1.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n_proposal1, 3, 3)
+    p2 = torch.gather(pts2, 1, i2.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n_proposal1, 3, 3)
+    R, t, H = procrustes(p2, p1, None, weight_thresh=0.5)
+    R = R.reshape(B, n_proposal1, 3, 3)
+    t = t.reshape(B, n_proposal1, 1, 3)
+    p1 = p1.reshape(B, n_proposal1, 3, 3)
+    p2 = p2.reshape(B, n_proposal1, 3, 3)
+    resid = torch.norm((p1 - t) @ R - p2, dim=3).mean(2)
+    return {"idx": idx, "i1": i1, "i2": i2, "R": R, "t": t.squeeze(2), "resid": resid,
+            "H": H.reshape(B, n_proposal1, 3, 3)}
+
+
+def score_hypotheses(R, t, pts1, w1, model_pts):
+    """MU:267-271: score = sum(w1) / (sum_i w1_i * min_m ||(p1_i - t) R - m|| + 1e-8).
+
+    R (B,H,3,3), t (B,H,3), pts1 (B,N1,3), w1 (B,N1), model_pts (B,Nm,3) -> (B,H).
+    Chunked over H so large sweeps fit in memory.
+    """
+    R, t = _t(R).float(), _t(t).float()
+    pts1, w1, model_pts = _t(pts1).float(), _t(w1).float(), _t(model_pts).float()
+    B, Hn = R.shape[:2]
+    out = torch.empty(B, Hn)
+    step = 256
+    for h0 in range(0, Hn, step):
+        Rc, tc = R[:, h0:h0 + step], t[:, h0:h0 + step]
+        tp = (pts1.unsqueeze(1) - tc.unsqueeze(2)) @ Rc            # (B,h,N1,3)
+        h = tp.shape[1]
+        tp = tp.reshape(B * h, -1, 3)
+        mp = model_pts.unsqueeze(1).repeat(1, h, 1, 1).reshape(B * h, -1, 3)
+        dis = torch.sqrt(sq_pairwise(tp, mp)).min(2)[0].reshape(B, h, -1)
+        out[:, h0:h0 + step] = w1.unsqueeze(1).sum(2) / ((dis * w1.unsqueeze(1)).sum(2) + 1e-8)
+    return out
+
+
+def coarse_Rt(atten, pts1, pts2, model_pts, n_proposal1, n_proposal2, rand, faithful=False):
+    """compute_coarse_Rt (MU:204-275) with the random draw made explicit.
+
+    Returns (R (B,3,3), t (B,3), stages) where ``stages`` holds every intermediate
+    of the parity plan plus ``proposal_id`` = original index (in [0,P1)) of the
+    selected hypothesis.
+    """
+    pts1, pts2 = _t(pts1).float(), _t(pts2).float()
+    model_pts = pts2 if model_pts is None else _t(model_pts).float()
+    B = pts1.shape[0]
+    a = coarse_assignment(atten)
+    h = coarse_hypotheses(a["cdf"], rand, pts1, pts2, n_proposal1, faithful)
+    top = torch.topk(h["resid"], n_proposal2, dim=1, largest=False)[1]
+    Rs = torch.gather(h["R"], 1, top.reshape(B, -1, 1, 1).repeat(1, 1, 3, 3))
+    ts = torch.gather(h["t"], 1, top.reshape(B, -1, 1).repeat(1, 1, 3))
+    scores = score_hypotheses(Rs, ts, pts1, a["w1"], model_pts)
+    best = scores.max(1)[1]
+    ar = torch.arange(B)
+    stages = dict(a)
+    stages.update(h)
+    stages.update({"top": top, "scores": scores, "best": best, "proposal_id": top[ar, best]})
+    return Rs[ar, best], ts[ar, best], stages
+
+
+def fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15):
+    """compute_fine_Rt (MU:308-341).  Returns R, t, pose_score, stages."""
+    pts1, pts2 = _t(pts1).float(), _t(pts2).float()
+    model_pts = pts2 if model_pts is None else _t(model_pts).float()
+    P = dual_softmax(atten)
+    w1, w2 = fg_masks(P)
+    A = P[:, 1:, 1:] * w1.unsqueeze(2) * w2.unsqueeze(1)
+    row = A.sum(2)
+    pred = (A / (A.sum(2, keepdim=True) + 1e-6)) @ pts2
+    R, t, H = procrustes(pred, pts1, row, weight_thresh=0.0)
+    moved = (pts1 - t.unsqueeze(1)) @ R
+    dis = torch.sqrt(sq_pairwise(moved, model_pts)).min(2)[0]
+    hit = (dis < dis_thres).float()
+    score = (hit * w1).sum(1) / (w1.sum(1) + 1e-8)
+    score = score * w1.mean(1)
+    return R, t, score, {"w1": w1, "w2": w2, "row": row, "pred": pred, "H": H, "dis": dis}
+
+
+# --------------------------------------------------------------------------
+# comparison helpers shared by tests, smoke() and bench
+# --------------------------------------------------------------------------
+def rotation_angle_deg(Ra, Rb):
+    """Geodesic angle via the chord formula 2*asin(||Ra-Rb||_F / (2*sqrt(2))) in fp64
+    (fp32 acos((tr-1)/2) bottoms out near 0.03 deg)."""
+    Ra = _t(Ra).double()
+    Rb = _t(Rb).double()
+    chord = (Ra - Rb).flatten(-2).norm(dim=-1) / (2.0 * np.sqrt(2.0))
+    return torch.rad2deg(2.0 * torch.asin(chord.clamp(max=1.0)))

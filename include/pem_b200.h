@@ -1,0 +1,200 @@
+/*
+ * pem_b200.h -- C ABI of libpem_b200.so: the SAM-6D Pose-Estimation-Model geometric
+ * hot path as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary ("B3").  Every entry point
+ *   - takes raw DEVICE pointers, explicit sizes and a CUDA stream (passed as void*,
+ *     i.e. a cudaStream_t; NULL = the legacy default stream),
+ *   - enqueues its kernels on that stream and returns WITHOUT synchronising,
+ *   - never allocates: outputs and scratch are caller-owned (see the
+ *     *_workspace_bytes queries),
+ *   - returns 0 on success, a negative PEM_E_* code for an invalid argument, or a
+ *     positive cudaError_t if a launch failed (the reference's CUDA_CHECK_ERRORS
+ *     prints and exit(-1)s instead: _ext_src/include/cuda_utils.h:42-51).
+ *
+ * All floating tensors are contiguous fp32, all index tensors contiguous int32,
+ * exactly as the reference's TORCH_CHECKs demand (_ext_src/include/utils.h:20-35).
+ *
+ * Reference paths below are relative to
+ * /root/reference/SAM-6D/Pose_Estimation_Model/ ; MU = utils/model_utils.py.
+ */
+#ifndef PEM_B200_H
+#define PEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEM_OK 0
+#define PEM_E_NULL (-1)      /* required pointer is NULL            */
+#define PEM_E_SHAPE (-2)     /* a size is <= 0 or out of range      */
+#define PEM_E_UNSUPPORTED (-3)
+#define PEM_E_WORKSPACE (-4) /* workspace missing / too small       */
+
+/* FPS flags */
+#define PEM_FPS_SKIP_NEAR_ORIGIN 1 /* CPU-reference rule: |p|^2 <= 1e-3 never sampled */
+
+typedef void *pem_stream_t; /* cudaStream_t */
+
+/* Library / build identification. */
+int pem_abi_version(void);
+const char *pem_build_info(void);
+const char *pem_status_string(int status);
+
+/* ---------------------------------------------------------------- pointnet2 ops */
+
+/*
+ * Furthest point sampling.  Replaces `furthest_point_sampling`
+ * (model/pointnet2/_ext_src/src/sampling.cpp:184-212; CPU loop :76-118, CUDA kernel
+ * sampling_gpu.cu:75-178).  xyz (B,N,3) -> idx (B,M) int32, idx[:,0] = 0.
+ * Semantics are the reference's CPU loop, bit for bit: unfused fp32 distance
+ * ((dx*dx)+(dy*dy))+(dz*dz), lowest index wins ties, and with
+ * PEM_FPS_SKIP_NEAR_ORIGIN points with |p|^2 <= 1e-3 (compared in double) are
+ * never selected.  flags = 0 drops the near-origin rule (the reference's CUDA variant,
+ * sampling_gpu.cu:106) but keeps lowest-index tie breaking.
+ * workspace: pem_fps_workspace_bytes(B,N) bytes (0 for N <= 16384; may then be NULL).
+ */
+size_t pem_fps_workspace_bytes(int B, int N);
+int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t *idx, void *workspace,
+            size_t workspace_bytes, pem_stream_t stream);
+
+/*
+ * gather_points (sampling.cpp:120-150; CPU loop :23-44; CUDA sampling_gpu.cu:13-35).
+ * feat (B,C,N), idx (B,M) -> out (B,C,M); an index outside [0,N) yields 0.0f (CPU rule).
+ */
+int pem_gather(const float *feat, const int32_t *idx, int B, int C, int N, int M, float *out,
+               pem_stream_t stream);
+
+/*
+ * Row gather for point-major tensors: feat (B,N,C) with row stride `row_stride`
+ * floats and batch stride `batch_stride` floats, idx (B,M) -> out (B,M,C) contiguous.
+ * This is `gather_operation(x.transpose(1,2).contiguous(), idx).transpose(1,2)` of
+ * MU:77-80 and transformer.py:667-671 without the two transposes.
+ */
+int pem_gather_rows(const float *feat, const int32_t *idx, int B, int N, int C, int M,
+                    long long batch_stride, long long row_stride, float *out, pem_stream_t stream);
+
+/*
+ * ball_query (ball_query.cpp:64-94; CPU loop :16-62; CUDA ball_query_gpu.cu:14-59).
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample): the first nsample points in index
+ * order with d2 < radius*radius (fp32, strict); remaining slots repeat the first hit;
+ * a centre with no hit gets zeros.  idx is fully written (no pre-zeroing needed).
+ * nsample <= 128.
+ */
+int pem_ball_query(const float *new_xyz, const float *xyz, int B, int M, int N, float radius,
+                   int nsample, int32_t *idx, pem_stream_t stream);
+
+/*
+ * group_points (group_points.cpp:79-108; CPU loop :20-45; CUDA group_points_gpu.cu:13-44).
+ * feat (B,C,N), idx (B,M,ns) -> out (B,C,M,ns); invalid index -> 0.0f.
+ */
+int pem_group(const float *feat, const int32_t *idx, int B, int C, int N, int M, int ns,
+              float *out, pem_stream_t stream);
+
+/*
+ * Fused QueryAndGroup.forward with use_xyz=True (pointnet2_utils.py:326-403):
+ * ball query, grouping of xyz minus the centre, grouping of `feat`, concatenation.
+ * xyz (B,N,3), new_xyz (B,M,3), feat (B,C,N) or NULL (C=0) -> out (B,3+C,M,ns).
+ * idx_out (B,M,ns) is optional (NULL to skip).  nsample <= 128.
+ */
+int pem_query_and_group(const float *xyz, const float *new_xyz, const float *feat, int B, int N,
+                        int M, int C, float radius, int nsample, float *out, int32_t *idx_out,
+                        pem_stream_t stream);
+
+/* ---------------------------------------------------------------- similarity */
+
+/*
+ * compute_feature_similarity, 'cosine' (MU:131-153):
+ * atten[b,i,j] = <n(f1[b,i]), n(f2[b,j])> / temp, n(x) = x / max(|x|, 1e-12) when
+ * normalize != 0.  f1 (B,N1,C), f2 (B,N2,C) -> atten (B,N1,N2).  fp32 FFMA arithmetic
+ * (exact-precision path; C % 4 == 0, 16-byte aligned inputs).
+ * workspace: pem_similarity_workspace_bytes(B,N1,N2) bytes when normalize != 0.
+ */
+size_t pem_similarity_workspace_bytes(int B, int N1, int N2);
+int pem_feature_similarity(const float *f1, const float *f2, int B, int N1, int N2, int C,
+                           float temp, int normalize, float *atten, void *workspace,
+                           size_t workspace_bytes, pem_stream_t stream);
+
+/* ---------------------------------------------------------------- coarse stage */
+
+/*
+ * Front half of compute_coarse_Rt (MU:230-242): dual softmax, foreground masks,
+ * masked score ** 1.5, fp64 prefix sum rounded to fp32 per element, normalised by
+ * (last + 1e-8).  atten (B,N1+1,N2+1) -> w1 (B,N1), w2 (B,N2), cdf (B,N1*N2).
+ * Requires (N1+1)*(N2+1) <= 50176 (one CTA holds the matrix in shared memory).
+ */
+int pem_coarse_assign(const float *atten, int B, int N1, int N2, float *w1, float *w2, float *cdf,
+                      pem_stream_t stream);
+
+/*
+ * Hypothesis generation (MU:248-261, 277-305, 343-436): for every one of the B*P1
+ * hypotheses draw 3 correspondences by inverse-CDF lookup of rand (first index with
+ * cdf >= r, 0 if none), solve the 3-point Procrustes (weights 1/(3+1e-5)) with a
+ * register-resident 3x3 SVD, and evaluate the 3-point residual.
+ * cdf (B,N1*N2), rand (B,3*P1), pts1 (B,N1,3), pts2 (B,N2,3) ->
+ * R (B,P1,9) row-major, t (B,P1,3), resid (B,P1), corr (B,3*P1) int32 flat
+ * correspondence index i1*N2+i2 (optional, may be NULL).
+ */
+int pem_coarse_hypotheses(const float *cdf, const float *rand, const float *pts1,
+                          const float *pts2, int B, int N1, int N2, int P1, float *R, float *t,
+                          float *resid, int32_t *corr, pem_stream_t stream);
+
+/*
+ * torch.topk(resid, P2, largest=False) as a set (MU:262): the P2 smallest residuals per
+ * instance, ties at the threshold resolved to the lowest proposal id, written in
+ * ascending proposal-id order.  resid (B,P1) -> sel (B,P2) int32.  NaN sorts last.
+ */
+int pem_select_smallest(const float *resid, int B, int P1, int P2, int32_t *sel,
+                        pem_stream_t stream);
+
+/*
+ * Hypothesis scoring (MU:267-271): for each selected hypothesis h transform the N1
+ * observed points, q_i = (p1_i - t_h) R_h, take the distance to the nearest of Nm model
+ * points (expanded form |q|^2 - 2 q.m + |m|^2 clamped at 0, then sqrt) and form
+ * score = sum(w1) / (sum_i w1_i d_i + 1e-8).
+ * R (B,P,9), t (B,P,3); sel (B,H) indices into P, or NULL meaning hypothesis h = h
+ * (then H <= P); pts1 (B,N1,3), w1 (B,N1), model (B,Nm,3) -> scores (B,H).
+ */
+int pem_score_hypotheses(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
+                         const float *pts1, const float *w1, int N1, const float *model, int Nm,
+                         float *scores, pem_stream_t stream);
+
+/*
+ * argmax over scores (MU:272-274), first maximum wins; copies the winner.
+ * -> R_out (B,9), t_out (B,3), proposal_id (B) = sel[b,argmax] (or argmax if sel NULL).
+ */
+int pem_select_best(const float *scores, const int32_t *sel, const float *R, const float *t,
+                    int B, int P, int H, float *R_out, float *t_out, int32_t *proposal_id,
+                    pem_stream_t stream);
+
+/* ---------------------------------------------------------------- fine stage */
+
+/*
+ * compute_fine_Rt (MU:308-341) on a materialised attention matrix.
+ * atten (B,N1+1,N2+1), pts1 (B,N1,3), pts2 (B,N2,3), model (B,Nm,3) ->
+ * R (B,9), t (B,3), score (B).  Optional diagnostics (may be NULL): w1 (B,N1),
+ * w2 (B,N2), rowsum (B,N1), pred (B,N1,3).
+ * workspace: pem_fine_workspace_bytes(B,N1,N2).
+ */
+size_t pem_fine_workspace_bytes(int B, int N1, int N2);
+int pem_fine_Rt(const float *atten, const float *pts1, const float *pts2, const float *model,
+                int B, int N1, int N2, int Nm, float dis_thres, float *R, float *t, float *score,
+                float *w1, float *w2, float *rowsum, float *pred, void *workspace,
+                size_t workspace_bytes, pem_stream_t stream);
+
+/*
+ * Weighted Procrustes (MU:343-436) for B' problems of n points each, one CTA per
+ * problem: src, ref (B',n,3), weights (B',n) or NULL (ones) -> R (B',9), t (B',3).
+ * ref ~ R src + t.
+ */
+int pem_weighted_procrustes(const float *src, const float *ref, const float *weights, int Bp,
+                            int n, float weight_thresh, float eps, float *R, float *t,
+                            pem_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEM_B200_H */

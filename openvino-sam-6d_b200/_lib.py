@@ -1,0 +1,76 @@
+"""ctypes binding of libpem_b200.so (the C ABI declared in include/pem_b200.h).
+
+The library is built in-tree by ``csrc/Makefile`` (``__graft_entry__.build()``).  There is
+no fallback of any kind: if the shared object is missing or a CUDA device is absent the
+ops raise -- the product path never routes through CPU code.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpem_b200.so")
+_lib = None
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_f = ctypes.c_float
+c_ll = ctypes.c_longlong
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/pem_b200.h
+SIGNATURES = {
+    "pem_abi_version": (c_i, []),
+    "pem_build_info": (ctypes.c_char_p, []),
+    "pem_status_string": (ctypes.c_char_p, [c_i]),
+    "pem_fps_workspace_bytes": (c_sz, [c_i, c_i]),
+    "pem_fps": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_sz, c_p]),
+    "pem_gather": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "pem_gather_rows": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_p, c_p]),
+    "pem_ball_query": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
+    "pem_group": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "pem_query_and_group": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p]),
+    "pem_similarity_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
+    "pem_feature_similarity": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_sz, c_p]),
+    "pem_coarse_assign": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "pem_coarse_hypotheses": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "pem_select_smallest": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
+    "pem_score_hypotheses": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p]),
+    "pem_select_best": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "pem_fine_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
+    "pem_fine_Rt": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p,
+                          c_p, c_p, c_p, c_sz, c_p]),
+    "pem_weighted_procrustes": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+}
+
+
+def build(force=False):
+    """Compile libpem_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if force:
+        subprocess.check_call(cmd + ["clean"])
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libpem_b200.so not found at %s: run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU fallback)" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().pem_status_string(int(status)).decode()
+        raise RuntimeError("%s failed: %s (status %d)" % (what, msg, status))

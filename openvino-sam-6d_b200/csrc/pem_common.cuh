@@ -1,0 +1,78 @@
+// Shared device/host helpers for libpem_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "pem_b200.h"
+
+#define PEM_NUM_SMS 148  // B200: 2 dies x 74 SMs
+
+#define PEM_REQUIRE_PTR(p) \
+    do {                   \
+        if ((p) == nullptr) return PEM_E_NULL; \
+    } while (0)
+#define PEM_REQUIRE(cond, code) \
+    do {                        \
+        if (!(cond)) return (code); \
+    } while (0)
+
+// Launch-status check: never synchronises; a sticky earlier error is also reported.
+static inline int pem_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PEM_OK : (int)e;
+}
+
+static inline cudaStream_t pem_cu_stream(pem_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+namespace pem {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// Unfused squared distance in the reference CPU evaluation order
+// ((dx*dx)+(dy*dy))+(dz*dz): nvcc must not contract these into FMAs, otherwise
+// sampled indices / neighbour lists stop being bit-exact.
+__device__ __forceinline__ float sqdist_unfused(float ax, float ay, float az, float bx, float by,
+                                                float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Block-wide sum for blocks of up to 1024 threads; result valid in every thread.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *smem /* >= 32 entries */) {
+    v = warp_sum(v);
+    const int w = warp_id(), l = lane_id(), nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) smem[w] = v;
+    __syncthreads();
+    T r = (l < nw) ? smem[l] : T(0);
+    r = warp_sum(r);
+    return r;
+}
+
+}  // namespace pem

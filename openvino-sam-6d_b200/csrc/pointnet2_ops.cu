@@ -1,0 +1,433 @@
+// pointnet2 ops of the PEM hot path as sm_100a kernels: furthest point sampling,
+// gather, ball query, grouping and the fused QueryAndGroup.
+//
+// Reference semantics (bit-exact targets) -- paths relative to
+// /root/reference/SAM-6D/Pose_Estimation_Model/model/pointnet2/_ext_src/src/ :
+//   FPS         sampling.cpp:76-118 (CPU loop; CUDA twin sampling_gpu.cu:75-178)
+//   gather      sampling.cpp:23-44  (CUDA twin sampling_gpu.cu:13-25)
+//   ball query  ball_query.cpp:16-62 (CUDA twin ball_query_gpu.cu:14-49)
+//   grouping    group_points.cpp:20-45 (CUDA twin group_points_gpu.cu:13-33)
+//   QueryAndGroup  ../pointnet2_utils.py:326-403
+//
+// Design notes (B200):
+//  * FPS is a chain of M-1 dependent argmax steps, so it is latency/issue bound,
+//    not HBM bound.  The cloud is read from HBM exactly once into shared memory
+//    (SoA, conflict-free) and -- up to 8192 points -- into registers together with
+//    the running min-distance; each step is one pass over register data, a
+//    redux.sync warp argmax, ONE __syncthreads (double-buffered per-warp keys) and
+//    a redundant per-warp final reduce.  Ties resolve to the lowest index by
+//    reducing the pair (distance bits, ~index) as an unsigned maximum.
+//  * Ball query is order dependent (first nsample hits in index order), so each
+//    thread owns one centre and scans the points in order from a shared-memory
+//    tile (one LDS.128 broadcast per point per warp); neighbour rows are staged in
+//    shared memory and written coalesced.  The fused QueryAndGroup consumes the
+//    staged rows directly and writes the (B,3+C,M,ns) tensor once.
+#include "pem_common.cuh"
+
+namespace pem {
+
+// ------------------------------------------------------------------------------------
+// FPS
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool near_origin(float x, float y, float z) {
+    // sampling.cpp:101-103: float mag compared with the double literal 1e-3
+    const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    return (double)mag <= 1e-3;
+}
+
+// argmax of (value, lowest index) over the CTA; returns the winning index (0 if no
+// thread has a valid candidate).  hi = float bits of a non-negative value (0 when
+// invalid), lo = ~index (0 when invalid).
+template <int THREADS>
+__device__ __forceinline__ int cta_argmax(unsigned hi, unsigned lo, unsigned long long *s_key) {
+    constexpr int NW = THREADS / 32;
+    const unsigned whi = __reduce_max_sync(kFull, hi);
+    const unsigned wlo = __reduce_max_sync(kFull, hi == whi ? lo : 0u);
+    if (NW == 1) return wlo ? (int)~wlo : 0;
+    if (lane_id() == 0) s_key[warp_id()] = ((unsigned long long)whi << 32) | wlo;
+    __syncthreads();
+    const unsigned long long key = lane_id() < NW ? s_key[lane_id()] : 0ull;
+    const unsigned h2 = (unsigned)(key >> 32), l2 = (unsigned)key;
+    const unsigned ghi = __reduce_max_sync(kFull, h2);
+    const unsigned glo = __reduce_max_sync(kFull, h2 == ghi ? l2 : 0u);
+    return glo ? (int)~glo : 0;
+}
+
+// One CTA per cloud, N <= THREADS*PPT.  IN_REGS: coordinates live in registers;
+// otherwise they are re-read from the SoA shared-memory copy every step.
+template <int THREADS, int PPT, bool IN_REGS>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_cta_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *__restrict__ idx) {
+    extern __shared__ float s_soa[];  // x[N] | y[N] | z[N]
+    __shared__ unsigned long long s_key[2][32];
+    float *sx = s_soa, *sy = s_soa + N, *sz = s_soa + 2 * N;
+    const int tid = threadIdx.x;
+    const float *src = xyz + (size_t)blockIdx.x * N * 3;
+    int32_t *out = idx + (size_t)blockIdx.x * M;
+
+    for (int e = tid; e < 3 * N; e += THREADS) {
+        const int k = e / 3, c = e - 3 * k;
+        s_soa[c * N + k] = src[e];
+    }
+    __syncthreads();
+
+    float px[IN_REGS ? PPT : 1], py[IN_REGS ? PPT : 1], pz[IN_REGS ? PPT : 1];
+    float run[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = i * THREADS + tid;
+        bool ok = k < N;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (ok) {
+            x = sx[k]; y = sy[k]; z = sz[k];
+            if (skip && near_origin(x, y, z)) ok = false;
+        }
+        if (IN_REGS) { px[i] = x; py[i] = y; pz[i] = z; }
+        // -inf marks "never selectable": fminf(d, -inf) stays -inf and -inf > best is false
+        run[i] = ok ? FLT_MAX : -INFINITY;
+    }
+
+    int cur = 0;
+    if (tid == 0) out[0] = 0;
+    for (int j = 1; j < M; ++j) {
+        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        float best = -FLT_MAX;
+        int arg = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = i * THREADS + tid;
+            float x, y, z;
+            if (IN_REGS) { x = px[i]; y = py[i]; z = pz[i]; }
+            else if (k < N) { x = sx[k]; y = sy[k]; z = sz[k]; }
+            else { x = y = z = 0.f; }
+            const float d = sqdist_unfused(x, y, z, cx, cy, cz);
+            const float m = fminf(d, run[i]);
+            run[i] = m;
+            if (m > best) { best = m; arg = k; }  // ascending k + strict > : lowest index wins
+        }
+        const bool valid = best > -FLT_MAX;
+        cur = cta_argmax<THREADS>(valid ? __float_as_uint(best) : 0u, valid ? ~(unsigned)arg : 0u,
+                                  s_key[j & 1]);
+        if (tid == 0) out[j] = cur;
+    }
+}
+
+// Fallback for clouds that do not fit one SM: coordinates from L2, running distance in
+// a caller-provided workspace (B*N floats).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_stream_kernel(const float *__restrict__ xyz, int N, int M, int skip, float *__restrict__ run,
+                  int32_t *__restrict__ idx) {
+    __shared__ unsigned long long s_key[2][32];
+    const int tid = threadIdx.x;
+    const float *src = xyz + (size_t)blockIdx.x * N * 3;
+    float *r = run + (size_t)blockIdx.x * N;
+    int32_t *out = idx + (size_t)blockIdx.x * M;
+    for (int k = tid; k < N; k += THREADS) {
+        const bool bad = skip && near_origin(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+        r[k] = bad ? -INFINITY : FLT_MAX;
+    }
+    int cur = 0;
+    if (tid == 0) out[0] = 0;
+    for (int j = 1; j < M; ++j) {
+        const float cx = __ldg(src + 3 * cur), cy = __ldg(src + 3 * cur + 1),
+                    cz = __ldg(src + 3 * cur + 2);
+        float best = -FLT_MAX;
+        int arg = 0;
+        for (int k = tid; k < N; k += THREADS) {
+            const float d = sqdist_unfused(__ldg(src + 3 * k), __ldg(src + 3 * k + 1),
+                                           __ldg(src + 3 * k + 2), cx, cy, cz);
+            const float m = fminf(d, r[k]);
+            r[k] = m;
+            if (m > best) { best = m; arg = k; }
+        }
+        const bool valid = best > -FLT_MAX;
+        cur = cta_argmax<THREADS>(valid ? __float_as_uint(best) : 0u, valid ? ~(unsigned)arg : 0u,
+                                  s_key[j & 1]);
+        if (tid == 0) out[j] = cur;
+    }
+}
+
+template <int THREADS, int PPT, bool IN_REGS>
+static int launch_fps_cta(const float *xyz, int B, int N, int M, int skip, int32_t *idx,
+                          cudaStream_t st) {
+    const size_t smem = (size_t)3 * N * sizeof(float);
+    auto kern = fps_cta_kernel<THREADS, PPT, IN_REGS>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<B, THREADS, smem, st>>>(xyz, N, M, skip, idx);
+    return pem_launch_status();
+}
+
+// ------------------------------------------------------------------------------------
+// gather / group
+// ------------------------------------------------------------------------------------
+// One warp per (b,c) channel row; lanes sweep the M samples (coalesced idx reads and
+// output writes, random 4-byte reads inside one N-float row that stays in L1/L2).
+__global__ void __launch_bounds__(256)
+gather_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int BC, int C, int N,
+              int M, float *__restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (row >= BC) return;
+    const int b = row / C;
+    const float *src = feat + (size_t)row * N;
+    const int32_t *ib = idx + (size_t)b * M;
+    float *dst = out + (size_t)row * M;
+    for (int j = lane_id(); j < M; j += 32) {
+        const int a = __ldg(ib + j);
+        dst[j] = (a >= 0 && a < N) ? __ldg(src + a) : 0.0f;
+    }
+}
+
+// Row gather on point-major data: one warp copies one C-float row.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int BM, int N,
+                   int C, int M, long long batch_stride, long long row_stride,
+                   float *__restrict__ out, int vec4) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (row >= BM) return;
+    const int b = row / M;
+    const int a = __ldg(idx + row);
+    const bool ok = a >= 0 && a < N;
+    const float *src = feat + (size_t)b * batch_stride + (size_t)(ok ? a : 0) * row_stride;
+    float *dst = out + (size_t)row * C;
+    if (vec4) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        for (int c = lane_id(); c < (C >> 2); c += 32)
+            d4[c] = ok ? __ldg(s4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (int c = lane_id(); c < C; c += 32) dst[c] = ok ? __ldg(src + c) : 0.0f;
+    }
+}
+
+// out[b,c,e] = feat[b,c,idx[b,e]] over the flattened e = j*ns + k.
+__global__ void __launch_bounds__(256)
+group_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int C, int N,
+             long long E, float *__restrict__ out) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const float *src = feat + ((size_t)b * C + c) * N;
+    const int32_t *ib = idx + (size_t)b * E;
+    float *dst = out + ((size_t)b * C + c) * E;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int a = __ldg(ib + e);
+        dst[e] = (a >= 0 && a < N) ? __ldg(src + a) : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// ball query / fused QueryAndGroup
+// ------------------------------------------------------------------------------------
+constexpr int kBqCentres = 128;  // centres (= threads) per CTA
+constexpr int kBqTile = 1024;    // points per shared-memory tile (float4 each)
+
+// Fills s_rows[tid*(ns+1) + l], l in [0,ns), with the neighbour list of centre j0+tid.
+__device__ __forceinline__ void ball_query_rows(const float *__restrict__ centres_b,
+                                                const float *__restrict__ xyz_b, int M, int N,
+                                                float r2, int ns, int j0, float4 *s_pts,
+                                                int *s_rows) {
+    const int tid = threadIdx.x, j = j0 + tid;
+    const bool active = j < M;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) { qx = centres_b[3 * j]; qy = centres_b[3 * j + 1]; qz = centres_b[3 * j + 2]; }
+    int cnt = active ? 0 : ns;
+    int first = 0;
+    int *row = s_rows + tid * (ns + 1);
+    for (int base = 0; base < N; base += kBqTile) {
+        if (__syncthreads_and(cnt >= ns)) break;  // also protects the tile from being overwritten
+        const int nt = min(kBqTile, N - base);
+        for (int k = tid; k < nt; k += kBqCentres) {
+            const float *p = xyz_b + 3 * (size_t)(base + k);
+            s_pts[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        }
+        __syncthreads();
+        if (__all_sync(kFull, cnt >= ns)) continue;
+        int k = 0;
+        for (; k + 4 <= nt && cnt < ns; k += 4) {
+            float d2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 p = s_pts[k + u];
+                d2[u] = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (d2[u] < r2 && cnt < ns) {
+                    if (cnt == 0) first = base + k + u;
+                    row[cnt++] = base + k + u;
+                }
+            }
+        }
+        for (; k < nt && cnt < ns; ++k) {
+            const float4 p = s_pts[k];
+            if (sqdist_unfused(qx, qy, qz, p.x, p.y, p.z) < r2) {
+                if (cnt == 0) first = base + k;
+                row[cnt++] = base + k;
+            }
+        }
+    }
+    if (active)
+        for (int l = cnt; l < ns; ++l) row[l] = first;  // back-fill; no hit -> zeros
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBqCentres)
+ball_query_kernel(const float *__restrict__ centres, const float *__restrict__ xyz, int M, int N,
+                  float r2, int ns, int32_t *__restrict__ idx) {
+    extern __shared__ float4 s_dyn[];
+    float4 *s_pts = s_dyn;
+    int *s_rows = reinterpret_cast<int *>(s_dyn + kBqTile);
+    const int b = blockIdx.y, j0 = blockIdx.x * kBqCentres;
+    ball_query_rows(centres + (size_t)b * M * 3, xyz + (size_t)b * N * 3, M, N, r2, ns, j0, s_pts,
+                    s_rows);
+    const int rows = min(kBqCentres, M - j0);
+    int32_t *dst = idx + ((size_t)b * M + j0) * ns;
+    for (int e = threadIdx.x; e < rows * ns; e += kBqCentres) {
+        const int jj = e / ns, l = e - jj * ns;
+        dst[e] = s_rows[jj * (ns + 1) + l];
+    }
+}
+
+__global__ void __launch_bounds__(kBqCentres)
+query_and_group_kernel(const float *__restrict__ xyz, const float *__restrict__ centres,
+                       const float *__restrict__ feat, int N, int M, int C, float r2, int ns,
+                       float *__restrict__ out, int32_t *__restrict__ idx_out) {
+    extern __shared__ float4 s_dyn[];
+    float4 *s_pts = s_dyn;
+    int *s_rows = reinterpret_cast<int *>(s_dyn + kBqTile);
+    const int b = blockIdx.y, j0 = blockIdx.x * kBqCentres;
+    const float *xyz_b = xyz + (size_t)b * N * 3;
+    const float *cen_b = centres + (size_t)b * M * 3;
+    ball_query_rows(cen_b, xyz_b, M, N, r2, ns, j0, s_pts, s_rows);
+    const int rows = min(kBqCentres, M - j0);
+    const int CT = 3 + C;
+    const size_t plane = (size_t)M * ns;
+    float *out_b = out + (size_t)b * CT * plane + (size_t)j0 * ns;
+    for (int e = threadIdx.x; e < rows * ns; e += kBqCentres) {
+        const int jj = e / ns, l = e - jj * ns;
+        const int a = s_rows[jj * (ns + 1) + l];
+        if (idx_out) idx_out[((size_t)b * M + j0) * ns + e] = a;
+        const float *p = xyz_b + 3 * (size_t)a;
+        const float *q = cen_b + 3 * (size_t)(j0 + jj);
+        // grouped_xyz -= new_xyz (pointnet2_utils.py:376): plain fp32 subtraction
+        out_b[e] = __fsub_rn(__ldg(p), __ldg(q));
+        out_b[plane + e] = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+        out_b[2 * plane + e] = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+        for (int c = 0; c < C; ++c)
+            out_b[(size_t)(3 + c) * plane + e] = __ldg(feat + ((size_t)b * C + c) * N + a);
+    }
+}
+
+static size_t bq_smem_bytes(int ns) {
+    return (size_t)kBqTile * sizeof(float4) + (size_t)kBqCentres * (ns + 1) * sizeof(int);
+}
+
+}  // namespace pem
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+using namespace pem;
+
+extern "C" size_t pem_fps_workspace_bytes(int B, int N) {
+    if (B <= 0 || N <= 16384) return 0;
+    return (size_t)B * N * sizeof(float);
+}
+
+extern "C" int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t *idx,
+                       void *workspace, size_t workspace_bytes, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(idx);
+    PEM_REQUIRE(B > 0 && N > 0 && M > 0, PEM_E_SHAPE);
+    cudaStream_t st = pem_cu_stream(stream);
+    const int skip = (flags & PEM_FPS_SKIP_NEAR_ORIGIN) ? 1 : 0;
+    if (N <= 1024) return launch_fps_cta<128, 8, true>(xyz, B, N, M, skip, idx, st);
+    if (N <= 2048) return launch_fps_cta<256, 8, true>(xyz, B, N, M, skip, idx, st);
+    if (N <= 4096) return launch_fps_cta<512, 8, true>(xyz, B, N, M, skip, idx, st);
+    if (N <= 8192) return launch_fps_cta<1024, 8, true>(xyz, B, N, M, skip, idx, st);
+    if (N <= 16384) return launch_fps_cta<1024, 16, false>(xyz, B, N, M, skip, idx, st);
+    PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fps_workspace_bytes(B, N),
+                PEM_E_WORKSPACE);
+    fps_stream_kernel<1024><<<B, 1024, 0, st>>>(xyz, N, M, skip, (float *)workspace, idx);
+    return pem_launch_status();
+}
+
+extern "C" int pem_gather(const float *feat, const int32_t *idx, int B, int C, int N, int M,
+                          float *out, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(feat);
+    PEM_REQUIRE_PTR(idx);
+    PEM_REQUIRE_PTR(out);
+    PEM_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0, PEM_E_SHAPE);
+    const int rows = B * C;
+    gather_kernel<<<(rows + 7) / 8, 256, 0, pem_cu_stream(stream)>>>(feat, idx, rows, C, N, M, out);
+    return pem_launch_status();
+}
+
+extern "C" int pem_gather_rows(const float *feat, const int32_t *idx, int B, int N, int C, int M,
+                               long long batch_stride, long long row_stride, float *out,
+                               pem_stream_t stream) {
+    PEM_REQUIRE_PTR(feat);
+    PEM_REQUIRE_PTR(idx);
+    PEM_REQUIRE_PTR(out);
+    PEM_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && row_stride >= C, PEM_E_SHAPE);
+    const int rows = B * M;
+    const int vec4 = (C % 4 == 0) && (row_stride % 4 == 0) && (batch_stride % 4 == 0) &&
+                     ((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    gather_rows_kernel<<<(rows + 7) / 8, 256, 0, pem_cu_stream(stream)>>>(
+        feat, idx, rows, N, C, M, batch_stride, row_stride, out, vec4);
+    return pem_launch_status();
+}
+
+extern "C" int pem_group(const float *feat, const int32_t *idx, int B, int C, int N, int M, int ns,
+                         float *out, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(feat);
+    PEM_REQUIRE_PTR(idx);
+    PEM_REQUIRE_PTR(out);
+    PEM_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && ns > 0 && C <= 65535 && B <= 65535,
+                PEM_E_SHAPE);
+    const long long E = (long long)M * ns;
+    const int gx = (int)((E + 1023) / 1024);  // 4 elements per thread
+    group_kernel<<<dim3(gx, C, B), 256, 0, pem_cu_stream(stream)>>>(feat, idx, C, N, E, out);
+    return pem_launch_status();
+}
+
+extern "C" int pem_ball_query(const float *new_xyz, const float *xyz, int B, int M, int N,
+                              float radius, int nsample, int32_t *idx, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(new_xyz);
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(idx);
+    PEM_REQUIRE(B > 0 && M > 0 && N > 0 && nsample > 0 && B <= 65535, PEM_E_SHAPE);
+    PEM_REQUIRE(nsample <= 128, PEM_E_UNSUPPORTED);
+    const size_t smem = bq_smem_bytes(nsample);
+    cudaError_t e = cudaFuncSetAttribute(ball_query_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const float r2 = radius * radius;  // fp32 product, as ball_query.cpp:20
+    ball_query_kernel<<<dim3((M + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
+                        pem_cu_stream(stream)>>>(new_xyz, xyz, M, N, r2, nsample, idx);
+    return pem_launch_status();
+}
+
+extern "C" int pem_query_and_group(const float *xyz, const float *new_xyz, const float *feat, int B,
+                                   int N, int M, int C, float radius, int nsample, float *out,
+                                   int32_t *idx_out, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(new_xyz);
+    PEM_REQUIRE_PTR(out);
+    PEM_REQUIRE(B > 0 && M > 0 && N > 0 && nsample > 0 && C >= 0 && B <= 65535, PEM_E_SHAPE);
+    PEM_REQUIRE(C == 0 || feat != nullptr, PEM_E_NULL);
+    PEM_REQUIRE(nsample <= 128, PEM_E_UNSUPPORTED);
+    const size_t smem = bq_smem_bytes(nsample);
+    cudaError_t e = cudaFuncSetAttribute(query_and_group_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const float r2 = radius * radius;
+    query_and_group_kernel<<<dim3((M + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
+                             pem_cu_stream(stream)>>>(xyz, new_xyz, feat, N, M, C, r2, nsample,
+                                                      out, idx_out);
+    return pem_launch_status();
+}

@@ -1,0 +1,30 @@
+"""Make the reference's own Python call sites run on libpem_b200.
+
+``install_pointnet2_ext()`` registers this package's ``pointnet2_ext`` module as
+``pointnet2._ext`` in ``sys.modules``: the reference's ``pointnet2_utils.py`` does
+``import pointnet2._ext as _ext`` (pointnet2_utils.py:25-33) and then runs unmodified.
+``patch_model_utils(mu)`` swaps the four geometric functions of an already imported reference
+``utils/model_utils.py`` module for the accelerated ones (same signatures).
+"""
+import sys
+import types
+
+
+def install_pointnet2_ext():
+    from . import pointnet2_ext
+    pkg = sys.modules.get("pointnet2")
+    if pkg is None:
+        pkg = types.ModuleType("pointnet2")
+        pkg.__path__ = []
+        sys.modules["pointnet2"] = pkg
+    pkg._ext = pointnet2_ext
+    sys.modules["pointnet2._ext"] = pointnet2_ext
+    return pointnet2_ext
+
+
+def patch_model_utils(mu):
+    from . import model_utils as fast
+    for name in ("sample_pts_feats", "compute_feature_similarity", "compute_coarse_Rt",
+                 "compute_fine_Rt", "weighted_procrustes", "WeightedProcrustes"):
+        setattr(mu, name, getattr(fast, name))
+    return mu

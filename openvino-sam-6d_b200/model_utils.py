@@ -1,0 +1,191 @@
+"""Host-side mirror of the geometric functions of the reference's ``utils/model_utils.py``
+(MU): same names, argument meaning and return values, backed by libpem_b200 kernels.
+
+  sample_pts_feats(pts, feats, npoint, return_index)              MU:70-84
+  compute_feature_similarity(feat1, feat2, type, temp, normalize) MU:131-153
+  compute_coarse_Rt(atten, pts1, pts2, model_pts, n1, n2)         MU:204-275
+  compute_fine_Rt(atten, pts1, pts2, model_pts, dis_thres)        MU:308-341
+  weighted_procrustes / WeightedProcrustes                        MU:343-455
+
+Differences a caller can see, all deliberate:
+  * the random draw of compute_coarse_Rt (``torch.rand`` inside MU:293) can be passed in
+    (``rand=``) so that two implementations consume identical values; when omitted it is
+    drawn with ``torch.rand`` on the tensors' device, as the reference does;
+  * ``return_stages=True`` additionally returns the intermediates the parity plan checks;
+  * CUDA tensors only.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import pointnet2_ext as _ext
+from .pointnet2_utils import furthest_point_sample, gather_rows
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be a float tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (libpem_b200 has no CPU path)" % name)
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
+    """FPS + point/feature gather.  pts (B,N,3), feats (B,N,C) -> (B,npoint,3), (B,npoint,C)
+    [, idx (B,npoint) i32].  The gathers read the point-major tensors directly."""
+    pts = _f32c(pts, "pts")
+    idx = furthest_point_sample(pts, npoint)
+    out_p = gather_rows(pts, idx)
+    out_f = gather_rows(feats, idx)
+    if return_index:
+        return out_p, out_f, idx
+    return out_p, out_f
+
+
+def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True):
+    """(B,N,C),(B,M,C) -> (B,N,M) cosine similarity / temp."""
+    if type != "cosine":
+        raise NotImplementedError("only the 'cosine' similarity of the PEM configs is provided")
+    f1, f2 = _f32c(feat1, "feat1"), _f32c(feat2, "feat2")
+    B, N1, C = f1.shape
+    N2 = f2.shape[1]
+    out = torch.empty((B, N1, N2), dtype=torch.float32, device=f1.device)
+    L = _lib.lib()
+    nbytes = L.pem_similarity_workspace_bytes(B, N1, N2)
+    ws = _ws(nbytes, f1.device)
+    with torch.cuda.device(f1.device):
+        _lib.check(L.pem_feature_similarity(f1.data_ptr(), f2.data_ptr(), B, N1, N2, C, float(temp),
+                                            1 if normalize_feat else 0, out.data_ptr(),
+                                            ws.data_ptr(), nbytes, _ext._stream()),
+                   "pem_feature_similarity")
+    return out
+
+
+def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300,
+                      rand=None, return_stages=False):
+    """atten (B,N1+1,N2+1), pts1 (B,N1,3), pts2 (B,N2,3), model_pts (B,Nm,3) -> R (B,3,3), t (B,3)."""
+    atten, pts1, pts2 = _f32c(atten, "atten"), _f32c(pts1, "pts1"), _f32c(pts2, "pts2")
+    model_pts = pts2 if model_pts is None else _f32c(model_pts, "model_pts")
+    B, N1, _ = pts1.shape
+    N2, Nm = pts2.shape[1], model_pts.shape[1]
+    P1, P2 = int(n_proposal1), int(n_proposal2)
+    dev = pts1.device
+    if rand is None:
+        rand = torch.rand(B, P1 * 3, device=dev)
+    rand = _f32c(rand, "rand")
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    w1, w2 = torch.empty((B, N1), **f32), torch.empty((B, N2), **f32)
+    cdf = torch.empty((B, N1 * N2), **f32)
+    Rh, th = torch.empty((B, P1, 3, 3), **f32), torch.empty((B, P1, 3), **f32)
+    resid = torch.empty((B, P1), **f32)
+    corr = torch.empty((B, P1 * 3), **i32) if return_stages else None
+    sel = torch.empty((B, P2), **i32)
+    scores = torch.empty((B, P2), **f32)
+    R, t = torch.empty((B, 3, 3), **f32), torch.empty((B, 3), **f32)
+    pid = torch.empty((B,), **i32)
+    L, st = _lib.lib(), _ext._stream()
+    with torch.cuda.device(dev):
+        _lib.check(L.pem_coarse_assign(atten.data_ptr(), B, N1, N2, w1.data_ptr(), w2.data_ptr(),
+                                       cdf.data_ptr(), st), "pem_coarse_assign")
+        _lib.check(L.pem_coarse_hypotheses(cdf.data_ptr(), rand.data_ptr(), pts1.data_ptr(),
+                                           pts2.data_ptr(), B, N1, N2, P1, Rh.data_ptr(),
+                                           th.data_ptr(), resid.data_ptr(),
+                                           None if corr is None else corr.data_ptr(), st),
+                   "pem_coarse_hypotheses")
+        _lib.check(L.pem_select_smallest(resid.data_ptr(), B, P1, P2, sel.data_ptr(), st),
+                   "pem_select_smallest")
+        _lib.check(L.pem_score_hypotheses(Rh.data_ptr(), th.data_ptr(), sel.data_ptr(), B, P1, P2,
+                                          pts1.data_ptr(), w1.data_ptr(), N1, model_pts.data_ptr(),
+                                          Nm, scores.data_ptr(), st), "pem_score_hypotheses")
+        _lib.check(L.pem_select_best(scores.data_ptr(), sel.data_ptr(), Rh.data_ptr(),
+                                     th.data_ptr(), B, P1, P2, R.data_ptr(), t.data_ptr(),
+                                     pid.data_ptr(), st), "pem_select_best")
+    if return_stages:
+        return R, t, {"w1": w1, "w2": w2, "cdf": cdf, "corr": corr, "R": Rh, "t": th,
+                      "resid": resid, "sel": sel, "scores": scores, "proposal_id": pid}
+    return R, t
+
+
+def score_hypotheses(R, t, pts1, w1, model_pts, sel=None):
+    """Standalone hypothesis scoring (MU:267-271) for the proposal sweep: R (B,P,3,3),
+    t (B,P,3) -> scores (B,H) with H = P (sel None) or sel.shape[1]."""
+    R, t = _f32c(R, "R"), _f32c(t, "t")
+    pts1, w1, model_pts = _f32c(pts1, "pts1"), _f32c(w1, "w1"), _f32c(model_pts, "model_pts")
+    B, P = R.shape[:2]
+    H = P if sel is None else sel.shape[1]
+    scores = torch.empty((B, H), dtype=torch.float32, device=R.device)
+    with torch.cuda.device(R.device):
+        _lib.check(_lib.lib().pem_score_hypotheses(
+            R.data_ptr(), t.data_ptr(), None if sel is None else sel.data_ptr(), B, P, H,
+            pts1.data_ptr(), w1.data_ptr(), pts1.shape[1], model_pts.data_ptr(),
+            model_pts.shape[1], scores.data_ptr(), _ext._stream()), "pem_score_hypotheses")
+    return scores
+
+
+def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, return_stages=False):
+    """atten (B,N1+1,N2+1), pts1 (B,N1,3), pts2 (B,N2,3) -> R (B,3,3), t (B,3), pose_score (B)."""
+    atten, pts1, pts2 = _f32c(atten, "atten"), _f32c(pts1, "pts1"), _f32c(pts2, "pts2")
+    model_pts = pts2 if model_pts is None else _f32c(model_pts, "model_pts")
+    B, N1, _ = pts1.shape
+    N2, Nm = pts2.shape[1], model_pts.shape[1]
+    dev = pts1.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    R, t, score = torch.empty((B, 3, 3), **f32), torch.empty((B, 3), **f32), torch.empty((B,), **f32)
+    w1 = w2 = row = pred = None
+    if return_stages:
+        w1, w2 = torch.empty((B, N1), **f32), torch.empty((B, N2), **f32)
+        row, pred = torch.empty((B, N1), **f32), torch.empty((B, N1, 3), **f32)
+    L = _lib.lib()
+    nbytes = L.pem_fine_workspace_bytes(B, N1, N2)
+    ws = _ws(nbytes, dev)
+    p = lambda x: None if x is None else x.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(L.pem_fine_Rt(atten.data_ptr(), pts1.data_ptr(), pts2.data_ptr(),
+                                 model_pts.data_ptr(), B, N1, N2, Nm, float(dis_thres),
+                                 R.data_ptr(), t.data_ptr(), score.data_ptr(), p(w1), p(w2),
+                                 p(row), p(pred), ws.data_ptr(), nbytes, _ext._stream()),
+                   "pem_fine_Rt")
+    if return_stages:
+        return R, t, score, {"w1": w1, "w2": w2, "row": row, "pred": pred}
+    return R, t, score
+
+
+def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0, eps=1e-5,
+                        return_transform=False):
+    """MU:343-436: rigid transform with ref ~ R src + t.  (B,n,3) or (n,3) inputs."""
+    squeeze = src_points.ndim == 2
+    if squeeze:
+        src_points, ref_points = src_points.unsqueeze(0), ref_points.unsqueeze(0)
+        weights = None if weights is None else weights.unsqueeze(0)
+    src, ref = _f32c(src_points, "src_points"), _f32c(ref_points, "ref_points")
+    w = None if weights is None else _f32c(weights, "weights")
+    B, n, _ = src.shape
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=src.device)
+    t = torch.empty((B, 3), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().pem_weighted_procrustes(
+            src.data_ptr(), ref.data_ptr(), None if w is None else w.data_ptr(), B, n,
+            float(weight_thresh), float(eps), R.data_ptr(), t.data_ptr(), _ext._stream()),
+            "pem_weighted_procrustes")
+    if return_transform:
+        T = torch.eye(4, device=src.device).repeat(B, 1, 1)
+        T[:, :3, :3], T[:, :3, 3] = R, t
+        return T.squeeze(0) if squeeze else T
+    return (R.squeeze(0), t.squeeze(0)) if squeeze else (R, t)
+
+
+class WeightedProcrustes(nn.Module):
+    """MU:438-455 (default weight_thresh 0.5, like the reference)."""
+
+    def __init__(self, weight_thresh=0.5, eps=1e-5, return_transform=False):
+        super().__init__()
+        self.weight_thresh, self.eps, self.return_transform = weight_thresh, eps, return_transform
+
+    def forward(self, src_points, tgt_points, weights=None):
+        return weighted_procrustes(src_points, tgt_points, weights, self.weight_thresh, self.eps,
+                                   self.return_transform)

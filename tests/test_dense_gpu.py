@@ -1,0 +1,205 @@
+"""GPU parity of the dense geometric stage (similarity, coarse and fine pose) through the
+C ABI vs the CPU oracle, following the staged plan of SURVEY.md section 8c:
+
+  S1  atten -> masks / cdf                      masks equal, cdf abs 2e-6 (values in [0,1])
+  S2  oracle cdf + rand -> correspondences      bit exact
+  S3  same triplets -> per-hypothesis R,t       1e-4 abs on well-conditioned triplets
+  S4  same hypotheses -> scores                 rel 1e-4
+  S5  end to end                                R <= 0.1 deg, t <= 1e-4 (radius units; 0.1 mm
+                                                 for a 1 m radius object), same proposal id
+Floating-point tolerances are stated next to each assert.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _coarse_inputs(pkg, oracle, ids, npoint=196, n_dense=2048, feat_dim=256, P1=6000, n_model=1024):
+    b = pkg.synth.make_batch(ids, n_dense=n_dense, n_model=n_model, feat_dim=feat_dim, n_proposal1=P1)
+    sp, sf, _ = oracle.sample_pts_feats(b["dense_pm"].numpy(), b["dense_fm"].numpy(), npoint)
+    tp, tf, _ = oracle.sample_pts_feats(b["dense_po"].numpy(), b["dense_fo"].numpy(), npoint)
+    sp, sf, tp, tf = (torch.from_numpy(np.ascontiguousarray(x)) for x in (sp, sf, tp, tf))
+    bg = b["bg"][:, None, :]
+    atten = oracle.feature_similarity(torch.cat([bg, sf], 1), torch.cat([bg, tf], 1), 0.1)
+    return b, sp, tp, atten
+
+
+@pytest.mark.parametrize("B,N1,N2,C", [(2, 197, 197, 256), (1, 2049, 2049, 256), (3, 50, 70, 64), (1, 130, 513, 32)])
+def test_similarity(pkg, oracle, dev, B, N1, N2, C):
+    g = torch.Generator().manual_seed(N1)
+    f1, f2 = torch.randn(B, N1, C, generator=g), torch.randn(B, N2, C, generator=g)
+    f1[0, 0] = 0.0  # zero row: F.normalize's eps path
+    want = oracle.feature_similarity(f1, f2, 0.1)
+    got = pkg.model_utils.compute_feature_similarity(f1.to(dev), f2.to(dev), "cosine", 0.1, True).cpu()
+    # logits are in [-10, 10]; fp32 accumulation-order noise only
+    assert (got - want).abs().max().item() < 3e-5
+    raw = pkg.model_utils.compute_feature_similarity(f1.to(dev), f2.to(dev), "cosine", 1.0, False).cpu()
+    ref = torch.bmm(f1, f2.transpose(1, 2))
+    assert (raw - ref).abs().max().item() < 1e-4 * ref.abs().max().item()
+
+
+def test_coarse_assign_S1(pkg, oracle, dev):
+    b, sp, tp, atten = _coarse_inputs(pkg, oracle, [10, 11])
+    want = oracle.coarse_assignment(atten)
+    _, _, st = pkg.model_utils.compute_coarse_Rt(atten.to(dev), sp.to(dev), tp.to(dev), b["model"].to(dev),
+                                                 6000, 300, rand=b["rand"].to(dev), return_stages=True)
+    assert torch.equal(st["w1"].cpu(), want["w1"]) and torch.equal(st["w2"].cpu(), want["w2"])
+    assert 0 < want["w1"].mean() < 1  # the masks are exercised
+    # cdf values are in [0,1]: exp/pow rounding differences only
+    assert (st["cdf"].cpu() - want["cdf"]).abs().max().item() < 2e-6
+    assert (st["cdf"].cpu()[:, 1:] >= st["cdf"].cpu()[:, :-1]).all()
+
+
+def test_coarse_hypotheses_S2_S3(pkg, oracle, dev):
+    b, sp, tp, atten = _coarse_inputs(pkg, oracle, [12])
+    a = oracle.coarse_assignment(atten)
+    want = oracle.coarse_hypotheses(a["cdf"], b["rand"], sp, tp, 6000)
+    L, ext = pkg._lib.lib(), pkg.pointnet2_ext
+    B, P1, N = 1, 6000, 196
+    cdf, rand = a["cdf"].contiguous().to(dev), b["rand"].to(dev)
+    p1, p2 = sp.to(dev), tp.to(dev)
+    R = torch.empty(B, P1, 3, 3, device=dev)
+    t = torch.empty(B, P1, 3, device=dev)
+    resid = torch.empty(B, P1, device=dev)
+    corr = torch.empty(B, P1 * 3, dtype=torch.int32, device=dev)
+    pkg._lib.check(L.pem_coarse_hypotheses(cdf.data_ptr(), rand.data_ptr(), p1.data_ptr(), p2.data_ptr(), B, N, N,
+                                           P1, R.data_ptr(), t.data_ptr(), resid.data_ptr(), corr.data_ptr(),
+                                           ext._stream()), "hyp")
+    # S2: identical cdf + rand -> identical correspondences, bit exact
+    assert torch.equal(corr.cpu().long(), want["idx"])
+    # S3: well-conditioned triplets (sigma2/sigma1 > 1e-2) agree to 1e-4 absolute
+    S = torch.linalg.svdvals(want["H"].double())
+    ok = (S[..., 1] / S[..., 0].clamp_min(1e-30)) > 1e-2
+    assert ok.float().mean() > 0.8
+    dR = (R.cpu() - want["R"]).abs().flatten(2).max(2)[0]
+    dt = (t.cpu() - want["t"]).abs().max(2)[0]
+    assert dR[ok].max().item() < 1e-4 and dt[ok].max().item() < 1e-4
+    assert (resid.cpu() - want["resid"])[ok].abs().max().item() < 1e-5
+    # every returned R is a proper rotation, conditioned or not
+    Rg = R.cpu().double()
+    eye = torch.eye(3, dtype=torch.float64)
+    assert ((Rg @ Rg.transpose(-1, -2)) - eye).abs().max().item() < 1e-5
+    assert (torch.det(Rg) - 1).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("P1,P2", [(6000, 300), (1000, 1000), (777, 1), (60000, 300)])
+def test_select_smallest(pkg, dev, P1, P2):
+    g = torch.Generator().manual_seed(P1)
+    v = torch.rand(3, P1, generator=g)
+    v[0, :50] = 0.0           # ties at the bottom (degenerate triplets have residual exactly 0)
+    v[1, 5] = float("nan")    # NaN sorts last
+    v[2] = torch.round(v[2] * 20) / 20  # heavy ties everywhere
+    sel = torch.empty(3, P2, dtype=torch.int32, device=dev)
+    vd = v.to(dev)
+    pkg._lib.check(pkg._lib.lib().pem_select_smallest(vd.data_ptr(), 3, P1, P2, sel.data_ptr(),
+                                                      pkg.pointnet2_ext._stream()), "select")
+    sel = sel.cpu().long()
+    for b in range(3):
+        s = sel[b]
+        assert len(set(s.tolist())) == P2 and (s[1:] > s[:-1]).all()  # a set, ascending ids
+        vv = torch.nan_to_num(v[b], nan=float("inf"))
+        kth = torch.sort(vv)[0][P2 - 1]
+        assert (vv[s] <= kth).all()                      # nothing above the threshold
+        assert (vv < kth).sum() == (vv[s] < kth).sum()   # everything below it is in
+        ties = torch.nonzero(vv == kth).flatten()
+        chosen = s[vv[s] == kth]
+        assert torch.equal(chosen, ties[: len(chosen)])  # lowest ids among the ties
+
+
+def test_score_hypotheses_S4(pkg, oracle, dev):
+    b, sp, tp, atten = _coarse_inputs(pkg, oracle, [13, 14])
+    a = oracle.coarse_assignment(atten)
+    h = oracle.coarse_hypotheses(a["cdf"], b["rand"], sp, tp, 6000)
+    R, t = h["R"][:, :500].contiguous(), h["t"][:, :500].contiguous()
+    want = oracle.score_hypotheses(R, t, sp, a["w1"], b["model"])
+    got = pkg.model_utils.score_hypotheses(R.to(dev), t.to(dev), sp.to(dev), a["w1"].to(dev), b["model"].to(dev)).cpu()
+    assert ((got - want).abs() / want.abs().clamp_min(1e-6)).max().item() < 1e-4
+    # with a selection list and 2048 model points (the sweep configuration)
+    model2 = pkg.synth.make_batch([13, 14], n_model=2048)["model"]
+    sel = torch.randperm(500)[:77].repeat(2, 1).to(torch.int32)
+    want2 = oracle.score_hypotheses(R[:, sel[0].long()], t[:, sel[0].long()], sp, a["w1"], model2)
+    got2 = pkg.model_utils.score_hypotheses(R.to(dev), t.to(dev), sp.to(dev), a["w1"].to(dev), model2.to(dev),
+                                            sel=sel.to(dev)).cpu()
+    assert ((got2 - want2).abs() / want2.abs().clamp_min(1e-6)).max().item() < 1e-4
+
+
+def test_coarse_end_to_end_S5(pkg, oracle, dev):
+    ids = [20, 21, 22, 23]
+    b, sp, tp, atten = _coarse_inputs(pkg, oracle, ids)
+    oR, ot, ost = oracle.coarse_Rt(atten, sp, tp, b["model"], 6000, 300, b["rand"])
+    R, t, st = pkg.model_utils.compute_coarse_Rt(atten.to(dev), sp.to(dev), tp.to(dev), b["model"].to(dev), 6000,
+                                                 300, rand=b["rand"].to(dev), return_stages=True)
+    same = st["proposal_id"].cpu().long() == ost["proposal_id"]
+    ang = oracle.rotation_angle_deg(R.cpu(), oR)
+    dt = (t.cpu() - ot).abs().max(1)[0]
+    # where the same proposal wins the pose must agree to 0.1 deg / 1e-4; a different winner is
+    # only acceptable when the oracle's own top-2 scores are within 1e-4 relative (near tie)
+    top2 = torch.topk(ost["scores"], 2, dim=1)[0]
+    near_tie = (top2[:, 0] - top2[:, 1]) / top2[:, 0] < 1e-4
+    assert (same | near_tie).all(), (st["proposal_id"].cpu(), ost["proposal_id"])
+    assert ang[same].max().item() < 0.1 and dt[same].max().item() < 1e-4
+    # correspondences drawn from OUR cdf differ from the oracle's only for draws that land
+    # within rounding distance of a bin edge
+    assert (st["corr"].cpu().long() != ost["idx"]).float().mean().item() < 0.02
+
+
+def _fine_case(pkg, oracle, ids, n_dense, feat_dim, n_model=1024):
+    b = pkg.synth.make_batch(ids, n_dense=n_dense, n_model=n_model, feat_dim=feat_dim, n_proposal1=16)
+    bg = b["bg"][:, None, :]
+    atten = oracle.feature_similarity(torch.cat([bg, b["dense_fm"]], 1), torch.cat([bg, b["dense_fo"]], 1), 0.1)
+    return b, atten
+
+
+@pytest.mark.parametrize("ids,n_dense,feat_dim", [([30, 31], 512, 64), ([32], 2048, 256), ([33, 34, 35], 200, 32)])
+def test_fine_Rt(pkg, oracle, dev, ids, n_dense, feat_dim):
+    b, atten = _fine_case(pkg, oracle, ids, n_dense, feat_dim)
+    oR, ot, os_, ost = oracle.fine_Rt(atten, b["dense_pm"], b["dense_po"], b["model"])
+    R, t, s, st = pkg.model_utils.compute_fine_Rt(atten.to(dev), b["dense_pm"].to(dev), b["dense_po"].to(dev),
+                                                  b["model"].to(dev), return_stages=True)
+    # masks: identical except for points whose foreground/background decision is a near tie
+    for k in ("w1", "w2"):
+        assert (st[k].cpu() != ost[k]).float().mean().item() < 2e-3
+    assert 0 < ost["w1"].mean() < 1
+    assert (st["row"].cpu() - ost["row"]).abs().max().item() < 1e-4       # row sums are in [0,1]
+    assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1     # north_star: <= 0.1 deg
+    assert (t.cpu() - ot).abs().max().item() < 1e-4                      # <= 0.1 mm at 1 m radius
+    assert (s.cpu() - os_).abs().max().item() < 2e-3                     # one point of 2048 flips 5e-4
+    # and the planted pose is recovered
+    assert oracle.rotation_angle_deg(R.cpu(), b["gt_R"]).max().item() < 1.0
+
+
+def test_fine_Rt_generic_logits(pkg, oracle, dev):
+    """atten need not come from cosine similarity: large-range logits must not overflow."""
+    g = torch.Generator().manual_seed(3)
+    atten = torch.randn(2, 301, 257, generator=g) * 30.0
+    p1, p2 = torch.randn(2, 300, 3, generator=g) * 0.3, torch.randn(2, 256, 3, generator=g) * 0.3
+    oR, ot, os_, ost = oracle.fine_Rt(atten, p1, p2, None)
+    R, t, s, st = pkg.model_utils.compute_fine_Rt(atten.to(dev), p1.to(dev), p2.to(dev), None, return_stages=True)
+    assert torch.isfinite(R).all() and torch.isfinite(t).all()
+    assert (st["w1"].cpu() != ost["w1"]).float().mean().item() < 5e-3
+    assert (st["row"].cpu() - ost["row"]).abs().max().item() < 1e-4
+    assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1
+    assert (t.cpu() - ot).abs().max().item() < 1e-4
+
+
+def test_weighted_procrustes(pkg, oracle, dev):
+    g = torch.Generator().manual_seed(9)
+    src = torch.randn(5, 400, 3, generator=g)
+    Rg = torch.linalg.qr(torch.randn(5, 3, 3, generator=g))[0]
+    Rg = Rg * torch.sign(torch.det(Rg)).view(-1, 1, 1)
+    ref = src @ Rg.transpose(1, 2) + torch.randn(5, 1, 3, generator=g) + 0.01 * torch.randn(5, 400, 3, generator=g)
+    w = torch.rand(5, 400, generator=g)
+    for thresh, ww in ((0.0, w), (0.5, w), (0.5, None)):
+        oR, ot, _ = oracle.procrustes(src, ref, ww, thresh)
+        R, t = pkg.model_utils.weighted_procrustes(src.to(dev), ref.to(dev), None if ww is None else ww.to(dev), thresh)
+        assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.01
+        assert (t.cpu() - ot).abs().max().item() < 1e-5
+    # reflection case: det-correction must yield a proper rotation
+    refl = src.clone()
+    refl[..., 0] *= -1
+    oR, ot, _ = oracle.procrustes(src, refl, None, 0.0)
+    R, t = pkg.model_utils.weighted_procrustes(src.to(dev), refl.to(dev), None, 0.0)
+    assert (torch.det(R.cpu()) - 1).abs().max().item() < 1e-5
+    assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.05

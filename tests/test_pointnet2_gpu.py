@@ -1,0 +1,141 @@
+"""GPU parity: pointnet2 ops through the C ABI vs the CPU oracle -- BIT EXACT
+(indices and gathered values; SURVEY.md section 8c, stage S0)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(B, N, seed, scale=0.4, dup=0.1, near_origin=3):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(B, N, 3, generator=g) * scale
+    nd = int(dup * N)
+    if nd:
+        dst = torch.randperm(N, generator=g)[:nd]
+        src = torch.randint(0, N, (nd,), generator=g)
+        p[:, dst] = p[:, src]
+    for k in range(min(near_origin, N)):
+        p[:, (7 * k + 3) % N] = 0.01 * torch.randn(3, generator=g)  # |p|^2 <= 1e-3: skipped
+    return p.contiguous()
+
+
+@pytest.mark.parametrize("B,N,M", [
+    (1, 1, 1), (2, 7, 7), (3, 100, 33), (2, 1000, 128), (4, 1024, 200), (3, 1025, 64),
+    (2, 2048, 196), (2, 3000, 300), (2, 4096, 64), (1, 5000, 100), (1, 8192, 50),
+    (2, 9000, 40), (1, 16384, 64), (1, 20000, 32), (2, 5, 9),
+])
+def test_fps_bit_exact(pkg, oracle, dev, B, N, M):
+    p = _cloud(B, N, seed=N + M)
+    want = oracle.fps(p.numpy(), M)
+    got = pkg.pointnet2_ext.furthest_point_sampling(p.to(dev), M)
+    assert got.dtype == torch.int32 and tuple(got.shape) == (B, M)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_cuda_variant_rule(pkg, oracle, dev):
+    """flags=0: the reference CUDA kernel's rule (no near-origin skip), lowest-index ties."""
+    p = _cloud(2, 1500, seed=5)
+    want = oracle.fps(p.numpy(), 77, skip_near_origin=False)
+    got = pkg.pointnet2_ext.furthest_point_sampling(p.to(dev), 77, skip_near_origin=False)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_all_points_identical_or_skipped(pkg, oracle, dev):
+    p = torch.full((1, 64, 3), 0.5)
+    np.testing.assert_array_equal(
+        pkg.pointnet2_ext.furthest_point_sampling(p.to(dev), 8).cpu().numpy(), oracle.fps(p.numpy(), 8))
+    z = torch.zeros((1, 64, 3))  # every point skipped: the CPU loop keeps returning 0
+    np.testing.assert_array_equal(
+        pkg.pointnet2_ext.furthest_point_sampling(z.to(dev), 8).cpu().numpy(), oracle.fps(z.numpy(), 8))
+
+
+def test_fps_default_instances(pkg, oracle, dev):
+    b = pkg.synth.make_batch([3, 4])
+    for key in ("dense_pm", "dense_po"):
+        want = oracle.fps(b[key].numpy(), 196)
+        got = pkg.pointnet2_ext.furthest_point_sampling(b[key].to(dev), 196)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,C,N,M", [(2, 3, 2048, 196), (2, 256, 2049, 196), (16, 128, 256, 64), (1, 5, 17, 40)])
+def test_gather_bit_exact(pkg, oracle, dev, B, C, N, M):
+    g = torch.Generator().manual_seed(C)
+    f = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, M), generator=g, dtype=torch.int32)
+    idx[0, 0] = -1  # invalid indices produce 0.0 (CPU rule)
+    idx[-1, -1] = N
+    want = oracle.gather(f.numpy(), idx.numpy())
+    got = pkg.pointnet2_ext.gather_points(f.to(dev), idx.to(dev))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # point-major row gather == transpose . gather . transpose
+    rows = pkg.pointnet2_utils.gather_rows(f.transpose(1, 2).contiguous().to(dev), idx.to(dev))
+    np.testing.assert_array_equal(rows.cpu().numpy(), want.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("B,M,N,r,ns", [
+    (2, 2048, 2048, 0.1, 32), (2, 2048, 2048, 0.2, 64), (1, 1024, 256, 0.1, 64),
+    (2, 100, 3000, 0.15, 16), (1, 130, 1025, 0.3, 1), (1, 5, 9, 0.5, 128),
+])
+def test_ball_query_bit_exact(pkg, oracle, dev, B, M, N, r, ns):
+    xyz = _cloud(B, N, seed=N + ns, scale=0.35, near_origin=0)
+    if M == N:
+        centres = (xyz + 1e-8).contiguous()  # fine_point_matching.py:117
+    else:
+        centres = _cloud(B, M, seed=M, scale=0.35, near_origin=0)
+    centres[:, -1] = 50.0  # a centre with no neighbour: row of zeros
+    want = oracle.ball_query(centres.numpy(), xyz.numpy(), r, ns)
+    got = pkg.pointnet2_ext.ball_query(centres.to(dev), xyz.to(dev), r, ns)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    assert (want[:, -1] == 0).all()
+
+
+@pytest.mark.parametrize("B,C,N,M,ns", [(2, 3, 2048, 2048, 32), (1, 256, 512, 100, 64), (7, 3, 2048, 64, 32)])
+def test_group_bit_exact(pkg, oracle, dev, B, C, N, M, ns):
+    g = torch.Generator().manual_seed(ns + C)
+    f = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, M, ns), generator=g, dtype=torch.int32)
+    idx[0, 0, 0] = -3
+    want = oracle.group(f.numpy(), idx.numpy())
+    got = pkg.pointnet2_ext.group_points(f.to(dev), idx.to(dev))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("r,ns", [(0.1, 32), (0.2, 64)])
+def test_query_and_group_fused_bit_exact(pkg, oracle, dev, r, ns):
+    b = pkg.synth.make_batch([5])
+    xyz = b["dense_po"]
+    new_xyz = (xyz + 1e-8).contiguous()
+    feat = xyz.transpose(1, 2).contiguous()
+    want, widx = oracle.query_and_group(xyz.numpy(), new_xyz.numpy(), feat.numpy(), r, ns)
+    got, gidx = pkg.pointnet2_utils.query_and_group(xyz.to(dev), new_xyz.to(dev), feat.to(dev), r, ns,
+                                                    return_idx=True)
+    np.testing.assert_array_equal(gidx.cpu().numpy(), widx)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # the unfused composition (module with fused=False) gives the same tensor
+    mod = pkg.pointnet2_utils.QueryAndGroup(r, ns, fused=False)
+    np.testing.assert_array_equal(mod(xyz.to(dev), new_xyz.to(dev), feat.to(dev)).cpu().numpy(), want)
+
+
+def test_sample_pts_feats(pkg, oracle, dev):
+    b = pkg.synth.make_batch([6])
+    p, f, idx = pkg.model_utils.sample_pts_feats(b["dense_pm"].to(dev), b["dense_fm"].to(dev), 196, True)
+    op, of, oidx = oracle.sample_pts_feats(b["dense_pm"].numpy(), b["dense_fm"].numpy(), 196)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oidx)
+    np.testing.assert_array_equal(p.cpu().numpy(), op)
+    np.testing.assert_array_equal(f.cpu().numpy(), of)
+
+
+def test_error_behaviour_matches_reference_checks(pkg, dev):
+    ext = pkg.pointnet2_ext
+    p = torch.randn(2, 64, 3, device=dev)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ext.furthest_point_sampling(p.transpose(1, 2), 4)
+    with pytest.raises(RuntimeError, match="float"):
+        ext.furthest_point_sampling(p.double(), 4)
+    with pytest.raises(RuntimeError, match="int"):
+        ext.gather_points(p.transpose(1, 2).contiguous(), torch.zeros(2, 4, dtype=torch.int64, device=dev))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.furthest_point_sampling(p.cpu(), 4)
+    with pytest.raises(NotImplementedError):
+        ext.three_nn(p, p)

@@ -70,12 +70,23 @@ int pem_gather(const float *feat, const int32_t *idx, int B, int C, int N, int M
 
 /*
  * Row gather for point-major tensors: feat (B,N,C) with row stride `row_stride`
- * floats and batch stride `batch_stride` floats, idx (B,M) -> out (B,M,C) contiguous.
+ * floats and batch stride `batch_stride` floats, idx (B,M) -> out (B,M,C) with rows
+ * contiguous and batch stride `out_batch_stride` floats (lets the caller gather straight
+ * into rows 1.. of a background-token-augmented (B,M+1,C) matrix).
  * This is `gather_operation(x.transpose(1,2).contiguous(), idx).transpose(1,2)` of
  * MU:77-80 and transformer.py:667-671 without the two transposes.
  */
 int pem_gather_rows(const float *feat, const int32_t *idx, int B, int N, int C, int M,
-                    long long batch_stride, long long row_stride, float *out, pem_stream_t stream);
+                    long long batch_stride, long long row_stride, float *out,
+                    long long out_batch_stride /* 0 = M*C */, pem_stream_t stream);
+
+/*
+ * out[b,i,:] = ((pts[b,i,:] - t[b]) @ R[b]) + eps, or pts + eps when R and t are NULL:
+ * `p1_ = (p1 - init_t) @ init_R` (fine_point_matching.py:45) and the `pts + 1e-8` query
+ * centres of PositionalEncoding (fine_point_matching.py:117).  pts (B,N,3), R (B,9), t (B,3).
+ */
+int pem_transform_points(const float *pts, const float *R, const float *t, int B, int N, float eps,
+                         float *out, pem_stream_t stream);
 
 /*
  * ball_query (ball_query.cpp:64-94; CPU loop :16-62; CUDA ball_query_gpu.cu:14-59).

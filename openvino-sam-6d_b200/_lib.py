@@ -26,7 +26,8 @@ SIGNATURES = {
     "pem_fps_workspace_bytes": (c_sz, [c_i, c_i]),
     "pem_fps": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_sz, c_p]),
     "pem_gather": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
-    "pem_gather_rows": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_p, c_p]),
+    "pem_gather_rows": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_p, c_ll, c_p]),
+    "pem_transform_points": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p]),
     "pem_ball_query": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
     "pem_group": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "pem_query_and_group": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p]),

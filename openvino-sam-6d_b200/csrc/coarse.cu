@@ -469,9 +469,8 @@ extern "C" int pem_coarse_assign(const float *atten, int B, int N1, int N2, floa
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0, PEM_E_SHAPE);
     PEM_REQUIRE((long long)(N1 + 1) * (N2 + 1) <= 50176, PEM_E_UNSUPPORTED);
     const size_t smem = coarse_assign_smem(N1, N2);
-    cudaError_t e = cudaFuncSetAttribute(coarse_assign_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(coarse_assign_kernel, smem, &cached)) return rc;
     coarse_assign_kernel<<<B, 1024, smem, pem_cu_stream(stream)>>>(atten, N1, N2, w1, w2, cdf);
     return pem_launch_status();
 }
@@ -516,9 +515,8 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     PEM_REQUIRE(N1 <= kScThreads, PEM_E_UNSUPPORTED);  // kScHyps*N1 <= kScQMax*kScThreads
     const size_t smem = score_smem(N1, Nm);
     PEM_REQUIRE(smem <= 227 * 1024, PEM_E_UNSUPPORTED);
-    cudaError_t e = cudaFuncSetAttribute(score_hypotheses_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel, smem, &cached)) return rc;
     score_hypotheses_kernel<<<dim3((H + kScHyps - 1) / kScHyps, B), kScThreads, smem,
                               pem_cu_stream(stream)>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm,
                                                        scores);

@@ -440,11 +440,8 @@ extern "C" int pem_fine_Rt(const float *atten, const float *pts1, const float *p
     // WSVD(pred_pts, pts1, assignment_score) with weight_thresh = 0.0 (MU:319,331)
     weighted_procrustes_kernel<<<B, 256, 0, st>>>(pred, pts1, rsA, N1, 0.0f, 1e-5f, R, t);
     const size_t smem = (size_t)Nm * sizeof(float4);
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(fine_pose_score_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static size_t cached = 40 * 1024;
+    if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
     fine_pose_score_kernel<<<dim3((N1 + kPsThreads - 1) / kPsThreads, B), kPsThreads, smem, st>>>(
         pts1, w1, R, t, model, N1, Nm, dis_thres, w.counters, score);
     return pem_launch_status();

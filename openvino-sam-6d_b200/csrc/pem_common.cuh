@@ -23,6 +23,20 @@ static inline int pem_launch_status() {
     return e == cudaSuccess ? PEM_OK : (int)e;
 }
 
+// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is raised only when a
+// larger size than ever before is requested (cached per call site), so steady-state calls --
+// including calls made while the stream is being captured into a CUDA graph -- issue no
+// runtime API call here.
+template <typename Kern>
+static inline int pem_ensure_dyn_smem(Kern kern, size_t bytes, size_t *cached) {
+    if (bytes <= *cached) return PEM_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    *cached = bytes;
+    return PEM_OK;
+}
+
 static inline cudaStream_t pem_cu_stream(pem_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 namespace pem {

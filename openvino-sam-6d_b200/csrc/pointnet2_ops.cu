@@ -153,11 +153,8 @@ static int launch_fps_cta(const float *xyz, int B, int N, int M, int skip, int32
                           cudaStream_t st) {
     const size_t smem = (size_t)3 * N * sizeof(float);
     auto kern = fps_cta_kernel<THREADS, PPT, IN_REGS>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static size_t cached = 40 * 1024;  // static shared memory counts against the 48 KB default too
+    if (int rc = pem_ensure_dyn_smem(kern, smem, &cached)) return rc;
     kern<<<B, THREADS, smem, st>>>(xyz, N, M, skip, idx);
     return pem_launch_status();
 }
@@ -186,14 +183,14 @@ gather_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, i
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int BM, int N,
                    int C, int M, long long batch_stride, long long row_stride,
-                   float *__restrict__ out, int vec4) {
+                   float *__restrict__ out, long long out_batch_stride, int vec4) {
     const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (row >= BM) return;
     const int b = row / M;
     const int a = __ldg(idx + row);
     const bool ok = a >= 0 && a < N;
     const float *src = feat + (size_t)b * batch_stride + (size_t)(ok ? a : 0) * row_stride;
-    float *dst = out + (size_t)row * C;
+    float *dst = out + (size_t)b * out_batch_stride + (size_t)(row - b * M) * C;
     if (vec4) {
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
         float4 *d4 = reinterpret_cast<float4 *>(dst);
@@ -322,6 +319,27 @@ query_and_group_kernel(const float *__restrict__ xyz, const float *__restrict__ 
     }
 }
 
+// out[b,i,:] = (p[b,i,:] - t[b]) @ R[b]  (+ eps on every coordinate): the point transform of
+// fine_point_matching.py:45 and the `pts + 1e-8` query centres of fine_point_matching.py:117.
+__global__ void __launch_bounds__(256)
+transform_points_kernel(const float *__restrict__ p, const float *__restrict__ R,
+                        const float *__restrict__ t, int N, float eps, float *__restrict__ out) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float *q = p + ((size_t)b * N + i) * 3;
+    float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+    float o0 = v0, o1 = v1, o2 = v2;
+    if (R != nullptr) {
+        const float *Rb = R + (size_t)b * 9, *tb = t + (size_t)b * 3;
+        v0 -= tb[0]; v1 -= tb[1]; v2 -= tb[2];
+        o0 = v0 * Rb[0] + v1 * Rb[3] + v2 * Rb[6];
+        o1 = v0 * Rb[1] + v1 * Rb[4] + v2 * Rb[7];
+        o2 = v0 * Rb[2] + v1 * Rb[5] + v2 * Rb[8];
+    }
+    float *o = out + ((size_t)b * N + i) * 3;
+    o[0] = __fadd_rn(o0, eps); o[1] = __fadd_rn(o1, eps); o[2] = __fadd_rn(o2, eps);
+}
+
 static size_t bq_smem_bytes(int ns) {
     return (size_t)kBqTile * sizeof(float4) + (size_t)kBqCentres * (ns + 1) * sizeof(int);
 }
@@ -369,16 +387,19 @@ extern "C" int pem_gather(const float *feat, const int32_t *idx, int B, int C, i
 
 extern "C" int pem_gather_rows(const float *feat, const int32_t *idx, int B, int N, int C, int M,
                                long long batch_stride, long long row_stride, float *out,
-                               pem_stream_t stream) {
+                               long long out_batch_stride, pem_stream_t stream) {
     PEM_REQUIRE_PTR(feat);
     PEM_REQUIRE_PTR(idx);
     PEM_REQUIRE_PTR(out);
     PEM_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && row_stride >= C, PEM_E_SHAPE);
+    if (out_batch_stride <= 0) out_batch_stride = (long long)M * C;
+    PEM_REQUIRE(out_batch_stride >= (long long)M * C, PEM_E_SHAPE);
     const int rows = B * M;
     const int vec4 = (C % 4 == 0) && (row_stride % 4 == 0) && (batch_stride % 4 == 0) &&
+                     (out_batch_stride % 4 == 0) &&
                      ((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0);
     gather_rows_kernel<<<(rows + 7) / 8, 256, 0, pem_cu_stream(stream)>>>(
-        feat, idx, rows, N, C, M, batch_stride, row_stride, out, vec4);
+        feat, idx, rows, N, C, M, batch_stride, row_stride, out, out_batch_stride, vec4);
     return pem_launch_status();
 }
 
@@ -403,9 +424,8 @@ extern "C" int pem_ball_query(const float *new_xyz, const float *xyz, int B, int
     PEM_REQUIRE(B > 0 && M > 0 && N > 0 && nsample > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(nsample <= 128, PEM_E_UNSUPPORTED);
     const size_t smem = bq_smem_bytes(nsample);
-    cudaError_t e = cudaFuncSetAttribute(ball_query_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(ball_query_kernel, smem, &cached)) return rc;
     const float r2 = radius * radius;  // fp32 product, as ball_query.cpp:20
     ball_query_kernel<<<dim3((M + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
                         pem_cu_stream(stream)>>>(new_xyz, xyz, M, N, r2, nsample, idx);
@@ -422,12 +442,22 @@ extern "C" int pem_query_and_group(const float *xyz, const float *new_xyz, const
     PEM_REQUIRE(C == 0 || feat != nullptr, PEM_E_NULL);
     PEM_REQUIRE(nsample <= 128, PEM_E_UNSUPPORTED);
     const size_t smem = bq_smem_bytes(nsample);
-    cudaError_t e = cudaFuncSetAttribute(query_and_group_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(query_and_group_kernel, smem, &cached)) return rc;
     const float r2 = radius * radius;
     query_and_group_kernel<<<dim3((M + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
                              pem_cu_stream(stream)>>>(xyz, new_xyz, feat, N, M, C, r2, nsample,
                                                       out, idx_out);
+    return pem_launch_status();
+}
+
+extern "C" int pem_transform_points(const float *pts, const float *R, const float *t, int B, int N,
+                                    float eps, float *out, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(pts);
+    PEM_REQUIRE_PTR(out);
+    PEM_REQUIRE(B > 0 && N > 0 && B <= 65535, PEM_E_SHAPE);
+    PEM_REQUIRE((R == nullptr) == (t == nullptr), PEM_E_NULL);
+    transform_points_kernel<<<dim3((N + 255) / 256, B), 256, 0, pem_cu_stream(stream)>>>(pts, R, t, N,
+                                                                                       eps, out);
     return pem_launch_status();
 }

@@ -52,7 +52,7 @@ def gather_rows(feats, idx):
         return out
     with torch.cuda.device(feats.device):
         _lib.check(_lib.lib().pem_gather_rows(feats.data_ptr(), idx.data_ptr(), B, N, C, M,
-                                              feats.stride(0), feats.stride(1), out.data_ptr(),
+                                              feats.stride(0), feats.stride(1), out.data_ptr(), 0,
                                               _ext._stream()), "pem_gather_rows")
     return out
 

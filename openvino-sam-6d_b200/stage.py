@@ -1,0 +1,182 @@
+"""The PEM geometric stage for a batch of detected instances, as one preallocated pipeline.
+
+This is what ``Net.forward`` (model/pose_estimation_model.py:29-55 of the reference) does
+between the networks, in the reference's order ("Instance"):
+
+  1. sample_pts_feats x2 (observed, template): FPS 2048->196 + point/feature gathers
+  2. coarse: similarity (197x197) -> compute_coarse_Rt -> init_R, init_t
+  3. fine front end: p1_ = (p1 - init_t) @ init_R; PositionalEncoding grouping
+     (QueryAndGroup r=0.1/ns=32 and r=0.2/ns=64) of p1_ and of the template cloud;
+     3 x 2 gather_operation of 196 rows from the (B,2049,256) feature tensors
+     (SparseToDenseTransformer._sample_feats, transformer.py:667-671)
+  4. fine: similarity (2049x2049) -> compute_fine_Rt -> R, t, pose_score
+
+The learned layers between those steps are outside the hot path; their inputs/outputs are
+stood in for by the synthetic instance tensors (synth.py): the coarse features are the
+gathered dense features, the fine features are the dense features, each with the
+background token prepended.
+
+All device buffers are allocated once; a step is a fixed sequence of C-ABI calls on one
+stream, captured into a CUDA graph (``use_graph=True``) so that a step costs one graph
+launch.  Input slots: ``pts`` (2,B,N,3) [0]=observed [1]=template, ``feats`` (2,B,N+1,C)
+whose row 0 is the background token and rows 1.. the dense features, ``model`` (B,Nm,3),
+``rand`` (B,3*P1).  Output: ``records`` (B,16) fp32 = R (9), t (3), pose_score, proposal
+id, instance id, pad -- the 64-byte per-instance record the multi-GPU gather moves.
+"""
+import torch
+
+from . import _lib
+
+PE_SCALES = ((0.1, 32), (0.2, 64))  # config/base.yaml:48-49, fine_point_matching.py:103
+
+
+class GeometricStage:
+    def __init__(self, batch, device, n_dense=2048, n_sparse=196, feat_dim=256, n_model=1024,
+                 n_proposal1=6000, n_proposal2=300, temp=0.1, dis_thres=0.15, use_graph=True,
+                 fine_mode="materialised"):
+        self.B, self.N, self.M, self.C, self.Nm = batch, n_dense, n_sparse, feat_dim, n_model
+        self.P1, self.P2, self.temp, self.dis_thres = n_proposal1, n_proposal2, temp, dis_thres
+        self.dev = torch.device(device)
+        self.L = _lib.lib()
+        self.fine_mode = fine_mode
+        B, N, M, C, Nm, P1, P2 = batch, n_dense, n_sparse, feat_dim, n_model, n_proposal1, n_proposal2
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        e = torch.empty
+        # inputs
+        self.pts = e((2, B, N, 3), **f32)
+        self.feats = e((2, B, N + 1, C), **f32)
+        self.model = e((B, Nm, 3), **f32)
+        self.rand = e((B, 3 * P1), **f32)
+        self.instance_ids = torch.zeros((B,), **f32)
+        # step 1
+        self.fps_idx = e((2, B, M), **i32)
+        self.sparse_pts = e((2, B, M, 3), **f32)
+        self.sparse_feats = e((2, B, M + 1, C), **f32)  # row 0 = background token
+        # step 2
+        self.atten_c = e((B, M + 1, M + 1), **f32)
+        self.w1c, self.w2c = e((B, M), **f32), e((B, M), **f32)
+        self.cdf = e((B, M * M), **f32)
+        self.hyp_R, self.hyp_t = e((B, P1, 9), **f32), e((B, P1, 3), **f32)
+        self.resid = e((B, P1), **f32)
+        self.sel = e((B, P2), **i32)
+        self.scores = e((B, P2), **f32)
+        self.init_R, self.init_t = e((B, 9), **f32), e((B, 3), **f32)
+        self.proposal_id = e((B,), **i32)
+        # step 3
+        self.pe_xyz = e((2, B, N, 3), **f32)      # [0] = p1_, [1] = template
+        self.pe_centres = e((2, B, N, 3), **f32)  # xyz + 1e-8
+        self.pe_featT = e((2, B, 3, N), **f32)    # xyz transposed: the "features" of PE
+        self.pe_out = [e((2 * B, 6, N, ns), **f32) for _, ns in PE_SCALES]
+        self.sparse_fine = [e((2, B, M, C), **f32) for _ in range(3)]
+        # step 4
+        self.atten_f = e((B, N + 1, N + 1), **f32) if fine_mode == "materialised" else None
+        self.R, self.t, self.score = e((B, 9), **f32), e((B, 3), **f32), e((B,), **f32)
+        self.records = torch.zeros((B, 16), **f32)
+        nb = max(self.L.pem_similarity_workspace_bytes(B, N + 1, N + 1),
+                 self.L.pem_fine_workspace_bytes(B, N, N), 256)
+        self.ws = torch.empty(nb, dtype=torch.uint8, device=self.dev)
+        self.ws_bytes = nb
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.graph = None
+        self.use_graph = use_graph
+        self.kernels_per_step = 0
+
+    # ---------------------------------------------------------------------------------
+    def load(self, batch):
+        """Copy a synthetic batch (synth.make_batch, host or device tensors) into the input slots."""
+        B = self.B
+        with torch.cuda.stream(self.stream):
+            self.pts[0].copy_(batch["dense_pm"], non_blocking=True)
+            self.pts[1].copy_(batch["dense_po"], non_blocking=True)
+            self.feats[0, :, 1:].copy_(batch["dense_fm"], non_blocking=True)
+            self.feats[1, :, 1:].copy_(batch["dense_fo"], non_blocking=True)
+            bg = batch["bg"].to(self.dev, non_blocking=True)
+            self.feats[:, :, 0].copy_(bg.unsqueeze(0).expand(2, B, -1))
+            self.sparse_feats[:, :, 0].copy_(bg.unsqueeze(0).expand(2, B, -1))
+            self.model.copy_(batch["model"], non_blocking=True)
+            self.rand.copy_(batch["rand"], non_blocking=True)
+        self.stream.synchronize()
+
+    # ---------------------------------------------------------------------------------
+    def _enqueue(self):
+        """The fixed launch sequence of one step on self.stream (also what gets captured)."""
+        L, st = self.L, self.stream.cuda_stream
+        B, N, M, C, Nm, P1, P2 = self.B, self.N, self.M, self.C, self.Nm, self.P1, self.P2
+        ck = _lib.check
+        p = lambda t: t.data_ptr()
+        n = 0
+        # 1. FPS on both clouds in one launch (2B clouds), then row gathers
+        ck(L.pem_fps(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), None, 0, st), "fps"); n += 1
+        ck(L.pem_gather_rows(p(self.pts), p(self.fps_idx), 2 * B, N, 3, M, N * 3, 3,
+                             p(self.sparse_pts), 0, st), "gather pts"); n += 1
+        # dense features live in rows 1.. of `feats`; gather into rows 1.. of `sparse_feats`
+        ck(L.pem_gather_rows(p(self.feats) + 4 * C, p(self.fps_idx), 2 * B, N, C, M, (N + 1) * C, C,
+                             p(self.sparse_feats) + 4 * C, (M + 1) * C, st), "gather feats"); n += 1
+        # 2. coarse
+        ck(L.pem_feature_similarity(p(self.sparse_feats[0]), p(self.sparse_feats[1]), B, M + 1, M + 1,
+                                    C, self.temp, 1, p(self.atten_c), p(self.ws), self.ws_bytes, st),
+           "coarse similarity"); n += 3
+        ck(L.pem_coarse_assign(p(self.atten_c), B, M, M, p(self.w1c), p(self.w2c), p(self.cdf), st),
+           "coarse_assign"); n += 1
+        ck(L.pem_coarse_hypotheses(p(self.cdf), p(self.rand), p(self.sparse_pts[0]),
+                                   p(self.sparse_pts[1]), B, M, M, P1, p(self.hyp_R), p(self.hyp_t),
+                                   p(self.resid), None, st), "coarse_hypotheses"); n += 1
+        ck(L.pem_select_smallest(p(self.resid), B, P1, P2, p(self.sel), st), "select_smallest"); n += 1
+        ck(L.pem_score_hypotheses(p(self.hyp_R), p(self.hyp_t), p(self.sel), B, P1, P2,
+                                  p(self.sparse_pts[0]), p(self.w1c), M, p(self.model), Nm,
+                                  p(self.scores), st), "score_hypotheses"); n += 1
+        ck(L.pem_select_best(p(self.scores), p(self.sel), p(self.hyp_R), p(self.hyp_t), B, P1, P2,
+                             p(self.init_R), p(self.init_t), p(self.proposal_id), st),
+           "select_best"); n += 1
+        # 3. fine front end: p1_ = (p1 - t) @ R ; PE grouping of p1_ and of the template
+        ck(L.pem_transform_points(p(self.pts[0]), p(self.init_R), p(self.init_t), B, N, 0.0,
+                                  p(self.pe_xyz[0]), st), "transform"); n += 1
+        ck(L.pem_transform_points(p(self.pts[1]), None, None, B, N, 0.0, p(self.pe_xyz[1]), st),
+           "copy template"); n += 1
+        ck(L.pem_transform_points(p(self.pe_xyz), None, None, 2 * B, N, 1e-8, p(self.pe_centres), st),
+           "centres"); n += 1
+        self.pe_featT.copy_(self.pe_xyz.transpose(2, 3)); n += 1
+        for (r, ns), out in zip(PE_SCALES, self.pe_out):
+            ck(L.pem_query_and_group(p(self.pe_xyz), p(self.pe_centres), p(self.pe_featT), 2 * B, N, N,
+                                     3, r, ns, p(out), None, st), "query_and_group"); n += 1
+        # 3 transformer blocks x (observed, template): gather 196 rows of the bg-prepended
+        # (B,2049,C) features with the FPS indices (reference quirk kept: index 0 fetches the
+        # background row, transformer.py:667-671)
+        for blk in range(3):
+            ck(L.pem_gather_rows(p(self.feats), p(self.fps_idx), 2 * B, N + 1, C, M, (N + 1) * C, C,
+                                 p(self.sparse_fine[blk]), 0, st), "gather fine"); n += 1
+        # 4. fine
+        ck(L.pem_feature_similarity(p(self.feats[0]), p(self.feats[1]), B, N + 1, N + 1, C, self.temp,
+                                    1, p(self.atten_f), p(self.ws), self.ws_bytes, st),
+           "fine similarity"); n += 3
+        ck(L.pem_fine_Rt(p(self.atten_f), p(self.pts[0]), p(self.pts[1]), p(self.model), B, N, N, Nm,
+                         self.dis_thres, p(self.R), p(self.t), p(self.score), None, None, None, None,
+                         p(self.ws), self.ws_bytes, st), "fine_Rt"); n += 9
+        # 64-byte records
+        self.records[:, 0:9].copy_(self.R)
+        self.records[:, 9:12].copy_(self.t)
+        self.records[:, 12].copy_(self.score)
+        self.records[:, 13].copy_(self.proposal_id)
+        self.records[:, 14].copy_(self.instance_ids)
+        n += 5
+        self.kernels_per_step = n
+
+    def run(self):
+        """Enqueue one step on self.stream (no synchronisation)."""
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            if not self.use_graph:
+                self._enqueue()
+                return
+            if self.graph is None:
+                self._enqueue()  # warm-up: sets function attributes, fills caches
+                self.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._enqueue()
+                self.graph = g
+            self.graph.replay()
+
+    def result(self):
+        """(R (B,3,3), t (B,3), pose_score (B), proposal_id (B)) views of the device outputs."""
+        return self.R.view(self.B, 3, 3), self.t, self.score, self.proposal_id

@@ -1,0 +1,73 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads, exports every symbol
+include/pem_b200.h declares, and validates arguments before touching the GPU."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "pem_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pem_[a-z0-9_A-Z]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    lib = pkg._lib.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    # and the ctypes table covers exactly the header
+    assert sorted(pkg._lib.SIGNATURES) == names
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "pem_b200.h")).read()
+    assert "torch" not in src.lower().replace("pytorch", "") or "at::" not in src
+    assert 'extern "C"' in src and "at::Tensor" not in src
+
+
+def test_identification(pkg):
+    lib = pkg._lib.lib()
+    assert lib.pem_abi_version() == 1
+    assert b"sm_100a" in lib.pem_build_info()
+    assert lib.pem_status_string(0) == b"ok"
+    assert b"NULL" in lib.pem_status_string(-1)
+
+
+def test_argument_validation_without_gpu(pkg):
+    """Invalid arguments are rejected with negative codes before any CUDA call."""
+    lib = pkg._lib.lib()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.pem_fps(None, 1, 8, 2, 1, p, None, 0, None) == -1
+    assert lib.pem_fps(p, 0, 8, 2, 1, p, None, 0, None) == -2
+    assert lib.pem_fps(p, 1, 100000, 2, 1, p, None, 0, None) == -4      # needs a workspace
+    assert lib.pem_gather(p, p, 1, 0, 8, 2, p, None) == -2
+    assert lib.pem_ball_query(p, p, 1, 4, 4, 0.1, 500, p, None) == -3   # nsample > 128
+    assert lib.pem_coarse_assign(p, 1, 300, 300, p, p, p, None) == -3   # matrix exceeds one SM
+    assert lib.pem_select_smallest(p, 1, 10, 11, p, None) == -2         # P2 > P1
+    assert lib.pem_fine_Rt(p, p, p, p, 1, 8, 8, 8, 0.15, p, p, p, None, None, None, None, None, 0, None) == -4
+    assert lib.pem_fps_workspace_bytes(4, 2048) == 0
+    assert lib.pem_fps_workspace_bytes(2, 210000) == 2 * 210000 * 4
+    assert lib.pem_fine_workspace_bytes(16, 2048, 2048) > 16 * 2049 * 4 * 6
+
+
+def test_product_package_never_imports_the_oracle():
+    """The product path must not route through oracle/ (or any CPU fallback)."""
+    pk = os.path.join(ROOT, "openvino-sam-6d_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "pem_oracle" not in text and "cpu_stage" not in text and "oracle/" not in text, f
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    import pytest
+    monkeypatch.setattr(pkg._lib, "_lib", None)
+    monkeypatch.setattr(pkg._lib, "LIB_PATH", "/nonexistent/libpem_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg._lib.lib()

@@ -152,12 +152,12 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident, per-step CUDA events on the launch stream -------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(max(W, 3)):
         stage.run()
         step_collective()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     wall0 = time.perf_counter()
@@ -305,7 +305,7 @@ def scoring_sweep_point(pkg, stage, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="instances per GPU")

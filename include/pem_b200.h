@@ -197,6 +197,31 @@ int pem_fine_Rt(const float *atten, const float *pts1, const float *pts2, const 
                 size_t workspace_bytes, pem_stream_t stream);
 
 /*
+ * Tensor-core similarity: the same function as pem_feature_similarity computed as a
+ * split-bf16 (hi*hi + lo*hi + hi*lo) tcgen05 GEMM with TMA-staged operands and the
+ * accumulator in TMEM; logits agree with the fp32 path to ~1e-5.  Requires C % 64 == 0,
+ * C <= 256, temp >= 0.025.  f1 (B,N1p,C), f2 (B,N2p,C) -> atten (B,N1p,N2p).
+ * workspace: pem_fine_fused_workspace_bytes(B, N1p-1, N2p-1, C).
+ */
+size_t pem_fine_fused_workspace_bytes(int B, int N1, int N2, int C);
+int pem_feature_similarity_tc(const float *f1, const float *f2, int B, int N1p, int N2p, int C,
+                              float temp, int normalize, float *atten, void *workspace,
+                              size_t workspace_bytes, pem_stream_t stream);
+
+/*
+ * Fused fine stage: compute_feature_similarity (MU:131-153, cosine, normalised) followed by
+ * compute_fine_Rt (MU:308-341) straight from the features; the (B,N1+1,N2+1) attention
+ * matrix is never written to memory (three tcgen05 GEMM passes with reducing epilogues).
+ * f1 (B,N1+1,C), f2 (B,N2+1,C) with the background token in row 0; other arguments and
+ * outputs as pem_fine_Rt.  Same constraints as pem_feature_similarity_tc.
+ */
+int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const float *pts2,
+                   const float *model, int B, int N1, int N2, int C, int Nm, float temp,
+                   float dis_thres, float *R, float *t, float *score, float *w1, float *w2,
+                   float *rowsum, float *pred, void *workspace, size_t workspace_bytes,
+                   pem_stream_t stream);
+
+/*
  * Weighted Procrustes (MU:343-436) for B' problems of n points each, one CTA per
  * problem: src, ref (B',n,3), weights (B',n) or NULL (ones) -> R (B',9), t (B',3).
  * ref ~ R src + t.

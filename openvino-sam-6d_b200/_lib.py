@@ -41,6 +41,10 @@ SIGNATURES = {
     "pem_fine_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "pem_fine_Rt": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p,
                           c_p, c_p, c_p, c_sz, c_p]),
+    "pem_fine_fused_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "pem_feature_similarity_tc": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_sz, c_p]),
+    "pem_fine_fused": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p,
+                             c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "pem_weighted_procrustes": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
 }
 

@@ -378,6 +378,22 @@ static FineWs fine_carve(void *base, int B, int N1, int N2) {
     return w;
 }
 
+// Shared tail of both fine paths: WSVD(pred_pts, pts1, assignment_score) with weight_thresh
+// 0.0 (MU:319,331), then the pose score (MU:334-339).  counters: (B,3) ints of scratch.
+int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA, const float *w1,
+                     const float *model, int B, int N1, int Nm, float dis_thres, int *counters,
+                     float *R, float *t, float *score, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)B * 3 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    weighted_procrustes_kernel<<<B, 256, 0, st>>>(pred, pts1, rowsumA, N1, 0.0f, 1e-5f, R, t);
+    const size_t smem = (size_t)Nm * sizeof(float4);
+    static size_t cached = 40 * 1024;
+    if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
+    fine_pose_score_kernel<<<dim3((N1 + kPsThreads - 1) / kPsThreads, B), kPsThreads, smem, st>>>(
+        pts1, w1, R, t, model, N1, Nm, dis_thres, counters, score);
+    return pem_launch_status();
+}
+
 }  // namespace pem
 
 using namespace pem;
@@ -425,8 +441,6 @@ extern "C" int pem_fine_Rt(const float *atten, const float *pts1, const float *p
     const dim3 grid(nslab, B);
 
     fine_init_kernel<<<(B * Cn + 255) / 256, 256, 0, st>>>(w.colmax_i, w.colmaxP, B * Cn);
-    cudaError_t e = cudaMemsetAsync(w.counters, 0, (size_t)B * 3 * sizeof(int), st);
-    if (e != cudaSuccess) return (int)e;
     fine_max_kernel<<<grid, kFnThreads, 0, st>>>(atten, R_, Cn, w.rowmax, w.colmax_i);
     fine_sum_kernel<<<grid, kFnThreads, 0, st>>>(atten, R_, Cn, w.rowmax, w.colmax_i, w.rowsum,
                                                  w.colpart);
@@ -437,12 +451,6 @@ extern "C" int pem_fine_Rt(const float *atten, const float *pts1, const float *p
     fine_wsum_kernel<<<grid, kFnThreads, 0, st>>>(atten, R_, Cn, w.rowmax, w.rowsum, w.colmax_i,
                                                   w.colsum, w.colmaxP, w.P0, w1, pts2, w2_out, rsA,
                                                   pred);
-    // WSVD(pred_pts, pts1, assignment_score) with weight_thresh = 0.0 (MU:319,331)
-    weighted_procrustes_kernel<<<B, 256, 0, st>>>(pred, pts1, rsA, N1, 0.0f, 1e-5f, R, t);
-    const size_t smem = (size_t)Nm * sizeof(float4);
-    static size_t cached = 40 * 1024;
-    if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
-    fine_pose_score_kernel<<<dim3((N1 + kPsThreads - 1) / kPsThreads, B), kPsThreads, smem, st>>>(
-        pts1, w1, R, t, model, N1, Nm, dis_thres, w.counters, score);
-    return pem_launch_status();
+    return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t, score,
+                            st);
 }

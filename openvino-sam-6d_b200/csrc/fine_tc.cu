@@ -1,0 +1,703 @@
+// Fused fine-stage path on the 5th-generation tensor cores (tcgen05 + TMEM + TMA):
+// compute_feature_similarity (MU:131-153) + compute_fine_Rt (MU:308-341) WITHOUT ever
+// materialising the (B, 2049, 2049) attention matrix in HBM.  (MU = the reference's
+// utils/model_utils.py.)
+//
+//   prep      normalise rows (F.normalize, eps 1e-12) and split every fp32 value into
+//             bf16 hi + bf16 lo; operands are stored row-padded to a multiple of 128.
+//   GEMM x3   S = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T  (split-bf16: ~2^-17 relative, i.e.
+//             fp32-class logits; plain bf16 would move the pose by up to 0.05 deg) with the
+//             accumulator in TMEM, recomputed in three passes whose epilogues reduce
+//             straight out of TMEM:
+//               pass 1  e = exp(s/temp - 1/temp);  row sums, column sums      (softmax stats)
+//               pass 2  foreground labels: row max of e^2/colsum vs the background column,
+//                       column max of e^2/rowsum vs the background row        (MU:321-322)
+//               pass 3  per row: sum_j P_ij w2_j  and  sum_j P_ij w2_j pts2_j  (MU:324-330)
+//             Because features are unit vectors, |s/temp| <= 1/temp, so a fixed shift
+//             replaces the running max of a streaming softmax.
+//   then the weighted Procrustes + pose score kernels of fine.cu.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: the 128-row A strip (hi+lo, 128 KB) is loaded once per task and
+//               stays resident in shared memory; B tiles stream through a 5-stage ring of
+//               16 KB SWIZZLE_128B chunks (mbarrier full/empty pairs).
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=128, K=16,
+//               kind::f16, bf16 in / fp32 accumulate), tcgen05.commit to free ring slots and
+//               to hand the accumulator to the epilogue; two 128-column TMEM accumulators
+//               are double-buffered so MMAs of tile n+1 overlap the epilogue of tile n.
+//   warps 2-5   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread), so
+//               row reductions are thread-local; column reductions use a 31-shuffle
+//               warp transpose-reduce per 32 columns and a 4-warp combine in shared memory.
+// A task = (instance, 128-row strip); tasks are dealt round-robin to the CTAs.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "pem_common.cuh"
+
+namespace pem {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64;  // BK bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int kChunkBytes = BM * BK * 2;    // 16 KB
+constexpr int kStages = 5;
+constexpr int kMaxKC = 4;                   // C <= 256
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;              // 2 accumulators x 128 columns
+
+enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3 };
+
+struct Params {
+    int B, R, Cn;          // instances, valid rows (N1+1), valid columns (N2+1)
+    int Mp, Np;            // padded rows of A' / B' per instance
+    int n_strips, n_tiles; // Mp/128, Np/128
+    int KC;                // C / 64
+    float temp;            // logits = cos / temp
+    float c1, c2;          // e = exp2(cos * c1 - c2)
+    // kStore
+    float *atten;          // (B,R,Cn)
+    // kStats
+    float *rowsum;         // (B,Mp)
+    float *colpart;        // (B,n_strips,Np)
+    // kLabel
+    const float *inv_rowsum;  // (B,Mp)
+    const float *inv_colsum;  // (B,Np)
+    float *w1;                // (B,Mp) indexed by full row index (row 0 = background, unused)
+    float *colmaxpart;        // (B,n_strips,Np): max over rows>=1 of e^2/rowsum
+    float *bgrow;             // (B,Np): e_0j^2 / rowsum_0
+    // kWsum
+    const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for j = 0 and padding
+    float *rowsumA;        // (B,R-1)
+    float *pred;           // (B,R-1,3)
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t bar, uint32_t dst,
+                                            int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 consecutive fp32 columns of this warp's 32 TMEM lanes: thread = lane (= output row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO (ignored for swizzled K-major, canonical 1) << 16 |
+// SBO = 1024 B (8 rows x 128 B) >> 4 << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+// Sum (or max) over the 32 lanes of v[c], c = 0..31; lane L ends up holding column L.
+template <bool IS_MAX>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int c = 0; c < half; ++c) {
+            const float send = up ? v[c] : v[c + half];
+            const float keep = up ? v[c + half] : v[c];
+            const float recv = __shfl_xor_sync(kFull, send, half);
+            v[c] = IS_MAX ? fmaxf(keep, recv) : keep + recv;
+        }
+    }
+    return v[0];
+}
+
+struct Smem {
+    // operand buffers first: SWIZZLE_128B needs 1024-byte alignment
+    uint8_t a_hi[kMaxKC][kChunkBytes];
+    uint8_t a_lo[kMaxKC][kChunkBytes];
+    uint8_t b[kStages][kChunkBytes];
+    float col[2][4][BN];   // per-quadrant column partials, double buffered
+    float4 G[2][BN];       // per-tile column constants (kLabel: inv_colsum in .x; kWsum: G)
+    uint64_t full[kStages], empty[kStages], a_full, a_empty, tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = warp_id(), lane = lane_id();
+    const int n_tasks = p.B * p.n_strips;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), 1);
+        }
+        mbar_init(smem_u32(&sm.a_full), 1);
+        mbar_init(smem_u32(&sm.a_empty), 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&sm.tmem_full[a]), 1);
+            mbar_init(smem_u32(&sm.tmem_empty[a]), 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM allocation is warp-collective
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&sm.tmem_base)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+                const int b = task / p.n_strips, s = task - b * p.n_strips;
+                mbar_wait(smem_u32(&sm.a_empty), a_phase ^ 1);
+                a_phase ^= 1;
+                mbar_expect_tx(smem_u32(&sm.a_full), 2u * p.KC * kChunkBytes);
+                const int rowA = b * p.Mp + s * BM;
+                for (int kc = 0; kc < p.KC; ++kc) {
+                    tma_load_2d(&tmA, smem_u32(&sm.a_full), smem_u32(sm.a_hi[kc]), kc * BK, rowA);
+                    tma_load_2d(&tmA, smem_u32(&sm.a_full), smem_u32(sm.a_lo[kc]), kc * BK,
+                                p.B * p.Mp + rowA);
+                }
+                for (int n = 0; n < p.n_tiles; ++n) {
+                    const int rowB = b * p.Np + n * BN;
+                    for (int kc = 0; kc < p.KC; ++kc) {
+                        for (int hl = 0; hl < 2; ++hl) {
+                            mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+                            mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
+                            tma_load_2d(&tmB, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]),
+                                        kc * BK, hl * p.B * p.Np + rowB);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, a_phase = 0, acc_phase = 0;
+            for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+                mbar_wait(smem_u32(&sm.a_full), a_phase);
+                a_phase ^= 1;
+                tc_fence_after();
+                for (int n = 0; n < p.n_tiles; ++n) {
+                    mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                    uint32_t accumulate = 0;
+                    for (int kc = 0; kc < p.KC; ++kc) {
+                        const uint32_t ah = smem_u32(sm.a_hi[kc]), al = smem_u32(sm.a_lo[kc]);
+                        // B_hi chunk: A_hi*B_hi + A_lo*B_hi
+                        mbar_wait(smem_u32(&sm.full[stage]), phase);
+                        tc_fence_after();
+                        uint32_t bs = smem_u32(sm.b[stage]);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t bd = umma_desc_sw128(bs + k * 32);
+                            tc_mma_bf16(d, umma_desc_sw128(ah + k * 32), bd, kIdesc, accumulate);
+                            accumulate = 1;
+                            tc_mma_bf16(d, umma_desc_sw128(al + k * 32), bd, kIdesc, 1);
+                        }
+                        tc_commit(smem_u32(&sm.empty[stage]));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        // B_lo chunk: A_hi*B_lo
+                        mbar_wait(smem_u32(&sm.full[stage]), phase);
+                        tc_fence_after();
+                        bs = smem_u32(sm.b[stage]);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma_bf16(d, umma_desc_sw128(ah + k * 32), umma_desc_sw128(bs + k * 32),
+                                        kIdesc, 1);
+                        tc_commit(smem_u32(&sm.empty[stage]));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(smem_u32(&sm.tmem_full[acc]));  // accumulator ready for the epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                tc_commit(smem_u32(&sm.a_empty));  // all MMAs reading the A strip have retired
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue ====================================
+        const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32)
+        const int et = quad * 32 + lane;      // row of the 128-row tile owned by this thread
+        const int ep_tid = (warp - 2) * 32 + lane;  // 0..127, used for column-indexed work
+        int acc = 0, cbuf = 0;
+        uint32_t acc_phase = 0;
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            const int b = task / p.n_strips, s = task - b * p.n_strips;
+            const int gi = s * BM + et;
+            const bool row_ok = gi < p.R;
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;  // row accumulators (mode dependent)
+            float row_const = 0.f, bg_val = 0.f;
+            if (MODE == kLabel) {
+                row_const = row_ok ? p.inv_rowsum[(size_t)b * p.Mp + gi] : 0.f;
+                r0 = -1.f;
+            }
+            for (int n = 0; n < p.n_tiles; ++n) {
+                const int j0 = n * BN;
+                if (MODE == kLabel || MODE == kWsum) {
+                    // stage this tile's per-column constants (double buffered by tile parity)
+                    const size_t cj = (size_t)b * p.Np + j0 + ep_tid;
+                    if (MODE == kLabel) sm.G[cbuf][ep_tid] = make_float4(p.inv_colsum[cj], 0.f, 0.f, 0.f);
+                    else sm.G[cbuf][ep_tid] = p.G[cj];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                    const int jc = j0 + c * 32;
+                    if (MODE == kStore) {
+                        if (row_ok) {
+                            float *dst = p.atten + ((size_t)b * p.R + gi) * p.Cn + jc;
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (jc + q < p.Cn) dst[q] = __fdiv_rn(v[q], p.temp);
+                        }
+                    } else if (MODE == kStats) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const float e = (row_ok && jc + q < p.Cn) ? ex2(fmaf(v[q], p.c1, -p.c2)) : 0.f;
+                            r0 += e;
+                            v[q] = e;
+                        }
+                        sm.col[cbuf][quad][c * 32 + lane] = warp_transpose_reduce<false>(v);
+                    } else if (MODE == kLabel) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const bool ok = row_ok && jc + q < p.Cn;
+                            const float e = ok ? ex2(fmaf(v[q], p.c1, -p.c2)) : 0.f;
+                            const float u = e * e;
+                            // row side: e^2 / colsum_j over j >= 1, and the background column j = 0
+                            const float pr = u * sm.G[cbuf][c * 32 + q].x;
+                            if (jc + q == 0) bg_val = pr; else r0 = fmaxf(r0, ok ? pr : -1.f);
+                            // column side: e^2 / rowsum_i over rows i >= 1
+                            v[q] = (ok && gi >= 1) ? u * row_const : -1.f;
+                            if (gi == 0 && jc + q < p.Cn) p.bgrow[(size_t)b * p.Np + jc + q] = u * row_const;
+                        }
+                        sm.col[cbuf][quad][c * 32 + lane] = warp_transpose_reduce<true>(v);
+                    } else {  // kWsum
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const float e = ex2(fmaf(v[q], p.c1, -p.c2));
+                            const float u = e * e;
+                            const float4 g = sm.G[cbuf][c * 32 + q];  // zero for j = 0 / padding / w2 = 0
+                            r0 = fmaf(u, g.w, r0);
+                            r1 = fmaf(u, g.x, r1);
+                            r2 = fmaf(u, g.y, r2);
+                            r3 = fmaf(u, g.z, r3);
+                        }
+                    }
+                }
+                // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (MODE == kStats || MODE == kLabel) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    float x = sm.col[cbuf][0][ep_tid];
+#pragma unroll
+                    for (int w = 1; w < 4; ++w)
+                        x = (MODE == kLabel) ? fmaxf(x, sm.col[cbuf][w][ep_tid]) : x + sm.col[cbuf][w][ep_tid];
+                    float *dst = (MODE == kLabel) ? p.colmaxpart : p.colpart;
+                    dst[((size_t)b * p.n_strips + s) * p.Np + j0 + ep_tid] = x;
+                }
+                cbuf ^= 1;
+            }
+            // per-row results of this task
+            if (MODE == kStats) {
+                p.rowsum[(size_t)b * p.Mp + gi] = r0;  // 0 for padded rows
+            } else if (MODE == kLabel) {
+                if (row_ok && gi >= 1) p.w1[(size_t)b * p.Mp + gi] = (r0 > bg_val) ? 1.f : 0.f;
+            } else if (MODE == kWsum) {
+                if (row_ok && gi >= 1) {
+                    const float f = p.w1[(size_t)b * p.Mp + gi] * p.inv_rowsum[(size_t)b * p.Mp + gi];
+                    const float sA = r0 * f;
+                    const size_t ri = (size_t)b * (p.R - 1) + gi - 1;
+                    p.rowsumA[ri] = sA;                      // assignment_score (MU:330)
+                    const float inv = 1.0f / (sA + 1e-6f);   // MU:327
+                    p.pred[ri * 3 + 0] = r1 * f * inv;
+                    p.pred[ri * 3 + 1] = r2 * f * inv;
+                    p.pred[ri * 3 + 2] = r3 * f * inv;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------- prep / finish
+// One warp per padded row: x / max(|x|,1e-12) split into bf16 hi and lo.
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float *__restrict__ f, int B, int rows, int rows_p, int C, int normalize,
+               __nv_bfloat16 *__restrict__ out /* (2, B*rows_p, C) */) {
+    const int gr = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (gr >= B * rows_p) return;
+    const int b = gr / rows_p, i = gr - b * rows_p;
+    __nv_bfloat16 *hi = out + (size_t)gr * C, *lo = out + ((size_t)B * rows_p + gr) * C;
+    if (i >= rows) {
+        for (int c = lane_id(); c < C; c += 32) { hi[c] = __float2bfloat16(0.f); lo[c] = hi[c]; }
+        return;
+    }
+    const float *src = f + ((size_t)b * rows + i) * C;
+    float inv = 1.f;
+    if (normalize) {
+        float s = 0.f;
+        for (int c = lane_id(); c < C; c += 32) { const float v = __ldg(src + c); s = fmaf(v, v, s); }
+        s = warp_sum(s);
+        inv = fmaxf(sqrtf(s), 1e-12f);
+    }
+    for (int c = lane_id(); c < C; c += 32) {
+        const float v = normalize ? __fdiv_rn(__ldg(src + c), inv) : __ldg(src + c);
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        hi[c] = h;
+        lo[c] = __float2bfloat16(v - __bfloat162float(h));
+    }
+}
+
+// after pass 1: 1/rowsum, 1/colsum (column partials summed in strip order: deterministic)
+__global__ void __launch_bounds__(256)
+tc_finish_stats_kernel(const float *__restrict__ rowsum, const float *__restrict__ colpart, int Mp,
+                       int Np, int n_strips, float *__restrict__ inv_rowsum,
+                       float *__restrict__ inv_colsum) {
+    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < Mp) {
+        const float r = rowsum[(size_t)b * Mp + k];
+        inv_rowsum[(size_t)b * Mp + k] = r > 0.f ? 1.0f / r : 0.f;
+    }
+    if (k < Np) {
+        float s = 0.f;
+        for (int t = 0; t < n_strips; ++t) s += colpart[((size_t)b * n_strips + t) * Np + k];
+        inv_colsum[(size_t)b * Np + k] = s > 0.f ? 1.0f / s : 0.f;
+    }
+}
+
+// after pass 2: w2_j and the per-column constants of pass 3
+__global__ void __launch_bounds__(256)
+tc_finish_label_kernel(const float *__restrict__ colmaxpart, const float *__restrict__ bgrow,
+                       const float *__restrict__ inv_colsum, const float *__restrict__ pts2, int Cn,
+                       int Np, int n_strips, float *__restrict__ w2_out, float4 *__restrict__ G) {
+    const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Np) return;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= 1 && j < Cn) {
+        float m = -1.f;
+        for (int t = 0; t < n_strips; ++t) m = fmaxf(m, colmaxpart[((size_t)b * n_strips + t) * Np + j]);
+        const bool fg = m > bgrow[(size_t)b * Np + j];  // label2 > 0 (MU:322)
+        if (w2_out) w2_out[(size_t)b * (Cn - 1) + j - 1] = fg ? 1.f : 0.f;
+        if (fg) {
+            const float ic = inv_colsum[(size_t)b * Np + j];
+            const float *q = pts2 + ((size_t)b * (Cn - 1) + j - 1) * 3;
+            g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+        }
+    }
+    G[(size_t)b * Np + j] = g;
+}
+
+// copy w1 (indexed by full row, padded) into the dense (B,N1) layout the scorer expects
+__global__ void __launch_bounds__(256)
+tc_compact_w1_kernel(const float *__restrict__ w1p, int Mp, int N1, float *__restrict__ w1) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N1) w1[(size_t)b * N1 + i] = w1p[(size_t)b * Mp + i + 1];
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) !=
+            cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2D bf16 tensor (rows x C), box = 128 rows x 64 columns, SWIZZLE_128B
+static int make_operand_map(CUtensorMap *map, const void *base, size_t rows, int C) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return PEM_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PEM_OK : PEM_E_UNSUPPORTED;
+}
+
+struct Ws {
+    __nv_bfloat16 *A, *Bm;
+    float *rowsum, *inv_rowsum, *inv_colsum, *colpart, *w1p, *bgrow, *w1, *w2, *rowsumA, *pred;
+    float4 *G;
+    int *counters;
+    size_t bytes;
+};
+
+static int pad128(int x) { return (x + 127) / 128 * 128; }
+
+static Ws carve(void *base, int B, int N1, int N2, int C) {
+    const size_t Mp = pad128(N1 + 1), Np = pad128(N2 + 1), ns = Mp / 128;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 1023) / 1024 * 1024;
+        return (char *)base + o;
+    };
+    Ws w;
+    w.A = (__nv_bfloat16 *)take(2 * B * Mp * C * 2);
+    w.Bm = (__nv_bfloat16 *)take(2 * B * Np * C * 2);
+    w.rowsum = (float *)take(B * Mp * 4);
+    w.inv_rowsum = (float *)take(B * Mp * 4);
+    w.inv_colsum = (float *)take(B * Np * 4);
+    w.colpart = (float *)take(B * ns * Np * 4);
+    w.w1p = (float *)take(B * Mp * 4);
+    w.bgrow = (float *)take(B * Np * 4);
+    w.w1 = (float *)take((size_t)B * N1 * 4);
+    w.w2 = (float *)take((size_t)B * N2 * 4);
+    w.rowsumA = (float *)take((size_t)B * N1 * 4);
+    w.pred = (float *)take((size_t)B * N1 * 12);
+    w.G = (float4 *)take(B * Np * 16);
+    w.counters = (int *)take(B * 3 * 4);
+    w.bytes = off;
+    return w;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = PEM_NUM_SMS;
+    }
+    return n;
+}
+
+template <int MODE>
+static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p,
+                       cudaStream_t st) {
+    const size_t smem = sizeof(Smem) + 1024;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE>, smem, &cached)) return rc;
+    const int grid = min(num_sms(), p.B * p.n_strips);
+    fine_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    return pem_launch_status();
+}
+
+static int fill_common(Params &p, int B, int N1, int N2, int C, float temp) {
+    if (C % BK != 0 || C > BK * kMaxKC) return PEM_E_UNSUPPORTED;
+    if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
+    p.B = B; p.R = N1 + 1; p.Cn = N2 + 1;
+    p.Mp = pad128(N1 + 1); p.Np = pad128(N2 + 1);
+    p.n_strips = p.Mp / BM; p.n_tiles = p.Np / BN; p.KC = C / BK;
+    p.temp = temp;
+    p.c1 = 1.4426950408889634f / temp;
+    p.c2 = 1.4426950408889634f / temp;
+    return PEM_OK;
+}
+
+}  // namespace tc
+}  // namespace pem
+
+using namespace pem;
+using namespace pem::tc;
+
+// fine.cu
+namespace pem {
+int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA, const float *w1,
+                     const float *model, int B, int N1, int Nm, float dis_thres, int *counters,
+                     float *R, float *t, float *score, cudaStream_t st);
+}
+
+extern "C" size_t pem_fine_fused_workspace_bytes(int B, int N1, int N2, int C) {
+    if (B <= 0 || N1 <= 0 || N2 <= 0 || C <= 0) return 0;
+    return carve(nullptr, B, N1, N2, C).bytes;
+}
+
+// features already carry the background token in row 0: f1 (B,N1+1,C), f2 (B,N2+1,C)
+extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B, int N1p, int N2p,
+                                         int C, float temp, int normalize, float *atten,
+                                         void *workspace, size_t workspace_bytes,
+                                         pem_stream_t stream) {
+    PEM_REQUIRE_PTR(f1);
+    PEM_REQUIRE_PTR(f2);
+    PEM_REQUIRE_PTR(atten);
+    PEM_REQUIRE(B > 0 && N1p > 0 && N2p > 0 && C > 0, PEM_E_SHAPE);
+    Params p{};
+    if (int rc = fill_common(p, B, N1p - 1, N2p - 1, C, temp)) return rc;
+    PEM_REQUIRE(workspace != nullptr &&
+                    workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1p - 1, N2p - 1, C),
+                PEM_E_WORKSPACE);
+    cudaStream_t st = pem_cu_stream(stream);
+    Ws w = carve(workspace, B, N1p - 1, N2p - 1, C);
+    tc_prep_kernel<<<(B * p.Mp + 7) / 8, 256, 0, st>>>(f1, B, p.R, p.Mp, C, normalize, w.A);
+    tc_prep_kernel<<<(B * p.Np + 7) / 8, 256, 0, st>>>(f2, B, p.Cn, p.Np, C, normalize, w.Bm);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
+    if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
+    p.atten = atten;
+    return launch_pass<kStore>(tmA, tmB, p, st);
+}
+
+extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const float *pts2,
+                              const float *model, int B, int N1, int N2, int C, int Nm, float temp,
+                              float dis_thres, float *R, float *t, float *score, float *w1_out,
+                              float *w2_out, float *rowsum_out, float *pred_out, void *workspace,
+                              size_t workspace_bytes, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(f1);
+    PEM_REQUIRE_PTR(f2);
+    PEM_REQUIRE_PTR(pts1);
+    PEM_REQUIRE_PTR(pts2);
+    PEM_REQUIRE_PTR(model);
+    PEM_REQUIRE_PTR(R);
+    PEM_REQUIRE_PTR(t);
+    PEM_REQUIRE_PTR(score);
+    PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
+    Params p{};
+    if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;
+    PEM_REQUIRE(workspace != nullptr &&
+                    workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
+                PEM_E_WORKSPACE);
+    cudaStream_t st = pem_cu_stream(stream);
+    Ws w = carve(workspace, B, N1, N2, C);
+    float *w1 = w1_out ? w1_out : w.w1;
+    float *rsA = rowsum_out ? rowsum_out : w.rowsumA;
+    float *pred = pred_out ? pred_out : w.pred;
+
+    tc_prep_kernel<<<(B * p.Mp + 7) / 8, 256, 0, st>>>(f1, B, p.R, p.Mp, C, 1, w.A);
+    tc_prep_kernel<<<(B * p.Np + 7) / 8, 256, 0, st>>>(f2, B, p.Cn, p.Np, C, 1, w.Bm);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
+    if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
+
+    // pass 1: softmax statistics
+    p.rowsum = w.rowsum;
+    p.colpart = w.colpart;
+    if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
+    const int mx = max(p.Mp, p.Np);
+    tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+        w.rowsum, w.colpart, p.Mp, p.Np, p.n_strips, w.inv_rowsum, w.inv_colsum);
+    // pass 2: foreground labels
+    p.inv_rowsum = w.inv_rowsum;
+    p.inv_colsum = w.inv_colsum;
+    p.w1 = w.w1p;
+    p.colmaxpart = w.colpart;  // the column partial buffer is free again
+    p.bgrow = w.bgrow;
+    if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
+    tc_finish_label_kernel<<<dim3((p.Np + 255) / 256, B), 256, 0, st>>>(
+        w.colpart, w.bgrow, w.inv_colsum, pts2, p.Cn, p.Np, p.n_strips, w2_out, w.G);
+    tc_compact_w1_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(w.w1p, p.Mp, N1, w1);
+    // pass 3: weighted row sums -> correspondences
+    p.G = w.G;
+    p.rowsumA = rsA;
+    p.pred = pred;
+    if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
+    // weighted Procrustes + pose score (fine.cu)
+    return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
+                            score, st);
+}

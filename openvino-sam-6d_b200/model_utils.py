@@ -46,8 +46,12 @@ def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
     return out_p, out_f
 
 
-def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True):
-    """(B,N,C),(B,M,C) -> (B,N,M) cosine similarity / temp."""
+def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True,
+                               backend="fp32"):
+    """(B,N,C),(B,M,C) -> (B,N,M) cosine similarity / temp.
+
+    backend="fp32": register-tiled FFMA kernel (exact fp32 arithmetic; used for the coarse
+    stage).  backend="tc": split-bf16 tcgen05 GEMM (tensor cores, logits within ~1e-5)."""
     if type != "cosine":
         raise NotImplementedError("only the 'cosine' similarity of the PEM configs is provided")
     f1, f2 = _f32c(feat1, "feat1"), _f32c(feat2, "feat2")
@@ -55,6 +59,15 @@ def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_
     N2 = f2.shape[1]
     out = torch.empty((B, N1, N2), dtype=torch.float32, device=f1.device)
     L = _lib.lib()
+    if backend == "tc":
+        nbytes = L.pem_fine_fused_workspace_bytes(B, N1 - 1, N2 - 1, C)
+        ws = _ws(nbytes, f1.device)
+        with torch.cuda.device(f1.device):
+            _lib.check(L.pem_feature_similarity_tc(f1.data_ptr(), f2.data_ptr(), B, N1, N2, C,
+                                                   float(temp), 1 if normalize_feat else 0,
+                                                   out.data_ptr(), ws.data_ptr(), nbytes,
+                                                   _ext._stream()), "pem_feature_similarity_tc")
+        return out
     nbytes = L.pem_similarity_workspace_bytes(B, N1, N2)
     ws = _ws(nbytes, f1.device)
     with torch.cuda.device(f1.device):
@@ -150,6 +163,40 @@ def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, return_st
                                  R.data_ptr(), t.data_ptr(), score.data_ptr(), p(w1), p(w2),
                                  p(row), p(pred), ws.data_ptr(), nbytes, _ext._stream()),
                    "pem_fine_Rt")
+    if return_stages:
+        return R, t, score, {"w1": w1, "w2": w2, "row": row, "pred": pred}
+    return R, t, score
+
+
+def compute_fine_Rt_fused(feat1, feat2, pts1, pts2, model_pts=None, temp=0.1, dis_thres=0.15,
+                          return_stages=False):
+    """compute_feature_similarity(feat1, feat2, 'cosine', temp, True) followed by
+    compute_fine_Rt(...), fused: the attention matrix never exists in memory.
+    feat1 (B,N1+1,C), feat2 (B,N2+1,C) carry the background token in row 0
+    (fine_point_matching.py:48-51)."""
+    f1, f2 = _f32c(feat1, "feat1"), _f32c(feat2, "feat2")
+    pts1, pts2 = _f32c(pts1, "pts1"), _f32c(pts2, "pts2")
+    model_pts = pts2 if model_pts is None else _f32c(model_pts, "model_pts")
+    B, N1, _ = pts1.shape
+    N2, Nm, C = pts2.shape[1], model_pts.shape[1], f1.shape[2]
+    assert f1.shape[1] == N1 + 1 and f2.shape[1] == N2 + 1
+    dev = pts1.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    R, t, score = torch.empty((B, 3, 3), **f32), torch.empty((B, 3), **f32), torch.empty((B,), **f32)
+    w1 = w2 = row = pred = None
+    if return_stages:
+        w1, w2 = torch.empty((B, N1), **f32), torch.empty((B, N2), **f32)
+        row, pred = torch.empty((B, N1), **f32), torch.empty((B, N1, 3), **f32)
+    L = _lib.lib()
+    nbytes = L.pem_fine_fused_workspace_bytes(B, N1, N2, C)
+    ws = _ws(nbytes, dev)
+    p = lambda x: None if x is None else x.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(L.pem_fine_fused(f1.data_ptr(), f2.data_ptr(), pts1.data_ptr(), pts2.data_ptr(),
+                                    model_pts.data_ptr(), B, N1, N2, C, Nm, float(temp),
+                                    float(dis_thres), R.data_ptr(), t.data_ptr(), score.data_ptr(),
+                                    p(w1), p(w2), p(row), p(pred), ws.data_ptr(), nbytes,
+                                    _ext._stream()), "pem_fine_fused")
     if return_stages:
         return R, t, score, {"w1": w1, "w2": w2, "row": row, "pred": pred}
     return R, t, score

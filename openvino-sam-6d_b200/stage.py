@@ -33,7 +33,7 @@ PE_SCALES = ((0.1, 32), (0.2, 64))  # config/base.yaml:48-49, fine_point_matchin
 class GeometricStage:
     def __init__(self, batch, device, n_dense=2048, n_sparse=196, feat_dim=256, n_model=1024,
                  n_proposal1=6000, n_proposal2=300, temp=0.1, dis_thres=0.15, use_graph=True,
-                 fine_mode="materialised"):
+                 fine_mode="fused"):
         self.B, self.N, self.M, self.C, self.Nm = batch, n_dense, n_sparse, feat_dim, n_model
         self.P1, self.P2, self.temp, self.dis_thres = n_proposal1, n_proposal2, temp, dis_thres
         self.dev = torch.device(device)
@@ -74,7 +74,8 @@ class GeometricStage:
         self.R, self.t, self.score = e((B, 9), **f32), e((B, 3), **f32), e((B,), **f32)
         self.records = torch.zeros((B, 16), **f32)
         nb = max(self.L.pem_similarity_workspace_bytes(B, N + 1, N + 1),
-                 self.L.pem_fine_workspace_bytes(B, N, N), 256)
+                 self.L.pem_fine_workspace_bytes(B, N, N),
+                 self.L.pem_fine_fused_workspace_bytes(B, N, N, C), 256)
         self.ws = torch.empty(nb, dtype=torch.uint8, device=self.dev)
         self.ws_bytes = nb
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -147,12 +148,13 @@ class GeometricStage:
             ck(L.pem_gather_rows(p(self.feats), p(self.fps_idx), 2 * B, N + 1, C, M, (N + 1) * C, C,
                                  p(self.sparse_fine[blk]), 0, st), "gather fine"); n += 1
         # 4. fine
-        ck(L.pem_feature_similarity(p(self.feats[0]), p(self.feats[1]), B, N + 1, N + 1, C, self.temp,
-                                    1, p(self.atten_f), p(self.ws), self.ws_bytes, st),
-           "fine similarity"); n += 3
-        ck(L.pem_fine_Rt(p(self.atten_f), p(self.pts[0]), p(self.pts[1]), p(self.model), B, N, N, Nm,
-                         self.dis_thres, p(self.R), p(self.t), p(self.score), None, None, None, None,
-                         p(self.ws), self.ws_bytes, st), "fine_Rt"); n += 9
+        if self.fine_mode == "fused":
+            ck(L.pem_fine_fused(p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]),
+                                p(self.model), B, N, N, C, Nm, self.temp, self.dis_thres, p(self.R),
+                                p(self.t), p(self.score), None, None, None, None, p(self.ws),
+                                self.ws_bytes, st), "fine_fused"); n += 11
+        else:
+            self._enqueue_fine_materialised(); n += 12
         # 64-byte records
         self.records[:, 0:9].copy_(self.R)
         self.records[:, 9:12].copy_(self.t)
@@ -161,6 +163,18 @@ class GeometricStage:
         self.records[:, 14].copy_(self.instance_ids)
         n += 5
         self.kernels_per_step = n
+
+    def _enqueue_fine_materialised(self):
+        L, st = self.L, self.stream.cuda_stream
+        B, N, C, Nm = self.B, self.N, self.C, self.Nm
+        ck = _lib.check
+        p = lambda t: t.data_ptr()
+        ck(L.pem_feature_similarity(p(self.feats[0]), p(self.feats[1]), B, N + 1, N + 1, C, self.temp,
+                                    1, p(self.atten_f), p(self.ws), self.ws_bytes, st),
+           "fine similarity")
+        ck(L.pem_fine_Rt(p(self.atten_f), p(self.pts[0]), p(self.pts[1]), p(self.model), B, N, N, Nm,
+                         self.dis_thres, p(self.R), p(self.t), p(self.score), None, None, None, None,
+                         p(self.ws), self.ws_bytes, st), "fine_Rt")
 
     def run(self):
         """Enqueue one step on self.stream (no synchronisation)."""

@@ -1,0 +1,36 @@
+"""GPU parity of the tcgen05 (tensor-core) paths: the split-bf16 similarity GEMM and the
+fused fine stage that never materialises the attention matrix, vs the CPU oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,N1,N2,C", [(1, 129, 129, 64), (2, 2049, 2049, 256), (3, 197, 197, 128), (1, 130, 513, 192)])
+def test_similarity_tensorcore(pkg, oracle, dev, B, N1, N2, C):
+    g = torch.Generator().manual_seed(N1 + C)
+    f1, f2 = torch.randn(B, N1, C, generator=g), torch.randn(B, N2, C, generator=g)
+    f1[0, 0] = 0.0
+    want = oracle.feature_similarity(f1, f2, 0.1)
+    got = pkg.model_utils.compute_feature_similarity(f1.to(dev), f2.to(dev), "cosine", 0.1, True, backend="tc").cpu()
+    # logits in [-10,10]; split-bf16 (hi*hi + lo*hi + hi*lo) keeps ~2^-17 relative per product
+    assert (got - want).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("ids,n_dense,feat_dim", [([30, 31], 512, 64), ([32, 36, 37], 2048, 256), ([33, 34, 35], 200, 128)])
+def test_fine_fused(pkg, oracle, dev, ids, n_dense, feat_dim):
+    b = pkg.synth.make_batch(ids, n_dense=n_dense, n_model=1024, feat_dim=feat_dim, n_proposal1=16)
+    bg = b["bg"][:, None, :]
+    f1, f2 = torch.cat([bg, b["dense_fm"]], 1), torch.cat([bg, b["dense_fo"]], 1)
+    atten = oracle.feature_similarity(f1, f2, 0.1)
+    oR, ot, os_, ost = oracle.fine_Rt(atten, b["dense_pm"], b["dense_po"], b["model"])
+    R, t, s, st = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), b["dense_pm"].to(dev),
+                                                        b["dense_po"].to(dev), b["model"].to(dev), 0.1, 0.15,
+                                                        return_stages=True)
+    for k in ("w1", "w2"):  # foreground decisions differ only at near ties
+        assert (st[k].cpu() != ost[k]).float().mean().item() < 2e-3, k
+    assert (st["row"].cpu() - ost["row"]).abs().max().item() < 1e-4
+    assert (st["pred"].cpu() - ost["pred"]).abs().max().item() < 1e-3
+    assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1   # north_star: <= 0.1 deg
+    assert (t.cpu() - ot).abs().max().item() < 1e-4                    # <= 0.1 mm at 1 m radius
+    assert (s.cpu() - os_).abs().max().item() < 2e-3

@@ -245,37 +245,43 @@ def _peaks():
 
 
 def dominant_kernel_roofline(pkg, stage, flush):
-    """The stage's dominant kernel group timed alone (CUDA events on its launch stream)."""
+    """The stage's dominant op -- the fused fine similarity + dual-softmax assignment
+    (3 tcgen05 GEMM passes, fine_tc.cu) -- timed alone with CUDA events on its launch stream.
+    Algorithmic flops = 2*(N+1)^2*C per instance, credited ONCE although the three passes
+    each recompute the product in split-bf16 (3 MMAs per product), i.e. 9x the MMA work."""
     L, st = pkg._lib.lib(), stage.stream.cuda_stream
-    B, N, C = stage.B, stage.N, stage.C
+    B, N, C, Nm = stage.B, stage.N, stage.C, stage.Nm
     p = lambda t: t.data_ptr()
     peaks, which = _peaks()
 
-    def fine_sim():
-        pkg._lib.check(L.pem_feature_similarity(p(stage.feats[0]), p(stage.feats[1]), B, N + 1, N + 1, C,
-                                                stage.temp, 1, p(stage.atten_f), p(stage.ws), stage.ws_bytes,
-                                                st), "fine similarity")
-    iters = 5
+    def fine():
+        pkg._lib.check(L.pem_fine_fused(p(stage.feats[0]), p(stage.feats[1]), p(stage.pts[0]), p(stage.pts[1]),
+                                        p(stage.model), B, N, N, C, Nm, stage.temp, stage.dis_thres, p(stage.R),
+                                        p(stage.t), p(stage.score), None, None, None, None, p(stage.ws),
+                                        stage.ws_bytes, st), "fine_fused")
+    iters = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = 0.0
     with torch.cuda.stream(stage.stream):
-        for _ in range(2):
-            fine_sim()
+        for _ in range(3):
+            fine()
         for _ in range(iters):
             flush.zero_()
             e0.record(stage.stream)
-            fine_sim()
+            fine()
             e1.record(stage.stream)
             stage.stream.synchronize()
             ms += e0.elapsed_time(e1)
     ms /= iters
-    flops = 2.0 * (N + 1) ** 2 * C * B  # SURVEY 8d: 2*(M+1)^2*C per instance, credited once
+    flops = 2.0 * (N + 1) ** 2 * C * B
     achieved = flops / (ms / 1e3) / 1e12
     peak = float(peaks["bf16_tflops"])
-    return {"kernel": "similarity_nt_kernel<128,128,8,8> (fine 2049x2049x256 similarity, fp32 FFMA)",
+    return {"kernel": "pem_fine_fused: tc_prep x2 + fine_tc_kernel<stats|label|wsum> (tcgen05 split-bf16 GEMM, "
+                      "2049x2049x256 per instance, x3 passes) + finish/Procrustes/score kernels",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None, "ms_per_launch": ms,
-            "peak_source": which + ", burst bf16 (kernel timed alone)"}
+            "executed_mma_tflops": achieved * 9.0 * (2176.0 / 2049.0) ** 2,
+            "peak_source": which + ", burst bf16 (op timed alone)"}
 
 
 def scoring_sweep_point(pkg, stage, dev):

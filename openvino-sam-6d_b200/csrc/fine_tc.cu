@@ -5,30 +5,36 @@
 //
 //   prep      normalise rows (F.normalize, eps 1e-12) and split every fp32 value into
 //             bf16 hi + bf16 lo; operands are stored row-padded to a multiple of 128.
-//   GEMM x3   S = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T  (split-bf16: ~2^-17 relative, i.e.
+//   GEMM x3   S = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (split-bf16: ~2^-17 relative, i.e.
 //             fp32-class logits; plain bf16 would move the pose by up to 0.05 deg) with the
 //             accumulator in TMEM, recomputed in three passes whose epilogues reduce
 //             straight out of TMEM:
 //               pass 1  e = exp(s/temp - 1/temp);  row sums, column sums      (softmax stats)
-//               pass 2  foreground labels: row max of e^2/colsum vs the background column,
-//                       column max of e^2/rowsum vs the background row        (MU:321-322)
+//               pass 2  foreground labels (MU:321-322), compared in the log2 domain:
+//                       row max of (2 s/temp - log colsum_j) vs the background column,
+//                       column max of (2 s/temp - log rowsum_i) vs the background row
 //               pass 3  per row: sum_j P_ij w2_j  and  sum_j P_ij w2_j pts2_j  (MU:324-330)
 //             Because features are unit vectors, |s/temp| <= 1/temp, so a fixed shift
 //             replaces the running max of a streaming softmax.
 //   then the weighted Procrustes + pose score kernels of fine.cu.
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: the 128-row A strip (hi+lo, 128 KB) is loaded once per task and
-//               stays resident in shared memory; B tiles stream through a 5-stage ring of
-//               16 KB SWIZZLE_128B chunks (mbarrier full/empty pairs).
+// Kernel anatomy (one persistent CTA per SM, 320 threads).  A task = (instance, 128-COLUMN
+// strip); the CTA walks all 128-row tiles of that strip:
+//   warp 0      TMA producer: the column strip of B' (hi+lo, 128 KB) is loaded once per task
+//               and stays resident in shared memory; row tiles of A' stream through a 5-stage
+//               ring of 16 KB SWIZZLE_128B chunks (mbarrier full/empty pairs).
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=128, K=16,
 //               kind::f16, bf16 in / fp32 accumulate), tcgen05.commit to free ring slots and
 //               to hand the accumulator to the epilogue; two 128-column TMEM accumulators
-//               are double-buffered so MMAs of tile n+1 overlap the epilogue of tile n.
-//   warps 2-5   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread), so
-//               row reductions are thread-local; column reductions use a 31-shuffle
-//               warp transpose-reduce per 32 columns and a 4-warp combine in shared memory.
-// A task = (instance, 128-row strip); tasks are dealt round-robin to the CTAs.
+//               are double-buffered so MMAs of tile m+1 overlap the epilogue of tile m.
+//   warps 2-9   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread, two
+//               warps per lane quadrant, 64 columns each).  Reductions along the columns of
+//               a tile are thread-local and leave as per-(row, strip-half) partials; reductions
+//               along the rows accumulate in 64 registers per thread ACROSS the row tiles of
+//               the task and are folded across lanes only once per task (31-shuffle transpose
+//               reduce per 32 columns + a 4-quadrant combine in shared memory).  Validity
+//               masks are folded into the per-row / per-column constants (+inf offsets).
+// Tasks are dealt round-robin to the CTAs (B*17 tasks at the default shapes).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -41,33 +47,35 @@ constexpr int BM = 128, BN = 128, BK = 64;  // BK bf16 = 128 bytes = one SWIZZLE
 constexpr int kChunkBytes = BM * BK * 2;    // 16 KB
 constexpr int kStages = 5;
 constexpr int kMaxKC = 4;                   // C <= 256
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 256;              // 2 accumulators x 128 columns
+constexpr int kHalfCols = BN / 2;           // columns per epilogue warp
 
 enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3 };
 
 struct Params {
     int B, R, Cn;          // instances, valid rows (N1+1), valid columns (N2+1)
     int Mp, Np;            // padded rows of A' / B' per instance
-    int n_strips, n_tiles; // Mp/128, Np/128
+    int n_mtiles, n_strips; // Mp/128 row tiles, Np/128 column strips
     int KC;                // C / 64
     float temp;            // logits = cos / temp
     float c1, c2;          // e = exp2(cos * c1 - c2)
     // kStore
     float *atten;          // (B,R,Cn)
     // kStats
-    float *rowsum;         // (B,Mp)
-    float *colpart;        // (B,n_strips,Np)
-    // kLabel
-    const float *inv_rowsum;  // (B,Mp)
-    const float *inv_colsum;  // (B,Np)
-    float *w1;                // (B,Mp) indexed by full row index (row 0 = background, unused)
-    float *colmaxpart;        // (B,n_strips,Np): max over rows>=1 of e^2/rowsum
-    float *bgrow;             // (B,Np): e_0j^2 / rowsum_0
+    float *rowpart;        // (B, 2*n_strips, Mp): row sums per column half-strip
+    float *colsum;         // (B,Np), complete
+    // kLabel (log2 domain)
+    const float *lrs;      // (B,Mp)  log2(rowsum_i); +inf for padded rows
+    const float *lcs;      // (B,Np)  log2(colsum_j); +inf for padded columns
+    float *rowmaxpart;     // (B, 2*n_strips, Mp): max over columns j>=1 of the half-strip
+    float *bgcol;          // (B,Mp): value of column 0
+    float *colmax;         // (B,Np): max over rows i>=1, complete
+    float *bgrow;          // (B,Np): value of row 0
     // kWsum
-    const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for j = 0 and padding
-    float *rowsumA;        // (B,R-1)
-    float *pred;           // (B,R-1,3)
+    const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for j = 0 / padding
+    float *rowpart4;       // (B, 2*n_strips, 4, Mp)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -105,6 +113,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t bar
         " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// One leader lane of a fully converged warp (same lane every time for the same mask).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -181,14 +199,19 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
 
 struct Smem {
     // operand buffers first: SWIZZLE_128B needs 1024-byte alignment
-    uint8_t a_hi[kMaxKC][kChunkBytes];
-    uint8_t a_lo[kMaxKC][kChunkBytes];
-    uint8_t b[kStages][kChunkBytes];
-    float col[2][4][BN];   // per-quadrant column partials, double buffered
-    float4 G[2][BN];       // per-tile column constants (kLabel: inv_colsum in .x; kWsum: G)
-    uint64_t full[kStages], empty[kStages], a_full, a_empty, tmem_full[2], tmem_empty[2];
+    uint8_t b_hi[kMaxKC][kChunkBytes];   // resident column strip of B'
+    uint8_t b_lo[kMaxKC][kChunkBytes];
+    uint8_t a[kStages][kChunkBytes];     // streamed row-tile chunks of A' (hi or lo)
+    float4 G[BN];                        // per-column constants of the task (kWsum)
+    float colc[BN];                      // per-column constants of the task (kLabel: log2 colsum)
+    float colred[4][BN];                 // per-quadrant column results
+    uint64_t full[kStages], empty[kStages], b_full, b_empty, tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
+
+__device__ __forceinline__ void epi_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -204,11 +227,11 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(smem_u32(&sm.full[s]), 1);
             mbar_init(smem_u32(&sm.empty[s]), 1);
         }
-        mbar_init(smem_u32(&sm.a_full), 1);
-        mbar_init(smem_u32(&sm.a_empty), 1);
+        mbar_init(smem_u32(&sm.b_full), 1);
+        mbar_init(smem_u32(&sm.b_empty), 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&sm.tmem_full[a]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[a]), 4);  // one arrival per epilogue warp
+            mbar_init(smem_u32(&sm.tmem_empty[a]), kEpiWarps);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -224,152 +247,179 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
+    // Both single-issuer roles run with warp-uniform control flow (all 32 lanes loop and wait);
+    // only the instruction issue is predicated on an elected lane, so addresses and
+    // descriptors stay in uniform registers (no per-instruction uniformisation loops).
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, a_phase = 0;
-            for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-                const int b = task / p.n_strips, s = task - b * p.n_strips;
-                mbar_wait(smem_u32(&sm.a_empty), a_phase ^ 1);
-                a_phase ^= 1;
-                mbar_expect_tx(smem_u32(&sm.a_full), 2u * p.KC * kChunkBytes);
-                const int rowA = b * p.Mp + s * BM;
+        int stage = 0;
+        uint32_t phase = 0, b_phase = 0;
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            const int b = task / p.n_strips, n = task - b * p.n_strips;
+            mbar_wait(smem_u32(&sm.b_empty), b_phase ^ 1);
+            b_phase ^= 1;
+            const int rowB = b * p.Np + n * BN;
+            if (elect_one()) {
+                mbar_expect_tx(smem_u32(&sm.b_full), 2u * p.KC * kChunkBytes);
                 for (int kc = 0; kc < p.KC; ++kc) {
-                    tma_load_2d(&tmA, smem_u32(&sm.a_full), smem_u32(sm.a_hi[kc]), kc * BK, rowA);
-                    tma_load_2d(&tmA, smem_u32(&sm.a_full), smem_u32(sm.a_lo[kc]), kc * BK,
-                                p.B * p.Mp + rowA);
+                    tma_load_2d(&tmB, smem_u32(&sm.b_full), smem_u32(sm.b_hi[kc]), kc * BK, rowB);
+                    tma_load_2d(&tmB, smem_u32(&sm.b_full), smem_u32(sm.b_lo[kc]), kc * BK,
+                                p.B * p.Np + rowB);
                 }
-                for (int n = 0; n < p.n_tiles; ++n) {
-                    const int rowB = b * p.Np + n * BN;
-                    for (int kc = 0; kc < p.KC; ++kc) {
-                        for (int hl = 0; hl < 2; ++hl) {
-                            mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+            }
+            __syncwarp();
+            for (int m = 0; m < p.n_mtiles; ++m) {
+                const int rowA = b * p.Mp + m * BM;
+                for (int kc = 0; kc < p.KC; ++kc) {
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl) {
+                        mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+                        if (elect_one()) {
                             mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
-                            tma_load_2d(&tmB, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]),
-                                        kc * BK, hl * p.B * p.Np + rowB);
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            tma_load_2d(&tmA, smem_u32(&sm.full[stage]), smem_u32(sm.a[stage]), kc * BK,
+                                        hl * p.B * p.Mp + rowA);
                         }
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, a_phase = 0, acc_phase = 0;
-            for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-                mbar_wait(smem_u32(&sm.a_full), a_phase);
-                a_phase ^= 1;
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, b_phase = 0, acc_phase = 0;
+        // descriptor high word is constant; the low word is (address >> 4) | LBO
+        const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
+        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            mbar_wait(smem_u32(&sm.b_full), b_phase);
+            b_phase ^= 1;
+            tc_fence_after();
+            for (int m = 0; m < p.n_mtiles; ++m) {
+                mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
                 tc_fence_after();
-                for (int n = 0; n < p.n_tiles; ++n) {
-                    mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
+                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < p.KC; ++kc) {
+                    const uint64_t bh = desc(smem_u32(sm.b_hi[kc])), bl = desc(smem_u32(sm.b_lo[kc]));
+                    // A_hi chunk: A_hi*B_hi + A_hi*B_lo
+                    mbar_wait(smem_u32(&sm.full[stage]), phase);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-                    uint32_t accumulate = 0;
-                    for (int kc = 0; kc < p.KC; ++kc) {
-                        const uint32_t ah = smem_u32(sm.a_hi[kc]), al = smem_u32(sm.a_lo[kc]);
-                        // B_hi chunk: A_hi*B_hi + A_lo*B_hi
-                        mbar_wait(smem_u32(&sm.full[stage]), phase);
-                        tc_fence_after();
-                        uint32_t bs = smem_u32(sm.b[stage]);
+                    uint64_t ad = desc(smem_u32(sm.a[stage]));
+                    if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t bd = umma_desc_sw128(bs + k * 32);
-                            tc_mma_bf16(d, umma_desc_sw128(ah + k * 32), bd, kIdesc, accumulate);
-                            accumulate = 1;
-                            tc_mma_bf16(d, umma_desc_sw128(al + k * 32), bd, kIdesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) {  // +32 bytes per K=16 step: +2 in the address field
+                            tc_mma_bf16(d, ad + 2 * k, bh + 2 * k, kIdesc, (kc | k) != 0);
+                            tc_mma_bf16(d, ad + 2 * k, bl + 2 * k, kIdesc, 1);
                         }
                         tc_commit(smem_u32(&sm.empty[stage]));
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
-                        // B_lo chunk: A_hi*B_lo
-                        mbar_wait(smem_u32(&sm.full[stage]), phase);
-                        tc_fence_after();
-                        bs = smem_u32(sm.b[stage]);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            tc_mma_bf16(d, umma_desc_sw128(ah + k * 32), umma_desc_sw128(bs + k * 32),
-                                        kIdesc, 1);
-                        tc_commit(smem_u32(&sm.empty[stage]));
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(smem_u32(&sm.tmem_full[acc]));  // accumulator ready for the epilogue
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    // A_lo chunk: A_lo*B_hi
+                    mbar_wait(smem_u32(&sm.full[stage]), phase);
+                    tc_fence_after();
+                    ad = desc(smem_u32(sm.a[stage]));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) tc_mma_bf16(d, ad + 2 * k, bh + 2 * k, kIdesc, 1);
+                        tc_commit(smem_u32(&sm.empty[stage]));
+                        if (kc == p.KC - 1) tc_commit(smem_u32(&sm.tmem_full[acc]));  // accumulator ready
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(smem_u32(&sm.a_empty));  // all MMAs reading the A strip have retired
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (elect_one()) tc_commit(smem_u32(&sm.b_empty));  // all MMAs reading the B strip retired
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ================================ epilogue ====================================
-        const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32)
-        const int et = quad * 32 + lane;      // row of the 128-row tile owned by this thread
-        const int ep_tid = (warp - 2) * 32 + lane;  // 0..127, used for column-indexed work
-        int acc = 0, cbuf = 0;
+        const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
+        const int half = (warp - 2) >> 2;          // columns [64*half, 64*half+64) of the tile
+        const int et = quad * 32 + lane;           // row of the 128-row tile owned by this thread
+        const int ep_tid = (warp - 2) * 32 + lane; // 0..255
+        const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
+        int acc = 0;
         uint32_t acc_phase = 0;
         for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-            const int b = task / p.n_strips, s = task - b * p.n_strips;
-            const int gi = s * BM + et;
-            const bool row_ok = gi < p.R;
-            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;  // row accumulators (mode dependent)
-            float row_const = 0.f, bg_val = 0.f;
-            if (MODE == kLabel) {
-                row_const = row_ok ? p.inv_rowsum[(size_t)b * p.Mp + gi] : 0.f;
-                r0 = -1.f;
+            const int b = task / p.n_strips, n = task - b * p.n_strips;
+            const int j0 = n * BN + half * kHalfCols;     // first global column of this warp
+            const int ncols = min(kHalfCols, p.Cn - j0);  // valid columns (<= 0: none)
+            float colacc[kHalfCols];
+#pragma unroll
+            for (int q = 0; q < kHalfCols; ++q) colacc[q] = (MODE == kLabel) ? -INFINITY : 0.f;
+            // per-column constants of the task
+            if (MODE == kLabel && ep_tid < BN) {
+                const int j = n * BN + ep_tid;
+                // excluded from the row max: padded columns and the background column 0
+                sm.colc[ep_tid] = (j >= 1 && j < p.Cn) ? p.lcs[(size_t)b * p.Np + j] : INFINITY;
             }
-            for (int n = 0; n < p.n_tiles; ++n) {
-                const int j0 = n * BN;
-                if (MODE == kLabel || MODE == kWsum) {
-                    // stage this tile's per-column constants (double buffered by tile parity)
-                    const size_t cj = (size_t)b * p.Np + j0 + ep_tid;
-                    if (MODE == kLabel) sm.G[cbuf][ep_tid] = make_float4(p.inv_colsum[cj], 0.f, 0.f, 0.f);
-                    else sm.G[cbuf][ep_tid] = p.G[cj];
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
+            if (MODE == kWsum && ep_tid < BN) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * BN + ep_tid];
+            if (MODE == kLabel || MODE == kWsum) epi_barrier();
+            const float lcs0 = (MODE == kLabel && j0 == 0) ? p.lcs[(size_t)b * p.Np] : 0.f;
+
+            for (int m = 0; m < p.n_mtiles; ++m) {
+                const int gi = m * BM + et;
+                const bool row_ok = gi < p.R;
+                float rowc = 0.f;  // per-row constant of this tile
+                if (MODE == kStats) rowc = row_ok ? kc2 : INFINITY;             // e = 0 for padded rows
+                if (MODE == kLabel) rowc = (row_ok && gi >= 1) ? p.lrs[(size_t)b * p.Mp + gi] : INFINITY;
+                float r0 = (MODE == kLabel) ? -INFINITY : 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
                 mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+                for (int c = 0; c < kHalfCols / 32; ++c) {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                    const int jc = j0 + c * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                  (uint32_t)(acc * BN + half * kHalfCols + c * 32), v);
                     if (MODE == kStore) {
                         if (row_ok) {
-                            float *dst = p.atten + ((size_t)b * p.R + gi) * p.Cn + jc;
+                            float *dst = p.atten + ((size_t)b * p.R + gi) * p.Cn + j0 + c * 32;
 #pragma unroll
                             for (int q = 0; q < 32; ++q)
-                                if (jc + q < p.Cn) dst[q] = __fdiv_rn(v[q], p.temp);
+                                if (c * 32 + q < ncols) dst[q] = __fdiv_rn(v[q], ktemp);
                         }
                     } else if (MODE == kStats) {
+                        if (ncols >= kHalfCols) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const float e = (row_ok && jc + q < p.Cn) ? ex2(fmaf(v[q], p.c1, -p.c2)) : 0.f;
-                            r0 += e;
-                            v[q] = e;
+                            for (int q = 0; q < 32; ++q) {
+                                const float e = ex2(fmaf(v[q], kc1, -rowc));
+                                r0 += e;
+                                colacc[c * 32 + q] += e;
+                            }
+                        } else {  // last strip: mask padded columns
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                const float e = (c * 32 + q < ncols) ? ex2(fmaf(v[q], kc1, -rowc)) : 0.f;
+                                r0 += e;
+                                colacc[c * 32 + q] += e;
+                            }
                         }
-                        sm.col[cbuf][quad][c * 32 + lane] = warp_transpose_reduce<false>(v);
                     } else if (MODE == kLabel) {
+                        const float c2x = kc2x;
+                        if (gi == 0) {  // background row: record it, keep it out of the column max
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (c * 32 + q < ncols)
+                                    p.bgrow[(size_t)b * p.Np + j0 + c * 32 + q] =
+                                        fmaf(v[q], c2x, -p.lrs[(size_t)b * p.Mp]);
+                        }
+                        if (c == 0 && j0 == 0 && row_ok)  // background column of this row
+                            p.bgcol[(size_t)b * p.Mp + gi] = fmaf(v[0], c2x, -lcs0);
 #pragma unroll
                         for (int q = 0; q < 32; ++q) {
-                            const bool ok = row_ok && jc + q < p.Cn;
-                            const float e = ok ? ex2(fmaf(v[q], p.c1, -p.c2)) : 0.f;
-                            const float u = e * e;
-                            // row side: e^2 / colsum_j over j >= 1, and the background column j = 0
-                            const float pr = u * sm.G[cbuf][c * 32 + q].x;
-                            if (jc + q == 0) bg_val = pr; else r0 = fmaxf(r0, ok ? pr : -1.f);
-                            // column side: e^2 / rowsum_i over rows i >= 1
-                            v[q] = (ok && gi >= 1) ? u * row_const : -1.f;
-                            if (gi == 0 && jc + q < p.Cn) p.bgrow[(size_t)b * p.Np + jc + q] = u * row_const;
+                            const float x = v[q] * c2x;
+                            r0 = fmaxf(r0, x - sm.colc[half * kHalfCols + c * 32 + q]);
+                            colacc[c * 32 + q] = fmaxf(colacc[c * 32 + q], x - rowc);
                         }
-                        sm.col[cbuf][quad][c * 32 + lane] = warp_transpose_reduce<true>(v);
                     } else {  // kWsum
 #pragma unroll
                         for (int q = 0; q < 32; ++q) {
-                            const float e = ex2(fmaf(v[q], p.c1, -p.c2));
+                            const float e = ex2(fmaf(v[q], kc1, -kc2));
                             const float u = e * e;
-                            const float4 g = sm.G[cbuf][c * 32 + q];  // zero for j = 0 / padding / w2 = 0
+                            const float4 g = sm.G[half * kHalfCols + c * 32 + q];
                             r0 = fmaf(u, g.w, r0);
                             r1 = fmaf(u, g.x, r1);
                             r2 = fmaf(u, g.y, r2);
@@ -382,34 +432,35 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (MODE == kStats || MODE == kLabel) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    float x = sm.col[cbuf][0][ep_tid];
+                // per-(row, half-strip) partials: consecutive lanes = consecutive rows
+                const size_t pr = ((size_t)b * 2 * p.n_strips + 2 * n + half);
+                if (MODE == kStats) p.rowpart[pr * p.Mp + gi] = r0;
+                if (MODE == kLabel) p.rowmaxpart[pr * p.Mp + gi] = r0;
+                if (MODE == kWsum) {
+                    float *dst = p.rowpart4 + pr * 4 * p.Mp + gi;
+                    dst[0] = r0; dst[p.Mp] = r1; dst[2 * p.Mp] = r2; dst[3 * p.Mp] = r3;
+                }
+            }
+            // fold the column accumulators across the 32 lanes, then across the 4 quadrants
+            if (MODE == kStats || MODE == kLabel) {
+#pragma unroll
+                for (int c = 0; c < kHalfCols / 32; ++c) {
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = colacc[c * 32 + q];
+                    sm.colred[quad][half * kHalfCols + c * 32 + lane] =
+                        warp_transpose_reduce<MODE == kLabel>(v);
+                }
+                epi_barrier();
+                if (ep_tid < BN && n * BN + ep_tid < p.Cn) {
+                    float x = sm.colred[0][ep_tid];
 #pragma unroll
                     for (int w = 1; w < 4; ++w)
-                        x = (MODE == kLabel) ? fmaxf(x, sm.col[cbuf][w][ep_tid]) : x + sm.col[cbuf][w][ep_tid];
-                    float *dst = (MODE == kLabel) ? p.colmaxpart : p.colpart;
-                    dst[((size_t)b * p.n_strips + s) * p.Np + j0 + ep_tid] = x;
-                }
-                cbuf ^= 1;
-            }
-            // per-row results of this task
-            if (MODE == kStats) {
-                p.rowsum[(size_t)b * p.Mp + gi] = r0;  // 0 for padded rows
-            } else if (MODE == kLabel) {
-                if (row_ok && gi >= 1) p.w1[(size_t)b * p.Mp + gi] = (r0 > bg_val) ? 1.f : 0.f;
-            } else if (MODE == kWsum) {
-                if (row_ok && gi >= 1) {
-                    const float f = p.w1[(size_t)b * p.Mp + gi] * p.inv_rowsum[(size_t)b * p.Mp + gi];
-                    const float sA = r0 * f;
-                    const size_t ri = (size_t)b * (p.R - 1) + gi - 1;
-                    p.rowsumA[ri] = sA;                      // assignment_score (MU:330)
-                    const float inv = 1.0f / (sA + 1e-6f);   // MU:327
-                    p.pred[ri * 3 + 0] = r1 * f * inv;
-                    p.pred[ri * 3 + 1] = r2 * f * inv;
-                    p.pred[ri * 3 + 2] = r3 * f * inv;
+                        x = (MODE == kLabel) ? fmaxf(x, sm.colred[w][ep_tid]) : x + sm.colred[w][ep_tid];
+                    ((MODE == kLabel) ? p.colmax : p.colsum)[(size_t)b * p.Np + n * BN + ep_tid] = x;
                 }
             }
+            epi_barrier();  // shared per-task constants / colred are reused by the next task
         }
     }
 
@@ -452,50 +503,76 @@ tc_prep_kernel(const float *__restrict__ f, int B, int rows, int rows_p, int C, 
     }
 }
 
-// after pass 1: 1/rowsum, 1/colsum (column partials summed in strip order: deterministic)
+// after pass 1: row sums from their per-half-strip partials (fixed order: deterministic),
+// reciprocals and log2 of both sums; +inf logs mark padded rows / columns
 __global__ void __launch_bounds__(256)
-tc_finish_stats_kernel(const float *__restrict__ rowsum, const float *__restrict__ colpart, int Mp,
-                       int Np, int n_strips, float *__restrict__ inv_rowsum,
-                       float *__restrict__ inv_colsum) {
+tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restrict__ colsum, int R,
+                       int Cn, int Mp, int Np, int n_part, float *__restrict__ inv_rowsum,
+                       float *__restrict__ lrs, float *__restrict__ inv_colsum,
+                       float *__restrict__ lcs) {
     const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < Mp) {
-        const float r = rowsum[(size_t)b * Mp + k];
-        inv_rowsum[(size_t)b * Mp + k] = r > 0.f ? 1.0f / r : 0.f;
+        float s = 0.f;
+        for (int t = 0; t < n_part; ++t) s += rowpart[((size_t)b * n_part + t) * Mp + k];
+        const bool ok = k < R && s > 0.f;
+        inv_rowsum[(size_t)b * Mp + k] = ok ? 1.0f / s : 0.f;
+        lrs[(size_t)b * Mp + k] = ok ? log2f(s) : INFINITY;
     }
     if (k < Np) {
-        float s = 0.f;
-        for (int t = 0; t < n_strips; ++t) s += colpart[((size_t)b * n_strips + t) * Np + k];
-        inv_colsum[(size_t)b * Np + k] = s > 0.f ? 1.0f / s : 0.f;
+        const float s = k < Cn ? colsum[(size_t)b * Np + k] : 0.f;
+        const bool ok = k < Cn && s > 0.f;
+        inv_colsum[(size_t)b * Np + k] = ok ? 1.0f / s : 0.f;
+        lcs[(size_t)b * Np + k] = ok ? log2f(s) : INFINITY;
     }
 }
 
-// after pass 2: w2_j and the per-column constants of pass 3
+// after pass 2: w1_i, w2_j and the per-column constants of pass 3
 __global__ void __launch_bounds__(256)
-tc_finish_label_kernel(const float *__restrict__ colmaxpart, const float *__restrict__ bgrow,
-                       const float *__restrict__ inv_colsum, const float *__restrict__ pts2, int Cn,
-                       int Np, int n_strips, float *__restrict__ w2_out, float4 *__restrict__ G) {
-    const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= Np) return;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j >= 1 && j < Cn) {
-        float m = -1.f;
-        for (int t = 0; t < n_strips; ++t) m = fmaxf(m, colmaxpart[((size_t)b * n_strips + t) * Np + j]);
-        const bool fg = m > bgrow[(size_t)b * Np + j];  // label2 > 0 (MU:322)
-        if (w2_out) w2_out[(size_t)b * (Cn - 1) + j - 1] = fg ? 1.f : 0.f;
-        if (fg) {
-            const float ic = inv_colsum[(size_t)b * Np + j];
-            const float *q = pts2 + ((size_t)b * (Cn - 1) + j - 1) * 3;
-            g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__restrict__ bgcol,
+                       const float *__restrict__ colmax, const float *__restrict__ bgrow,
+                       const float *__restrict__ inv_colsum, const float *__restrict__ pts2, int R,
+                       int Cn, int Mp, int Np, int n_part, float *__restrict__ w1 /* (B,R-1) */,
+                       float *__restrict__ w2_out /* (B,Cn-1) or null */, float4 *__restrict__ G) {
+    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 1 && k < R) {
+        float m = -INFINITY;
+        for (int t = 0; t < n_part; ++t) m = fmaxf(m, rowmaxpart[((size_t)b * n_part + t) * Mp + k]);
+        w1[(size_t)b * (R - 1) + k - 1] = m > bgcol[(size_t)b * Mp + k] ? 1.f : 0.f;  // label1 > 0
+    }
+    if (k < Np) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k >= 1 && k < Cn) {
+            const bool fg = colmax[(size_t)b * Np + k] > bgrow[(size_t)b * Np + k];  // label2 > 0
+            if (w2_out) w2_out[(size_t)b * (Cn - 1) + k - 1] = fg ? 1.f : 0.f;
+            if (fg) {
+                const float ic = inv_colsum[(size_t)b * Np + k];
+                const float *q = pts2 + ((size_t)b * (Cn - 1) + k - 1) * 3;
+                g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+            }
         }
+        G[(size_t)b * Np + k] = g;
     }
-    G[(size_t)b * Np + j] = g;
 }
 
-// copy w1 (indexed by full row, padded) into the dense (B,N1) layout the scorer expects
+// after pass 3: assignment_score and the soft correspondences (MU:324-330)
 __global__ void __launch_bounds__(256)
-tc_compact_w1_kernel(const float *__restrict__ w1p, int Mp, int N1, float *__restrict__ w1) {
-    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N1) w1[(size_t)b * N1 + i] = w1p[(size_t)b * Mp + i + 1];
+tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restrict__ inv_rowsum,
+                      const float *__restrict__ w1, int R, int Mp, int n_part,
+                      float *__restrict__ rowsumA, float *__restrict__ pred) {
+    const int b = blockIdx.y, i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < n_part; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] += rowpart4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
+    const size_t ri = (size_t)b * (R - 1) + i - 1;
+    const float f = w1[ri] * inv_rowsum[(size_t)b * Mp + i];
+    const float sA = a[0] * f;
+    rowsumA[ri] = sA;                       // assignment_score (MU:330)
+    const float inv = 1.0f / (sA + 1e-6f);  // MU:327
+    pred[ri * 3 + 0] = a[1] * f * inv;
+    pred[ri * 3 + 1] = a[2] * f * inv;
+    pred[ri * 3 + 2] = a[3] * f * inv;
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -532,7 +609,8 @@ static int make_operand_map(CUtensorMap *map, const void *base, size_t rows, int
 
 struct Ws {
     __nv_bfloat16 *A, *Bm;
-    float *rowsum, *inv_rowsum, *inv_colsum, *colpart, *w1p, *bgrow, *w1, *w2, *rowsumA, *pred;
+    float *rowpart;  // (B, 2*n_strips, 4, Mp): the largest of the per-pass row partial layouts
+    float *colA, *colB, *inv_rowsum, *lrs, *inv_colsum, *lcs, *bgcol, *w1, *w2, *rowsumA, *pred;
     float4 *G;
     int *counters;
     size_t bytes;
@@ -541,7 +619,7 @@ struct Ws {
 static int pad128(int x) { return (x + 127) / 128 * 128; }
 
 static Ws carve(void *base, int B, int N1, int N2, int C) {
-    const size_t Mp = pad128(N1 + 1), Np = pad128(N2 + 1), ns = Mp / 128;
+    const size_t Mp = pad128(N1 + 1), Np = pad128(N2 + 1), ns = Np / 128;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t o = off;
@@ -551,12 +629,14 @@ static Ws carve(void *base, int B, int N1, int N2, int C) {
     Ws w;
     w.A = (__nv_bfloat16 *)take(2 * B * Mp * C * 2);
     w.Bm = (__nv_bfloat16 *)take(2 * B * Np * C * 2);
-    w.rowsum = (float *)take(B * Mp * 4);
+    w.rowpart = (float *)take(B * 2 * ns * 4 * Mp * 4);
+    w.colA = (float *)take(B * Np * 4);   // colsum, then colmax
+    w.colB = (float *)take(B * Np * 4);   // bgrow
     w.inv_rowsum = (float *)take(B * Mp * 4);
+    w.lrs = (float *)take(B * Mp * 4);
     w.inv_colsum = (float *)take(B * Np * 4);
-    w.colpart = (float *)take(B * ns * Np * 4);
-    w.w1p = (float *)take(B * Mp * 4);
-    w.bgrow = (float *)take(B * Np * 4);
+    w.lcs = (float *)take(B * Np * 4);
+    w.bgcol = (float *)take(B * Mp * 4);
     w.w1 = (float *)take((size_t)B * N1 * 4);
     w.w2 = (float *)take((size_t)B * N2 * 4);
     w.rowsumA = (float *)take((size_t)B * N1 * 4);
@@ -594,7 +674,7 @@ static int fill_common(Params &p, int B, int N1, int N2, int C, float temp) {
     if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
     p.B = B; p.R = N1 + 1; p.Cn = N2 + 1;
     p.Mp = pad128(N1 + 1); p.Np = pad128(N2 + 1);
-    p.n_strips = p.Mp / BM; p.n_tiles = p.Np / BN; p.KC = C / BK;
+    p.n_mtiles = p.Mp / BM; p.n_strips = p.Np / BN; p.KC = C / BK;
     p.temp = temp;
     p.c1 = 1.4426950408889634f / temp;
     p.c2 = 1.4426950408889634f / temp;
@@ -675,28 +755,31 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
 
-    // pass 1: softmax statistics
-    p.rowsum = w.rowsum;
-    p.colpart = w.colpart;
-    if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
+    const int n_part = 2 * p.n_strips;
     const int mx = max(p.Mp, p.Np);
+    // pass 1: softmax statistics
+    p.rowpart = w.rowpart;
+    p.colsum = w.colA;
+    if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
     tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-        w.rowsum, w.colpart, p.Mp, p.Np, p.n_strips, w.inv_rowsum, w.inv_colsum);
+        w.rowpart, w.colA, p.R, p.Cn, p.Mp, p.Np, n_part, w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
     // pass 2: foreground labels
-    p.inv_rowsum = w.inv_rowsum;
-    p.inv_colsum = w.inv_colsum;
-    p.w1 = w.w1p;
-    p.colmaxpart = w.colpart;  // the column partial buffer is free again
-    p.bgrow = w.bgrow;
+    p.lrs = w.lrs;
+    p.lcs = w.lcs;
+    p.rowmaxpart = w.rowpart;
+    p.bgcol = w.bgcol;
+    p.colmax = w.colA;
+    p.bgrow = w.colB;
     if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
-    tc_finish_label_kernel<<<dim3((p.Np + 255) / 256, B), 256, 0, st>>>(
-        w.colpart, w.bgrow, w.inv_colsum, pts2, p.Cn, p.Np, p.n_strips, w2_out, w.G);
-    tc_compact_w1_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(w.w1p, p.Mp, N1, w1);
+    tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+        w.rowpart, w.bgcol, w.colA, w.colB, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part, w1,
+        w2_out, w.G);
     // pass 3: weighted row sums -> correspondences
     p.G = w.G;
-    p.rowsumA = rsA;
-    p.pred = pred;
+    p.rowpart4 = w.rowpart;
     if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
+    tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(w.rowpart, w.inv_rowsum, w1, p.R,
+                                                                     p.Mp, n_part, rsA, pred);
     // weighted Procrustes + pose score (fine.cu)
     return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
                             score, st);

@@ -106,7 +106,7 @@ def cpu_arm(args, n_instances, reps):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n = 2
+    n = int(os.environ.get("PEM_BENCH_CPU_INSTANCES", 2))
     r = cpu_arm(args, n, args.warmup + args.steps)
     timed = r["seconds"][args.warmup:]
     ms = 1e3 * sum(timed) / len(timed)
@@ -137,12 +137,13 @@ def run_b200(args, rank, world, local_rank):
     stage = pkg.stage.GeometricStage(B, dev)
     stage.instance_ids.copy_(torch.tensor(ids, dtype=torch.float32))
     stage.load(host)
-    gathered = torch.zeros((world * B, 16), dtype=torch.float32, device=dev)
+    gathered = [stage.records]
 
     def step_collective():
+        # the only multi-GPU traffic: one all-gather of the 64-byte pose records (NCCL over NVLink)
         if world > 1:
             with torch.cuda.stream(stage.stream):
-                dist.all_gather_into_tensor(gathered, stage.records)
+                gathered[0] = pkg.parallel.gather_records(stage.records, world * B, world)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -189,7 +190,7 @@ def run_b200(args, rank, world, local_rank):
         stage.run()
         step_collective()
         with torch.cuda.stream(stage.stream):
-            rec_host.copy_(gathered if world > 1 else stage.records, non_blocking=True)
+            rec_host.copy_(gathered[0], non_blocking=True)
         stage.stream.synchronize()
 
     for _ in range(max(W, 3)):

@@ -140,21 +140,27 @@ def test_coarse_end_to_end_S5(pkg, oracle, dev):
       * our overall winner is as good as the reference's (score within 15 %)."""
     ids = [20, 21, 22, 23]
     b, sp, tp, atten = _coarse_inputs(pkg, oracle, ids)
-    oR, ot, ost = oracle.coarse_Rt(atten, sp, tp, b["model"], 6000, 300, b["rand"])
-    R, t, st = pkg.model_utils.compute_coarse_Rt(atten.to(dev), sp.to(dev), tp.to(dev), b["model"].to(dev), 6000,
-                                                 300, rand=b["rand"].to(dev), return_stages=True)
+    check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, b["model"], 6000, 300, b["rand"])
+
+
+def check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, model, P1, P2, rand, min_common=20):
+    atten, sp, tp, model, rand = (torch.as_tensor(x) for x in (atten, sp, tp, model, rand))
+    n_inst = sp.shape[0]
+    oR, ot, ost = oracle.coarse_Rt(atten, sp, tp, model, P1, P2, rand)
+    R, t, st = pkg.model_utils.compute_coarse_Rt(atten.to(dev), sp.to(dev), tp.to(dev), model.to(dev), P1,
+                                                 P2, rand=rand.to(dev), return_stages=True)
     st = {k: v.cpu() for k, v in st.items()}
     S = torch.linalg.svdvals(ost["H"].double())
     posed = (S[..., 1] / S[..., 0].clamp_min(1e-30)) > 1e-3
     n_same_winner = 0
-    for i in range(len(ids)):
+    for i in range(n_inst):
         ours, theirs = st["sel"][i].long(), ost["top"][i]
         assert len(set(ours.tolist()) ^ set(theirs.tolist())) <= 8
         o_score = dict(zip(theirs.tolist(), ost["scores"][i].tolist()))
         g_score = dict(zip(ours.tolist(), st["scores"][i].tolist()))
         same_draw = (st["corr"][i].long() == ost["idx"][i]).view(-1, 3).all(1)
         common = [h for h in ours.tolist() if h in o_score and posed[i, h] and same_draw[h]]
-        assert len(common) >= 20
+        assert len(common) >= min_common
         for h in common:
             assert (st["R"][i, h].view(3, 3) - ost["R"][i, h]).abs().max().item() < 2e-3   # cond <= 1e3
             assert abs(g_score[h] - o_score[h]) / o_score[h] < 2e-2
@@ -162,12 +168,17 @@ def test_coarse_end_to_end_S5(pkg, oracle, dev):
         best_g = max(common, key=lambda h: g_score[h])
         second = sorted((o_score[h] for h in common), reverse=True)[1]
         assert best_o == best_g or (o_score[best_o] - second) / o_score[best_o] < 2e-2, (i, best_o, best_g)
-        n_same_winner += int(st["proposal_id"][i].item() == ost["proposal_id"][i].item())
+        same = st["proposal_id"][i].item() == ost["proposal_id"][i].item()
+        n_same_winner += int(same)
+        if same and posed[i, ost["proposal_id"][i]]:  # identical well-posed winner -> pose within tolerance
+            assert oracle.rotation_angle_deg(R[i].cpu(), oR[i]).item() < 0.1
+            assert (t[i].cpu() - ot[i]).abs().max().item() < 1e-4
         assert abs(st["scores"][i].max().item() - ost["scores"][i].max().item()) / ost["scores"][i].max().item() < 0.15
-    print("coarse winner identical on %d of %d instances (the rest: degenerate-triplet lottery)" % (n_same_winner, len(ids)))
+    print("coarse winner identical on %d of %d instances (the rest: degenerate-triplet lottery)" % (n_same_winner, n_inst))
     # correspondences drawn from OUR cdf differ from the oracle's only for draws that land
     # within rounding distance of a bin edge
     assert (st["corr"].long() != ost["idx"]).float().mean().item() < 0.005
+    return oR, ot
 
 
 def test_coarse_selection_and_argmax_given_reference_hypotheses(pkg, oracle, dev):

@@ -1,0 +1,75 @@
+"""CPU: host-side logic that needs no GPU -- synthetic instances, the pose-record sharding and
+gather of the multi-GPU path (world_size 2 over gloo), bench.py's reference arm plumbing."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+from conftest import ROOT
+
+
+def test_synth_is_deterministic_and_shaped(pkg):
+    a = pkg.synth.make_batch([3, 4], n_dense=256, n_model=64, feat_dim=32, n_proposal1=10)
+    b = pkg.synth.make_batch([3, 4], n_dense=256, n_model=64, feat_dim=32, n_proposal1=10)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert a["dense_pm"].shape == (2, 256, 3) and a["dense_fm"].shape == (2, 256, 32)
+    assert a["model"].shape == (2, 64, 3) and a["rand"].shape == (2, 30) and a["bg"].shape == (2, 32)
+    assert abs(a["dense_po"].norm(dim=2).max().item() - 1.0) < 1e-5          # radius-normalised template
+    assert (torch.det(a["gt_R"]) - 1).abs().max() < 1e-5
+    c = pkg.synth.make_batch([4], n_dense=256, n_model=64, feat_dim=32, n_proposal1=10)
+    assert torch.equal(c["dense_pm"][0], a["dense_pm"][1])                   # one seed per instance id
+
+
+def test_shard_plan(pkg):
+    sh = pkg.parallel.shard_instances(10, 4)
+    assert sh == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert pkg.parallel.shard_instances(256, 8) == [(32 * r, 32 * r + 32) for r in range(8)]
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import __graft_entry__ as g
+pkg = g.load_package()
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lo, hi = pkg.parallel.shard_instances(10, world)[rank]
+rec = pkg.parallel.pack_records(torch.eye(3).repeat(hi - lo, 1, 1) * (rank + 1), torch.full((hi - lo, 3), float(rank)),
+                                torch.arange(lo, hi).float() / 10, torch.arange(lo, hi, dtype=torch.int32) + 100,
+                                torch.arange(lo, hi))
+allrec = pkg.parallel.gather_records(rec, 10, world)
+R, t, s, pid, iid = pkg.parallel.unpack_records(allrec)
+assert iid.tolist() == list(range(10)), iid
+assert pid.tolist() == [100 + i for i in range(10)]
+assert torch.allclose(s, torch.arange(10).float() / 10)
+assert t[:5].eq(0).all() and t[5:].eq(1).all()
+assert R[7, 0, 0] == 2.0
+if rank == 0:
+    print("GATHER_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_pose_record_gather_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GATHER_OK" in out.stdout
+
+
+def test_bench_reference_arm_contract():
+    """--impl reference prints one JSON line with the contract's keys (tiny run)."""
+    env = dict(os.environ, PEM_BENCH_CPU_INSTANCES="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "pem_instances_per_sec"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["value"] > 0 and line["cpu_baseline"]["cores"] >= 1

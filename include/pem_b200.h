@@ -115,6 +115,16 @@ int pem_query_and_group(const float *xyz, const float *new_xyz, const float *fea
                         int M, int C, float radius, int nsample, float *out, int32_t *idx_out,
                         pem_stream_t stream);
 
+/*
+ * Fused PositionalEncoding grouping (fine_point_matching.py:113-137): both QueryAndGroup scales
+ * of PEM on one cloud in a single pass, i.e. for s in {1,2}
+ *   out_s = QueryAndGroup(radius_s, nsample_s)(xyz, xyz + centre_eps, xyz^T)   (B,6,N,nsample_s)
+ * The squared distance is evaluated once per (centre, point) and compared against both radii;
+ * results are bit-identical to two pem_query_and_group calls.  N <= 65535, nsample <= 128.
+ */
+int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, float radius1, int nsample1,
+                  float *out1, float radius2, int nsample2, float *out2, pem_stream_t stream);
+
 /* ---------------------------------------------------------------- similarity */
 
 /*

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pem_ball_query": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
     "pem_group": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "pem_query_and_group": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p]),
+    "pem_pe_group2": (c_i, [c_p, c_i, c_i, c_f, c_f, c_i, c_p, c_f, c_i, c_p, c_p]),
     "pem_similarity_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "pem_feature_similarity": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "pem_coarse_assign": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),

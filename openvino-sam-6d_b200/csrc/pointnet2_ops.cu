@@ -220,56 +220,96 @@ group_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, in
 // ball query / fused QueryAndGroup
 // ------------------------------------------------------------------------------------
 constexpr int kBqCentres = 128;  // centres (= threads) per CTA
-constexpr int kBqTile = 1024;    // points per shared-memory tile (float4 each)
+constexpr int kBqTile = 512;     // points per shared-memory tile (float4 each)
+
+// Neighbour scan shared by ball_query / QueryAndGroup / the fused PE grouping.
+// One thread = one centre.  Points stream through a shared-memory tile as float4 (one
+// LDS.128 broadcast per point per warp).  For every block of 32 points the thread builds a
+// 32-bit hit mask per radius (8 unfused FP ops + compare + predicated OR per point -- the
+// append logic is NOT in the inner loop), then extracts the set bits in index order, which
+// is exactly the reference's "first nsample hits in index order" rule.  The tile is padded
+// with far-away points so the inner loop needs no bounds checks.
+template <int NSCALE, typename RowT>
+struct NeighbourScan {
+    int cnt[NSCALE], first[NSCALE];
+    RowT *row[NSCALE];
+
+    __device__ __forceinline__ void extract(unsigned m, int s, int ns, int base) {
+        while (m != 0u && cnt[s] < ns) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1u;
+            if (cnt[s] == 0) first[s] = base + bit;
+            row[s][cnt[s]++] = (RowT)(base + bit);
+        }
+    }
+
+    // centres_b: (M,3); centre = centres_b[j] + eps (eps = 0 for a plain ball query)
+    __device__ __forceinline__ void run(const float *__restrict__ centres_b,
+                                        const float *__restrict__ xyz_b, int M, int N, float eps,
+                                        const float (&r2)[NSCALE], const int (&ns)[NSCALE], int j0,
+                                        float4 *s_pts) {
+        const int tid = threadIdx.x, j = j0 + tid;
+        const bool active = j < M;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (active) {
+            qx = __fadd_rn(centres_b[3 * j], eps);
+            qy = __fadd_rn(centres_b[3 * j + 1], eps);
+            qz = __fadd_rn(centres_b[3 * j + 2], eps);
+        }
+#pragma unroll
+        for (int s = 0; s < NSCALE; ++s) { cnt[s] = active ? 0 : ns[s]; first[s] = 0; }
+        for (int base = 0; base < N; base += kBqTile) {
+            bool done = true;
+#pragma unroll
+            for (int s = 0; s < NSCALE; ++s) done = done && cnt[s] >= ns[s];
+            if (__syncthreads_and(done)) break;  // also protects the tile from being overwritten
+            const int nt = min(kBqTile, N - base);
+            const int ntp = (nt + 31) & ~31;
+            for (int k = tid; k < ntp; k += kBqCentres) {
+                if (k < nt) {
+                    const float *p = xyz_b + 3 * (size_t)(base + k);
+                    s_pts[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+                } else {
+                    s_pts[k] = make_float4(3e18f, 3e18f, 3e18f, 0.f);  // d2 = +inf: never a hit
+                }
+            }
+            __syncthreads();
+            if (__all_sync(kFull, done)) continue;
+            for (int kb = 0; kb < ntp; kb += 32) {
+                unsigned m[NSCALE];
+#pragma unroll
+                for (int s = 0; s < NSCALE; ++s) m[s] = 0u;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const float4 p = s_pts[kb + u];
+                    const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
+#pragma unroll
+                    for (int s = 0; s < NSCALE; ++s)
+                        if (d2 < r2[s]) m[s] |= 1u << u;
+                }
+#pragma unroll
+                for (int s = 0; s < NSCALE; ++s) extract(m[s], s, ns[s], base + kb);
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int s = 0; s < NSCALE; ++s)
+                for (int l = cnt[s]; l < ns[s]; ++l) row[s][l] = (RowT)first[s];  // back-fill; no hit -> 0
+        }
+        __syncthreads();
+    }
+};
 
 // Fills s_rows[tid*(ns+1) + l], l in [0,ns), with the neighbour list of centre j0+tid.
 __device__ __forceinline__ void ball_query_rows(const float *__restrict__ centres_b,
                                                 const float *__restrict__ xyz_b, int M, int N,
                                                 float r2, int ns, int j0, float4 *s_pts,
                                                 int *s_rows) {
-    const int tid = threadIdx.x, j = j0 + tid;
-    const bool active = j < M;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (active) { qx = centres_b[3 * j]; qy = centres_b[3 * j + 1]; qz = centres_b[3 * j + 2]; }
-    int cnt = active ? 0 : ns;
-    int first = 0;
-    int *row = s_rows + tid * (ns + 1);
-    for (int base = 0; base < N; base += kBqTile) {
-        if (__syncthreads_and(cnt >= ns)) break;  // also protects the tile from being overwritten
-        const int nt = min(kBqTile, N - base);
-        for (int k = tid; k < nt; k += kBqCentres) {
-            const float *p = xyz_b + 3 * (size_t)(base + k);
-            s_pts[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-        }
-        __syncthreads();
-        if (__all_sync(kFull, cnt >= ns)) continue;
-        int k = 0;
-        for (; k + 4 <= nt && cnt < ns; k += 4) {
-            float d2[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 p = s_pts[k + u];
-                d2[u] = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (d2[u] < r2 && cnt < ns) {
-                    if (cnt == 0) first = base + k + u;
-                    row[cnt++] = base + k + u;
-                }
-            }
-        }
-        for (; k < nt && cnt < ns; ++k) {
-            const float4 p = s_pts[k];
-            if (sqdist_unfused(qx, qy, qz, p.x, p.y, p.z) < r2) {
-                if (cnt == 0) first = base + k;
-                row[cnt++] = base + k;
-            }
-        }
-    }
-    if (active)
-        for (int l = cnt; l < ns; ++l) row[l] = first;  // back-fill; no hit -> zeros
-    __syncthreads();
+    NeighbourScan<1, int> scan;
+    scan.row[0] = s_rows + threadIdx.x * (ns + 1);
+    const float r2a[1] = {r2};
+    const int nsa[1] = {ns};
+    scan.run(centres_b, xyz_b, M, N, 0.f, r2a, nsa, j0, s_pts);
 }
 
 __global__ void __launch_bounds__(kBqCentres)
@@ -338,6 +378,50 @@ transform_points_kernel(const float *__restrict__ p, const float *__restrict__ R
     }
     float *o = out + ((size_t)b * N + i) * 3;
     o[0] = __fadd_rn(o0, eps); o[1] = __fadd_rn(o1, eps); o[2] = __fadd_rn(o2, eps);
+}
+
+// Fused PositionalEncoding front end (fine_point_matching.py:113-137): both QueryAndGroup
+// scales of one cloud in a single pass over the points (the distance is computed once and
+// compared against both radii).  centre = xyz + eps; channels 0-2 = neighbour - centre,
+// channels 3-5 = neighbour (the "features" of PE are the coordinates themselves).
+// Neighbour rows are staged as uint16 (N <= 65535), row strides odd in 32-bit words.
+__global__ void __launch_bounds__(kBqCentres)
+pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int ns1,
+                 float *__restrict__ out1, float r2b, int ns2, float *__restrict__ out2) {
+    extern __shared__ float4 s_dyn[];
+    float4 *s_pts = s_dyn;
+    unsigned short *rows1 = reinterpret_cast<unsigned short *>(s_dyn + kBqTile);
+    const int st1 = ns1 + 2, st2 = ns2 + 2;
+    unsigned short *rows2 = rows1 + kBqCentres * st1;
+    const int b = blockIdx.y, j0 = blockIdx.x * kBqCentres;
+    const float *xyz_b = xyz + (size_t)b * N * 3;
+    NeighbourScan<2, unsigned short> scan;
+    scan.row[0] = rows1 + threadIdx.x * st1;
+    scan.row[1] = rows2 + threadIdx.x * st2;
+    const float r2[2] = {r2a, r2b};
+    const int ns[2] = {ns1, ns2};
+    scan.run(xyz_b, xyz_b, N, N, eps, r2, ns, j0, s_pts);
+    const int rows = min(kBqCentres, N - j0);
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int nss = s ? ns2 : ns1, stride = s ? st2 : st1;
+        const unsigned short *rw = s ? rows2 : rows1;
+        const size_t plane = (size_t)N * nss;
+        float *out_b = (s ? out2 : out1) + (size_t)b * 6 * plane + (size_t)j0 * nss;
+        for (int e = threadIdx.x; e < rows * nss; e += kBqCentres) {
+            const int jj = e / nss, l = e - jj * nss;
+            const int a = rw[jj * stride + l];
+            const float *p = xyz_b + 3 * (size_t)a;
+            const float *q = xyz_b + 3 * (size_t)(j0 + jj);
+            const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+            out_b[e] = __fsub_rn(px, __fadd_rn(__ldg(q), eps));
+            out_b[plane + e] = __fsub_rn(py, __fadd_rn(__ldg(q + 1), eps));
+            out_b[2 * plane + e] = __fsub_rn(pz, __fadd_rn(__ldg(q + 2), eps));
+            out_b[3 * plane + e] = px;
+            out_b[4 * plane + e] = py;
+            out_b[5 * plane + e] = pz;
+        }
+    }
 }
 
 static size_t bq_smem_bytes(int ns) {
@@ -459,5 +543,23 @@ extern "C" int pem_transform_points(const float *pts, const float *R, const floa
     PEM_REQUIRE((R == nullptr) == (t == nullptr), PEM_E_NULL);
     transform_points_kernel<<<dim3((N + 255) / 256, B), 256, 0, pem_cu_stream(stream)>>>(pts, R, t, N,
                                                                                        eps, out);
+    return pem_launch_status();
+}
+
+extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, float radius1,
+                             int nsample1, float *out1, float radius2, int nsample2, float *out2,
+                             pem_stream_t stream) {
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(out1);
+    PEM_REQUIRE_PTR(out2);
+    PEM_REQUIRE(B > 0 && N > 0 && nsample1 > 0 && nsample2 > 0 && B <= 65535, PEM_E_SHAPE);
+    PEM_REQUIRE(nsample1 <= 128 && nsample2 <= 128 && N <= 65535, PEM_E_UNSUPPORTED);
+    const size_t smem = (size_t)kBqTile * sizeof(float4) +
+                        (size_t)kBqCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(pe_group2_kernel, smem, &cached)) return rc;
+    pe_group2_kernel<<<dim3((N + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
+                       pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,
+                                                radius2 * radius2, nsample2, out2);
     return pem_launch_status();
 }

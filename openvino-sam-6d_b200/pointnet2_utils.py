@@ -78,6 +78,22 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, return_idx=False):
     return (out, idx) if return_idx else out
 
 
+def pe_group2(xyz, radius1=0.1, nsample1=32, radius2=0.2, nsample2=64, centre_eps=1e-8):
+    """Both grouping scales of PositionalEncoding.forward (fine_point_matching.py:113-137) in one
+    kernel: returns (QueryAndGroup(r1,ns1)(xyz, xyz+eps, xyz^T), QueryAndGroup(r2,ns2)(...)),
+    each (B,6,N,ns), bit-identical to the two separate calls."""
+    _ext._check(xyz, "xyz", torch.float32, "a float")
+    B, N, _ = xyz.shape
+    out1 = torch.empty((B, 6, N, nsample1), dtype=torch.float32, device=xyz.device)
+    out2 = torch.empty((B, 6, N, nsample2), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.lib().pem_pe_group2(xyz.data_ptr(), B, N, float(centre_eps), float(radius1),
+                                            int(nsample1), out1.data_ptr(), float(radius2),
+                                            int(nsample2), out2.data_ptr(), _ext._stream()),
+                   "pem_pe_group2")
+    return out1, out2
+
+
 class QueryAndGroup(nn.Module):
     """pointnet2_utils.py:303-403.  Only the configuration PEM uses is accelerated
     (use_xyz=True, no uniform re-sampling); other flags raise."""

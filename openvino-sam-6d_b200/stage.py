@@ -64,9 +64,7 @@ class GeometricStage:
         self.init_R, self.init_t = e((B, 9), **f32), e((B, 3), **f32)
         self.proposal_id = e((B,), **i32)
         # step 3
-        self.pe_xyz = e((2, B, N, 3), **f32)      # [0] = p1_, [1] = template
-        self.pe_centres = e((2, B, N, 3), **f32)  # xyz + 1e-8
-        self.pe_featT = e((2, B, 3, N), **f32)    # xyz transposed: the "features" of PE
+        self.pe_xyz = e((1, B, N, 3), **f32)      # p1_ = (p1 - init_t) @ init_R
         self.pe_out = [e((2 * B, 6, N, ns), **f32) for _, ns in PE_SCALES]
         self.sparse_fine = [e((2, B, M, C), **f32) for _ in range(3)]
         # step 4
@@ -133,14 +131,13 @@ class GeometricStage:
         # 3. fine front end: p1_ = (p1 - t) @ R ; PE grouping of p1_ and of the template
         ck(L.pem_transform_points(p(self.pts[0]), p(self.init_R), p(self.init_t), B, N, 0.0,
                                   p(self.pe_xyz[0]), st), "transform"); n += 1
-        ck(L.pem_transform_points(p(self.pts[1]), None, None, B, N, 0.0, p(self.pe_xyz[1]), st),
-           "copy template"); n += 1
-        ck(L.pem_transform_points(p(self.pe_xyz), None, None, 2 * B, N, 1e-8, p(self.pe_centres), st),
-           "centres"); n += 1
-        self.pe_featT.copy_(self.pe_xyz.transpose(2, 3)); n += 1
-        for (r, ns), out in zip(PE_SCALES, self.pe_out):
-            ck(L.pem_query_and_group(p(self.pe_xyz), p(self.pe_centres), p(self.pe_featT), 2 * B, N, N,
-                                     3, r, ns, p(out), None, st), "query_and_group"); n += 1
+        # both PE scales of one cloud in a single kernel (distance computed once per pair); the
+        # template cloud is grouped straight from the input slot
+        (r1, ns1), (r2, ns2) = PE_SCALES
+        ck(L.pem_pe_group2(p(self.pe_xyz[0]), B, N, 1e-8, r1, ns1, p(self.pe_out[0]), r2, ns2,
+                           p(self.pe_out[1]), st), "pe_group2 observed"); n += 1
+        ck(L.pem_pe_group2(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
+                           p(self.pe_out[1][B:]), st), "pe_group2 template"); n += 1
         # 3 transformer blocks x (observed, template): gather 196 rows of the bg-prepended
         # (B,2049,C) features with the FPS indices (reference quirk kept: index 0 fetches the
         # background row, transformer.py:667-671)

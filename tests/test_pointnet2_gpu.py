@@ -139,3 +139,27 @@ def test_error_behaviour_matches_reference_checks(pkg, dev):
         ext.furthest_point_sampling(p.cpu(), 4)
     with pytest.raises(NotImplementedError):
         ext.three_nn(p, p)
+
+
+def test_pe_group2_fused_bit_exact(pkg, oracle, dev):
+    """Both PositionalEncoding grouping scales in one kernel == two QueryAndGroup calls."""
+    b = pkg.synth.make_batch([7, 8])
+    for key in ("dense_po", "dense_pm"):
+        xyz = b[key] - (b["gt_t"][:, None, :] if key == "dense_pm" else 0.0)
+        xyz = xyz.contiguous()
+        new_xyz = (xyz + 1e-8).contiguous()
+        feat = xyz.transpose(1, 2).contiguous()
+        o1, o2 = pkg.pointnet2_utils.pe_group2(xyz.to(dev))
+        w1, _ = oracle.query_and_group(xyz.numpy(), new_xyz.numpy(), feat.numpy(), 0.1, 32)
+        w2, _ = oracle.query_and_group(xyz.numpy(), new_xyz.numpy(), feat.numpy(), 0.2, 64)
+        np.testing.assert_array_equal(o1.cpu().numpy(), w1)
+        np.testing.assert_array_equal(o2.cpu().numpy(), w2)
+    # ragged size, tiny nsample, radius large enough to fill every row early
+    g = torch.Generator().manual_seed(2)
+    xyz = (torch.randn(1, 777, 3, generator=g) * 0.2).contiguous()
+    o1, o2 = pkg.pointnet2_utils.pe_group2(xyz.to(dev), 0.05, 3, 0.6, 128)
+    feat = xyz.transpose(1, 2).contiguous()
+    w1, _ = oracle.query_and_group(xyz.numpy(), (xyz + 1e-8).numpy(), feat.numpy(), 0.05, 3)
+    w2, _ = oracle.query_and_group(xyz.numpy(), (xyz + 1e-8).numpy(), feat.numpy(), 0.6, 128)
+    np.testing.assert_array_equal(o1.cpu().numpy(), w1)
+    np.testing.assert_array_equal(o2.cpu().numpy(), w2)

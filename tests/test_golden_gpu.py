@@ -47,7 +47,7 @@ def test_pointnet2_default_golden(pkg, dev):
 def test_coarse_default_golden(pkg, oracle, dev):
     g = _g("coarse_default.npz")
     oR, ot = check_coarse_against_oracle(pkg, oracle, dev, g["atten"], g["pts1"], g["pts2"], g["model"], 6000, 300,
-                                         g["rand"])
+                                         g["rand"], min_common=5)
     # the oracle reproduces the stored reference output bit for bit (also checked on CPU)
     assert torch.equal(oR, torch.from_numpy(g["R"])) and torch.equal(ot, torch.from_numpy(g["t"]))
 

@@ -73,3 +73,33 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["metric"] == "pem_instances_per_sec"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["value"] > 0 and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_dropin_registers_pointnet2_ext(pkg):
+    """The reference's own pointnet2_utils.py imports cleanly on top of our `_ext` mirror
+    (import-level check; the ops themselves need a GPU)."""
+    import importlib
+    import pytest
+    ref = "/root/reference/SAM-6D/Pose_Estimation_Model/model/pointnet2"
+    if not os.path.isdir(ref):
+        pytest.skip("live reference not present")
+    saved = {k: sys.modules.get(k) for k in ("pointnet2", "pointnet2._ext", "pointnet2_utils")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        ext = pkg.install_pointnet2_ext()
+        assert sys.modules["pointnet2._ext"] is ext
+        for name in ("gather_points", "gather_points_grad", "furthest_point_sampling", "three_nn",
+                     "three_interpolate", "three_interpolate_grad", "ball_query", "group_points",
+                     "group_points_grad"):                      # bindings.cpp:11-24
+            assert callable(getattr(ext, name)), name
+        sys.path.insert(0, ref)
+        ref_utils = importlib.import_module("pointnet2_utils")
+        assert ref_utils._ext is ext
+        assert ref_utils.furthest_point_sample is not None and ref_utils.QueryAndGroup is not None
+    finally:
+        sys.path.remove(ref) if ref in sys.path else None
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v

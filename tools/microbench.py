@@ -1,0 +1,130 @@
+"""Per-kernel microbenchmarks with roofline fractions: BASELINE.json configs[3] (hypothesis-
+scoring sweep) and configs[4] (pointnet2 ops on 64 clouds x 16k points -> 2048 samples), plus the
+default-shape kernels of the stage.  Writes gpurun_out/microbench_<tag>.json.
+CUDA events, 3 warm-ups, L2 flushed between timed launches."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+pkg = g.load_package()
+O = g.load_oracle()
+mu, pu, ext = pkg.model_utils, pkg.pointnet2_utils, pkg.pointnet2_ext
+dev = torch.device("cuda:0")
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+HBM = peaks["hbm_gbs"]
+FP32_OPS = 148 * 128 * 1.965e9 / 1e12  # T lane-ops/s (one op per lane per cycle; FMA counts once)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+out = {"peaks": {"hbm_gbs": HBM, "fp32_lane_tops": FP32_OPS, "bf16_tflops": peaks["bf16_tflops"]}, "rows": []}
+
+
+def timeit(fn, iters=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.median(ms))
+
+
+def row(name, ms, **kw):
+    r = {"kernel": name, "ms": ms}
+    r.update(kw)
+    out["rows"].append(r)
+    print(json.dumps(r), flush=True)
+
+
+def ellipsoid_clouds(B, N, seed):
+    gen = torch.Generator().manual_seed(seed)
+    u = torch.randn(B, N, 3, generator=gen)
+    u = u / u.norm(dim=2, keepdim=True)
+    ax = 0.4 + 0.6 * torch.rand(B, 1, 3, generator=gen)
+    p = u * ax
+    return (p / p.norm(dim=2).amax(1).view(B, 1, 1)).contiguous()
+
+
+# ------------------------------------------------------------------ configs[4]: pointnet2 microbench
+B, N, M = 64, 16384, 2048
+xyz = ellipsoid_clouds(B, N, 1).to(dev)
+ms = timeit(lambda: ext.furthest_point_sampling(xyz, M))
+flop = B * (M - 1) * N * 10
+row("fps 64x16384->2048", ms, gflops=flop / ms / 1e6, frac_fp32_lane_peak=flop / ms / 1e9 / FP32_OPS,
+    streaming_equiv_gbs=B * (M - 1) * N * 20 / ms / 1e6, frac_hbm_streaming_equiv=B * (M - 1) * N * 20 / ms / 1e6 / HBM)
+idx = ext.furthest_point_sampling(xyz, M)
+chk = O.fps(xyz[:2].cpu().numpy(), M)
+row("fps bit-exact vs oracle (2 clouds)", 0.0, equal=bool((idx[:2].cpu().numpy() == chk).all()))
+centres = pu.gather_rows(xyz, idx)
+for r, ns in ((0.1, 32), (0.2, 64)):
+    ms = timeit(lambda: ext.ball_query(centres, xyz, r, ns))
+    flop = B * M * N * 9
+    row("ball_query 64x(2048 centres,16384 pts) r=%.1f ns=%d" % (r, ns), ms, gflops=flop / ms / 1e6,
+        frac_fp32_lane_peak=flop / ms / 1e9 / FP32_OPS)
+bq = ext.ball_query(centres, xyz, 0.2, 64)
+want = O.ball_query(centres[:1].cpu().numpy(), xyz[:1].cpu().numpy(), 0.2, 64)
+row("ball_query bit-exact vs oracle (1 cloud)", 0.0, equal=bool((bq[:1].cpu().numpy() == want).all()))
+for C in (3, 256):
+    feat = torch.randn(B, C, N, device=dev)
+    ms = timeit(lambda: ext.group_points(feat, bq))
+    byts = B * (4 * M * 64 + 8 * C * M * 64)
+    row("group_points C=%d idx (2048,64)" % C, ms, gbs=byts / ms / 1e6, frac_hbm=byts / ms / 1e6 / HBM)
+    del feat
+feat = torch.randn(B, 256, N, device=dev)
+ms = timeit(lambda: ext.gather_points(feat, idx))
+byts = B * (4 * M + 8 * 256 * M)
+row("gather_points C=256 -> 2048", ms, gbs=byts / ms / 1e6, frac_hbm=byts / ms / 1e6 / HBM)
+featr = feat.transpose(1, 2).contiguous()
+ms = timeit(lambda: pu.gather_rows(featr, idx))
+row("gather_rows (point-major) C=256 -> 2048", ms, gbs=byts / ms / 1e6, frac_hbm=byts / ms / 1e6 / HBM)
+del feat, featr, xyz, bq
+
+# ------------------------------------------------------------------ default-shape stage kernels, B = 16
+B = 16
+base = pkg.synth.make_batch(list(range(4)))
+b = {k: v.to(dev) for k, v in pkg.synth.replicate_batch(base, B // 4).items()}
+pm, po = b["dense_pm"], b["dense_po"]
+both = torch.cat([pm, po], 0).contiguous()
+ms = timeit(lambda: ext.furthest_point_sampling(both, 196))
+flop = 2 * B * 195 * 2048 * 10
+row("fps 32x2048->196", ms, gflops=flop / ms / 1e6, frac_fp32_lane_peak=flop / ms / 1e9 / FP32_OPS)
+ms = timeit(lambda: pu.pe_group2(both))
+flop = 2 * B * 2048 * 2048 * 9
+byts = 2 * B * 6 * 2048 * 96 * 4
+row("pe_group2 32 clouds (both PE scales)", ms, gflops=flop / ms / 1e6, frac_fp32_lane_peak=flop / ms / 1e9 / FP32_OPS,
+    out_gbs=byts / ms / 1e6)
+
+# ------------------------------------------------------------------ configs[3]: scoring sweep
+sp, sf, _ = mu.sample_pts_feats(pm, b["dense_fm"], 196, True)
+tp, tf, _ = mu.sample_pts_feats(po, b["dense_fo"], 196, True)
+bg = b["bg"][:, None, :]
+ac = mu.compute_feature_similarity(torch.cat([bg, sf], 1), torch.cat([bg, tf], 1), "cosine", 0.1)
+model2 = pkg.synth.make_batch([0], n_model=2048)["model"].to(dev).repeat(B, 1, 1).contiguous()
+for P1 in (6000, 12000, 24000, 36000, 48000, 60000):
+    rand = torch.rand(B, 3 * P1, device=dev)
+    _, _, st = mu.compute_coarse_Rt(ac, sp, tp, model2, P1, 300, rand=rand, return_stages=True)
+    R, t, w1 = st["R"], st["t"], st["w1"]
+    nfg = float(w1.sum().item()) / B
+    ms = timeit(lambda: mu.score_hypotheses(R, t, sp, w1, model2), iters=3)
+    pairs = B * P1 * nfg * 2048
+    row("score_hypotheses sweep P=%d x Nm=2048 x B=16" % P1, ms, hyps_per_sec=B * P1 / ms * 1e3,
+        lane_tops=pairs * 4 / ms / 1e9, frac_fp32_lane_peak=pairs * 4 / ms / 1e9 / FP32_OPS,
+        mean_foreground_points=nfg)
+    ms2 = timeit(lambda: mu.compute_coarse_Rt(ac, sp, tp, model2, P1, P1, rand=rand), iters=3)
+    row("compute_coarse_Rt P1=P2=%d (sample+solve+select+score all)" % P1, ms2, hyps_per_sec=B * P1 / ms2 * 1e3)
+
+tag = os.environ.get("TAG", "r1")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "microbench_%s.json" % tag), "w"), indent=1)

@@ -48,12 +48,14 @@ coarse_assign_kernel(const float *__restrict__ atten, int N1, int N2, float *__r
         s = warp_sum(s);
         if (lane_id() == 0) { rmax[i] = m; rsum[i] = s; }
     }
-    for (int j = tid; j < Cn; j += 1024) {
+    for (int j = warp_id(); j < Cn; j += 32) {  // warp per column too (odd row stride: no conflicts)
         float m = -INFINITY;
-        for (int i = 0; i < R; ++i) m = fmaxf(m, S[i * Cn + j]);
+        for (int i = lane_id(); i < R; i += 32) m = fmaxf(m, S[i * Cn + j]);
+        m = warp_max(m);
         float s = 0.f;
-        for (int i = 0; i < R; ++i) s += expf(S[i * Cn + j] - m);
-        cmax[j] = m; csum[j] = s;
+        for (int i = lane_id(); i < R; i += 32) s += expf(S[i * Cn + j] - m);
+        s = warp_sum(s);
+        if (lane_id() == 0) { cmax[j] = m; csum[j] = s; }
     }
     __syncthreads();
 
@@ -76,12 +78,15 @@ coarse_assign_kernel(const float *__restrict__ atten, int N1, int N2, float *__r
             w1[(size_t)b * N1 + i - 1] = f;
         }
     }
-    for (int j = 1 + tid; j < Cn; j += 1024) {
+    for (int j = 1 + warp_id(); j < Cn; j += 32) {
         float m = -INFINITY;
-        for (int i = 1; i < R; ++i) m = fmaxf(m, S[i * Cn + j]);
-        const float f = (m > S[j]) ? 1.f : 0.f;
-        w2s[j] = f;
-        w2[(size_t)b * N2 + j - 1] = f;
+        for (int i = 1 + lane_id(); i < R; i += 32) m = fmaxf(m, S[i * Cn + j]);
+        m = warp_max(m);
+        if (lane_id() == 0) {
+            const float f = (m > S[j]) ? 1.f : 0.f;
+            w2s[j] = f;
+            w2[(size_t)b * N2 + j - 1] = f;
+        }
     }
     __syncthreads();
 
@@ -242,14 +247,29 @@ select_smallest_kernel(const float *__restrict__ resid, int P1, int P2, int32_t 
             if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned k = s_k, cum = 0u, bin = 0u;
-            for (; bin < 255u; ++bin) {
-                if (cum + hist[bin] >= k) break;
-                cum += hist[bin];
+        if (warp_id() == 0) {  // which of the 256 bins holds the k-th element: 8 bins per lane
+            const unsigned k = s_k;
+            unsigned loc = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) loc += hist[lane_id() * 8 + q];
+            unsigned inc = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nb = __shfl_up_sync(kFull, inc, o);
+                if (lane_id() >= o) inc += nb;
             }
-            s_k = k - cum;
-            s_prefix = prefix | (bin << (8 * pass));
+            const unsigned before = inc - loc;  // elements in lower lanes' bins
+            const unsigned hit = __ballot_sync(kFull, inc >= k);  // first lane whose cumulative count reaches k
+            const int owner = hit ? __ffs(hit) - 1 : 31;
+            if (lane_id() == owner) {
+                unsigned cum = before, bin = lane_id() * 8;
+                for (int q = 0; q < 7; ++q, ++bin) {
+                    if (cum + hist[bin] >= k) break;
+                    cum += hist[bin];
+                }
+                s_k = k - cum;
+                s_prefix = prefix | (bin << (8 * pass));
+            }
         }
         mask |= 255u << (8 * pass);
         __syncthreads();
@@ -303,8 +323,8 @@ select_smallest_kernel(const float *__restrict__ resid, int P1, int P2, int32_t 
 // score_hypotheses
 // ------------------------------------------------------------------------------------
 constexpr int kScThreads = 256;
-constexpr int kScHyps = 8;   // hypotheses per CTA
-constexpr int kScQMax = 8;   // register-held query points per thread
+constexpr int kScHypsMax = 8;  // hypotheses per CTA (8 for large sweeps, 4 to fill the GPU on small ones)
+constexpr int kScQMax = 8;     // register-held query points per thread
 
 template <int Q>
 __device__ __forceinline__ void score_items(const float4 *__restrict__ s_model, int Nm,
@@ -344,6 +364,7 @@ __device__ __forceinline__ void score_items(const float4 *__restrict__ s_model, 
     }
 }
 
+template <int kScHyps>
 __global__ void __launch_bounds__(kScThreads)
 score_hypotheses_kernel(const float *__restrict__ R, const float *__restrict__ t,
                         const int32_t *__restrict__ sel, int P, int H,
@@ -408,8 +429,8 @@ score_hypotheses_kernel(const float *__restrict__ R, const float *__restrict__ t
     }
 }
 
-static size_t score_smem(int N1, int Nm) {
-    return (size_t)Nm * sizeof(float4) + ((size_t)kScHyps * N1 + kScHyps * 12) * sizeof(float) +
+static size_t score_smem(int N1, int Nm, int hyps) {
+    return (size_t)Nm * sizeof(float4) + ((size_t)hyps * N1 + hyps * 12) * sizeof(float) +
            (size_t)N1 * sizeof(int);
 }
 
@@ -512,14 +533,23 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     PEM_REQUIRE_PTR(scores);
     PEM_REQUIRE(B > 0 && P > 0 && H > 0 && N1 > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(sel != nullptr || H <= P, PEM_E_SHAPE);
-    PEM_REQUIRE(N1 <= kScThreads, PEM_E_UNSUPPORTED);  // kScHyps*N1 <= kScQMax*kScThreads
-    const size_t smem = score_smem(N1, Nm);
+    PEM_REQUIRE(N1 <= kScThreads, PEM_E_UNSUPPORTED);  // hyps*N1 <= kScQMax*kScThreads
+    // 8 hypotheses per CTA amortise the model-point staging best; small problems use 4 so the
+    // grid still covers every SM several times
+    const bool big = (long long)B * ((H + 7) / 8) >= 4LL * PEM_NUM_SMS * 4;
+    const size_t smem = score_smem(N1, Nm, big ? 8 : 4);
     PEM_REQUIRE(smem <= 227 * 1024, PEM_E_UNSUPPORTED);
-    static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel, smem, &cached)) return rc;
-    score_hypotheses_kernel<<<dim3((H + kScHyps - 1) / kScHyps, B), kScThreads, smem,
-                              pem_cu_stream(stream)>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm,
-                                                       scores);
+    if (big) {
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<8>, smem, &cached)) return rc;
+        score_hypotheses_kernel<8><<<dim3((H + 7) / 8, B), kScThreads, smem, pem_cu_stream(stream)>>>(
+            R, t, sel, P, H, pts1, w1, N1, model, Nm, scores);
+    } else {
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<4>, smem, &cached)) return rc;
+        score_hypotheses_kernel<4><<<dim3((H + 3) / 4, B), kScThreads, smem, pem_cu_stream(stream)>>>(
+            R, t, sel, P, H, pts1, w1, N1, model, Nm, scores);
+    }
     return pem_launch_status();
 }
 

@@ -77,6 +77,7 @@ class GeometricStage:
         self.ws = torch.empty(nb, dtype=torch.uint8, device=self.dev)
         self.ws_bytes = nb
         self.stream = torch.cuda.Stream(device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev)  # template-only work, forked inside a step
         self.graph = None
         self.use_graph = use_graph
         self.kernels_per_step = 0
@@ -105,6 +106,12 @@ class GeometricStage:
         ck = _lib.check
         p = lambda t: t.data_ptr()
         n = 0
+        # fork: the PE grouping of the template cloud depends on nothing but the template, so it
+        # runs on a side stream concurrently with the (latency-bound, few-CTA) coarse chain
+        (r1, ns1), (r2, ns2) = PE_SCALES
+        self.side.wait_stream(self.stream)
+        ck(L.pem_pe_group2(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
+                           p(self.pe_out[1][B:]), self.side.cuda_stream), "pe_group2 template"); n += 1
         # 1. FPS on both clouds in one launch (2B clouds), then row gathers
         ck(L.pem_fps(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), None, 0, st), "fps"); n += 1
         ck(L.pem_gather_rows(p(self.pts), p(self.fps_idx), 2 * B, N, 3, M, N * 3, 3,
@@ -131,13 +138,9 @@ class GeometricStage:
         # 3. fine front end: p1_ = (p1 - t) @ R ; PE grouping of p1_ and of the template
         ck(L.pem_transform_points(p(self.pts[0]), p(self.init_R), p(self.init_t), B, N, 0.0,
                                   p(self.pe_xyz[0]), st), "transform"); n += 1
-        # both PE scales of one cloud in a single kernel (distance computed once per pair); the
-        # template cloud is grouped straight from the input slot
-        (r1, ns1), (r2, ns2) = PE_SCALES
+        # both PE scales of the observed cloud in a single kernel (distance computed once per pair)
         ck(L.pem_pe_group2(p(self.pe_xyz[0]), B, N, 1e-8, r1, ns1, p(self.pe_out[0]), r2, ns2,
                            p(self.pe_out[1]), st), "pe_group2 observed"); n += 1
-        ck(L.pem_pe_group2(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
-                           p(self.pe_out[1][B:]), st), "pe_group2 template"); n += 1
         # 3 transformer blocks x (observed, template): gather 196 rows of the bg-prepended
         # (B,2049,C) features with the FPS indices (reference quirk kept: index 0 fetches the
         # background row, transformer.py:667-671)
@@ -152,6 +155,7 @@ class GeometricStage:
                                 self.ws_bytes, st), "fine_fused"); n += 11
         else:
             self._enqueue_fine_materialised(); n += 12
+        self.stream.wait_stream(self.side)  # join
         # 64-byte records
         self.records[:, 0:9].copy_(self.R)
         self.records[:, 9:12].copy_(self.t)
@@ -191,3 +195,58 @@ class GeometricStage:
     def result(self):
         """(R (B,3,3), t (B,3), pose_score (B), proposal_id (B)) views of the device outputs."""
         return self.R.view(self.B, 3, 3), self.t, self.score, self.proposal_id
+
+
+class PipelinedStage:
+    """Host-facing throughput path: `depth` GeometricStage replicas, each with its own input
+    slots, stream and CUDA graph.  submit() enqueues H2D copies of one pinned host batch, the
+    stage and the D2H copy of its pose records on the next replica's stream and returns
+    immediately, so the copies of batch k+1 overlap the kernels of batch k (the copy engines and
+    the SMs run concurrently); collect() waits for the oldest batch in flight."""
+
+    def __init__(self, batch, device, depth=2, **kw):
+        self.stages = [GeometricStage(batch, device, **kw) for _ in range(depth)]
+        self.host_records = [torch.empty((batch, 16), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.inflight = []
+        self.k = 0
+
+    def load_constants(self, host_batch):
+        for s in self.stages:
+            s.load(host_batch)
+
+    def submit(self, pinned, post=None):
+        """pinned: dict of pinned host tensors dense_pm/dense_po/dense_fm/dense_fo/model/rand."""
+        i = self.k % len(self.stages)
+        s = self.stages[i]
+        if len(self.inflight) == len(self.stages):
+            self.collect()
+        with torch.cuda.stream(s.stream):
+            s.pts[0].copy_(pinned["dense_pm"], non_blocking=True)
+            s.pts[1].copy_(pinned["dense_po"], non_blocking=True)
+            s.feats[0, :, 1:].copy_(pinned["dense_fm"], non_blocking=True)
+            s.feats[1, :, 1:].copy_(pinned["dense_fo"], non_blocking=True)
+            s.model.copy_(pinned["model"], non_blocking=True)
+            s.rand.copy_(pinned["rand"], non_blocking=True)
+        s.run()
+        with torch.cuda.stream(s.stream):
+            src = post(s) if post is not None else s.records
+            self.host_records[i][: src.shape[0]].copy_(src[: self.host_records[i].shape[0]], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(s.stream)
+        self.inflight.append((i, done))
+        self.k += 1
+
+    def collect(self):
+        i, done = self.inflight.pop(0)
+        done.synchronize()
+        return self.host_records[i]
+
+    def drain(self):
+        out = None
+        while self.inflight:
+            out = self.collect()
+        return out
+
+    @property
+    def kernels_per_step(self):
+        return self.stages[0].kernels_per_step

@@ -175,7 +175,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- e2e: pinned host -> H2D -> stage -> D2H records, all inside the timed region --------
     # through the host-facing PipelinedStage (two replicas: copies of batch k+1 overlap batch k)
-    pin = {k: host[k].pin_memory() for k in ("dense_pm", "dense_po", "dense_fm", "dense_fo", "model", "rand")}
+    pin = pkg.stage.PipelinedStage.pin_inputs(host)
     h2d = sum(v.numel() * v.element_size() for v in pin.values())
     d2h = B * 16 * 4
     pipe = pkg.stage.PipelinedStage(B, dev, depth=2)

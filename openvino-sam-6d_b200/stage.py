@@ -214,17 +214,30 @@ class PipelinedStage:
         for s in self.stages:
             s.load(host_batch)
 
+    @staticmethod
+    def pin_inputs(host_batch):
+        """Pinned host buffers laid out exactly like the device input slots, so that each step's
+        upload is four contiguous cudaMemcpyAsync calls: pts (2,B,N,3), feats (2,B,N+1,C) with
+        the background token in row 0, model (B,Nm,3), rand (B,3*P1)."""
+        pm, fm = host_batch["dense_pm"], host_batch["dense_fm"]
+        B, N, C = fm.shape
+        pts = torch.stack([pm, host_batch["dense_po"]]).contiguous().pin_memory()
+        feats = torch.empty((2, B, N + 1, C), dtype=torch.float32).pin_memory()
+        feats[:, :, 0] = host_batch["bg"].unsqueeze(0)
+        feats[0, :, 1:] = fm
+        feats[1, :, 1:] = host_batch["dense_fo"]
+        return {"pts": pts, "feats": feats, "model": host_batch["model"].contiguous().pin_memory(),
+                "rand": host_batch["rand"].contiguous().pin_memory()}
+
     def submit(self, pinned, post=None):
-        """pinned: dict of pinned host tensors dense_pm/dense_po/dense_fm/dense_fo/model/rand."""
+        """pinned: the dict returned by pin_inputs()."""
         i = self.k % len(self.stages)
         s = self.stages[i]
         if len(self.inflight) == len(self.stages):
             self.collect()
         with torch.cuda.stream(s.stream):
-            s.pts[0].copy_(pinned["dense_pm"], non_blocking=True)
-            s.pts[1].copy_(pinned["dense_po"], non_blocking=True)
-            s.feats[0, :, 1:].copy_(pinned["dense_fm"], non_blocking=True)
-            s.feats[1, :, 1:].copy_(pinned["dense_fo"], non_blocking=True)
+            s.pts.copy_(pinned["pts"], non_blocking=True)
+            s.feats.copy_(pinned["feats"], non_blocking=True)
             s.model.copy_(pinned["model"], non_blocking=True)
             s.rand.copy_(pinned["rand"], non_blocking=True)
         s.run()

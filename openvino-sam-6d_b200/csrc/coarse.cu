@@ -38,32 +38,69 @@ coarse_assign_kernel(const float *__restrict__ atten, int N1, int N2, float *__r
     for (int e = tid; e < R * Cn; e += 1024) S[e] = __ldg(A + e);
     __syncthreads();
 
-    // softmax statistics: warp per row, thread per column
-    for (int i = warp_id(); i < R; i += 32) {
-        float m = -INFINITY;
-        for (int j = lane_id(); j < Cn; j += 32) m = fmaxf(m, S[i * Cn + j]);
-        m = warp_max(m);
-        float s = 0.f;
-        for (int j = lane_id(); j < Cn; j += 32) s += expf(S[i * Cn + j] - m);
-        s = warp_sum(s);
-        if (lane_id() == 0) { rmax[i] = m; rsum[i] = s; }
-    }
-    for (int j = warp_id(); j < Cn; j += 32) {  // warp per column too (odd row stride: no conflicts)
-        float m = -INFINITY;
-        for (int i = lane_id(); i < R; i += 32) m = fmaxf(m, S[i * Cn + j]);
-        m = warp_max(m);
-        float s = 0.f;
-        for (int i = lane_id(); i < R; i += 32) s += expf(S[i * Cn + j] - m);
-        s = warp_sum(s);
-        if (lane_id() == 0) { cmax[j] = m; csum[j] = s; }
-    }
+    // Range of the logits.  When it is small (cosine similarity / temp always is: |s| <= 1/temp)
+    // a single shift serves every row and column, and one exp per element replaces four.
+    float lmax = -INFINITY, lmin = INFINITY;
+    for (int e = tid; e < R * Cn; e += 1024) { lmax = fmaxf(lmax, S[e]); lmin = fminf(lmin, S[e]); }
+    lmax = warp_max(lmax);
+    lmin = warp_min(lmin);
+    float *s_f = reinterpret_cast<float *>(s_scan);  // 68 floats of scratch, free until the scan
+    if (lane_id() == 0) { s_f[warp_id()] = lmax; s_f[32 + warp_id()] = lmin; }
+    __syncthreads();
+    float gmax = s_f[lane_id()], gmin = s_f[32 + lane_id()];
+    gmax = warp_max(gmax);
+    gmin = warp_min(gmin);
+    const bool fast = (gmax - gmin) < 80.0f;  // block-uniform
     __syncthreads();
 
-    // P = softmax(dim=2) * softmax(dim=1), in place (MU:230)
-    for (int e = tid; e < R * Cn; e += 1024) {
-        const int i = e / Cn, j = e - i * Cn;
-        const float v = S[e];
-        S[e] = __fdiv_rn(expf(v - rmax[i]), rsum[i]) * __fdiv_rn(expf(v - cmax[j]), csum[j]);
+    if (fast) {
+        for (int e = tid; e < R * Cn; e += 1024) S[e] = expf(S[e] - gmax);
+        __syncthreads();
+        for (int i = warp_id(); i < R; i += 32) {
+            float s = 0.f;
+            for (int j = lane_id(); j < Cn; j += 32) s += S[i * Cn + j];
+            s = warp_sum(s);
+            if (lane_id() == 0) rsum[i] = 1.0f / s;
+        }
+        for (int j = warp_id(); j < Cn; j += 32) {  // odd row stride: conflict-free column walks
+            float s = 0.f;
+            for (int i = lane_id(); i < R; i += 32) s += S[i * Cn + j];
+            s = warp_sum(s);
+            if (lane_id() == 0) csum[j] = 1.0f / s;
+        }
+        __syncthreads();
+        // P = softmax(dim=2) * softmax(dim=1) (MU:230)
+        for (int e = tid; e < R * Cn; e += 1024) {
+            const int i = e / Cn, j = e - i * Cn;
+            const float v = S[e];
+            S[e] = (v * rsum[i]) * (v * csum[j]);
+        }
+    } else {
+        // general logits: per-row and per-column maxima (warp per row / per column)
+        for (int i = warp_id(); i < R; i += 32) {
+            float m = -INFINITY;
+            for (int j = lane_id(); j < Cn; j += 32) m = fmaxf(m, S[i * Cn + j]);
+            m = warp_max(m);
+            float s = 0.f;
+            for (int j = lane_id(); j < Cn; j += 32) s += expf(S[i * Cn + j] - m);
+            s = warp_sum(s);
+            if (lane_id() == 0) { rmax[i] = m; rsum[i] = s; }
+        }
+        for (int j = warp_id(); j < Cn; j += 32) {
+            float m = -INFINITY;
+            for (int i = lane_id(); i < R; i += 32) m = fmaxf(m, S[i * Cn + j]);
+            m = warp_max(m);
+            float s = 0.f;
+            for (int i = lane_id(); i < R; i += 32) s += expf(S[i * Cn + j] - m);
+            s = warp_sum(s);
+            if (lane_id() == 0) { cmax[j] = m; csum[j] = s; }
+        }
+        __syncthreads();
+        for (int e = tid; e < R * Cn; e += 1024) {
+            const int i = e / Cn, j = e - i * Cn;
+            const float v = S[e];
+            S[e] = __fdiv_rn(expf(v - rmax[i]), rsum[i]) * __fdiv_rn(expf(v - cmax[j]), csum[j]);
+        }
     }
     __syncthreads();
 

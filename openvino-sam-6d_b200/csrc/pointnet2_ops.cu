@@ -22,7 +22,11 @@
 //    tile (one LDS.128 broadcast per point per warp); neighbour rows are staged in
 //    shared memory and written coalesced.  The fused QueryAndGroup consumes the
 //    staged rows directly and writes the (B,3+C,M,ns) tensor once.
+#include <cooperative_groups.h>
+
 #include "pem_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pem {
 
@@ -112,6 +116,111 @@ fps_cta_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *_
     }
 }
 
+// Thread-block-cluster variant for clouds too large for one SM's registers: the cloud is
+// split into contiguous slabs, one per CTA of the cluster (coordinates + running distance in
+// registers, or coordinates in that CTA's shared memory).  Every step each CTA reduces its slab
+// locally, then writes a 20-byte record (distance bits, ~global index, x, y, z of its local
+// winner) into every peer's shared memory through DSMEM; one cluster barrier later all CTAs
+// hold all records, pick the same global winner and already have its coordinates.
+struct FpsRecord { unsigned hi, lo; float x, y, z; };
+
+template <int THREADS, int PPT, bool IN_REGS>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_cluster_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *__restrict__ idx) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / C;
+    const int per = (N + C - 1) / C;
+    const int lo_pt = rank * per;
+    const int n_loc = max(0, min(per, N - lo_pt));
+    extern __shared__ float s_soa[];  // x[per] | y[per] | z[per] of this CTA's slab
+    __shared__ unsigned long long s_key[2][32];
+    __shared__ FpsRecord s_rec[2][16];
+    float *sx = s_soa, *sy = s_soa + per, *sz = s_soa + 2 * per;
+    const int tid = threadIdx.x;
+    const float *src = xyz + ((size_t)cloud * N + lo_pt) * 3;
+    int32_t *out = idx + (size_t)cloud * M;
+
+    for (int e = tid; e < 3 * n_loc; e += THREADS) {
+        const int k = e / 3, c = e - 3 * k;
+        s_soa[c * per + k] = src[e];
+    }
+    __syncthreads();
+    float px[IN_REGS ? PPT : 1], py[IN_REGS ? PPT : 1], pz[IN_REGS ? PPT : 1];
+    float run[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = i * THREADS + tid;
+        bool ok = k < n_loc;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (ok) {
+            x = sx[k]; y = sy[k]; z = sz[k];
+            if (skip && near_origin(x, y, z)) ok = false;
+        }
+        if (IN_REGS) { px[i] = x; py[i] = y; pz[i] = z; }
+        run[i] = ok ? FLT_MAX : -INFINITY;
+    }
+    // the first sample is point 0 of the cloud (owned by rank 0): every CTA reads it from global
+    const float *p0 = xyz + (size_t)cloud * N * 3;
+    float cx = __ldg(p0), cy = __ldg(p0 + 1), cz = __ldg(p0 + 2);
+    if (rank == 0 && tid == 0) out[0] = 0;
+    cluster.sync();  // peers' shared memory is live before the first remote store
+    for (int j = 1; j < M; ++j) {
+        float best = -FLT_MAX;
+        int arg = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = i * THREADS + tid;
+            float x, y, z;
+            if (IN_REGS) { x = px[i]; y = py[i]; z = pz[i]; }
+            else if (k < n_loc) { x = sx[k]; y = sy[k]; z = sz[k]; }
+            else { x = y = z = 0.f; }
+            const float m = fminf(sqdist_unfused(x, y, z, cx, cy, cz), run[i]);
+            run[i] = m;
+            if (m > best) { best = m; arg = k; }
+        }
+        const bool valid = best > -FLT_MAX;
+        // local winner (local index; 0 with hi = lo = 0 when the slab has no candidate)
+        const unsigned hi = valid ? __float_as_uint(best) : 0u;
+        const unsigned lo = valid ? ~(unsigned)(lo_pt + arg) : 0u;
+        // CTA-level reduction of (hi, lo) -- same scheme as cta_argmax, but keep the pair
+        constexpr int NW = THREADS / 32;
+        const unsigned whi = __reduce_max_sync(kFull, hi);
+        const unsigned wlo = __reduce_max_sync(kFull, hi == whi ? lo : 0u);
+        const int par = j & 1;
+        if (lane_id() == 0) s_key[par][warp_id()] = ((unsigned long long)whi << 32) | wlo;
+        __syncthreads();
+        // warp 0 computes the CTA key; lane r then delivers this CTA's record to CTA r
+        if (warp_id() == 0) {
+            const unsigned long long key = lane_id() < NW ? s_key[par][lane_id()] : 0ull;
+            const unsigned h2 = (unsigned)(key >> 32), l2 = (unsigned)key;
+            const unsigned chi = __reduce_max_sync(kFull, h2);
+            const unsigned clo = __reduce_max_sync(kFull, h2 == chi ? l2 : 0u);
+            if (lane_id() < C) {
+                FpsRecord r;
+                r.hi = chi; r.lo = clo;
+                const int li = clo ? (int)(~clo) - lo_pt : 0;
+                r.x = sx[li]; r.y = sy[li]; r.z = sz[li];
+                FpsRecord *dst = cluster.map_shared_rank(&s_rec[par][rank], lane_id());
+                *dst = r;
+            }
+        }
+        cluster.sync();  // release/acquire: all records visible everywhere
+        // global winner: max (hi, lo) over the C records; ties on distance -> lowest global index
+        unsigned ghi = 0u, glo = 0u;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        for (int r = 0; r < C; ++r) {
+            const FpsRecord q = s_rec[par][r];
+            if (q.hi > ghi || (q.hi == ghi && q.lo > glo)) { ghi = q.hi; glo = q.lo; gx = q.x; gy = q.y; gz = q.z; }
+        }
+        int cur = 0;
+        if (glo != 0u) { cur = (int)~glo; cx = gx; cy = gy; cz = gz; }
+        else { cx = __ldg(p0); cy = __ldg(p0 + 1); cz = __ldg(p0 + 2); }  // nothing selectable: index 0
+        if (rank == 0 && tid == 0) out[j] = cur;
+    }
+    cluster.sync();  // no CTA exits while a peer may still write into its shared memory
+}
+
 // Fallback for clouds that do not fit one SM: coordinates from L2, running distance in
 // a caller-provided workspace (B*N floats).
 template <int THREADS>
@@ -156,6 +265,37 @@ static int launch_fps_cta(const float *xyz, int B, int N, int M, int skip, int32
     static size_t cached = 40 * 1024;  // static shared memory counts against the 48 KB default too
     if (int rc = pem_ensure_dyn_smem(kern, smem, &cached)) return rc;
     kern<<<B, THREADS, smem, st>>>(xyz, N, M, skip, idx);
+    return pem_launch_status();
+}
+
+template <int THREADS, int PPT, bool IN_REGS>
+static int launch_fps_cluster(const float *xyz, int B, int N, int M, int skip, int32_t *idx, int C,
+                              cudaStream_t st) {
+    const int per = (N + C - 1) / C;
+    const size_t smem = (size_t)3 * per * sizeof(float);
+    auto kern = fps_cluster_kernel<THREADS, PPT, IN_REGS>;
+    static size_t cached = 40 * 1024;
+    if (int rc = pem_ensure_dyn_smem(kern, smem, &cached)) return rc;
+    static bool nonportable = false;
+    if (C > 8 && !nonportable) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return (int)e;
+        nonportable = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * C);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, N, M, skip, idx);
+    if (e != cudaSuccess) return (int)e;
     return pem_launch_status();
 }
 
@@ -436,7 +576,7 @@ static size_t bq_smem_bytes(int ns) {
 using namespace pem;
 
 extern "C" size_t pem_fps_workspace_bytes(int B, int N) {
-    if (B <= 0 || N <= 16384) return 0;
+    if (B <= 0 || N <= 16 * 16384) return 0;
     return (size_t)B * N * sizeof(float);
 }
 
@@ -451,7 +591,18 @@ extern "C" int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t
     if (N <= 2048) return launch_fps_cta<256, 8, true>(xyz, B, N, M, skip, idx, st);
     if (N <= 4096) return launch_fps_cta<512, 8, true>(xyz, B, N, M, skip, idx, st);
     if (N <= 8192) return launch_fps_cta<1024, 8, true>(xyz, B, N, M, skip, idx, st);
-    if (N <= 16384) return launch_fps_cta<1024, 16, false>(xyz, B, N, M, skip, idx, st);
+    // larger clouds: thread-block clusters (slabs of <= 8192 points in registers), as long as the
+    // clusters of all clouds fit on the chip at once; many medium clouds stay one CTA per cloud
+    if (N <= 16384) {
+        if (2 * B <= PEM_NUM_SMS) return launch_fps_cluster<1024, 8, true>(xyz, B, N, M, skip, idx, 2, st);
+        return launch_fps_cta<1024, 16, false>(xyz, B, N, M, skip, idx, st);
+    }
+    if (N <= 65536) {
+        const int C = N <= 32768 ? 4 : 8;
+        return launch_fps_cluster<1024, 8, true>(xyz, B, N, M, skip, idx, C, st);
+    }
+    if (N <= 16 * 16384)  // e.g. the 210 000-point template cloud: 16 CTAs, coordinates in shared memory
+        return launch_fps_cluster<1024, 16, false>(xyz, B, N, M, skip, idx, 16, st);
     PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fps_workspace_bytes(B, N),
                 PEM_E_WORKSPACE);
     fps_stream_kernel<1024><<<B, 1024, 0, st>>>(xyz, N, M, skip, (float *)workspace, idx);

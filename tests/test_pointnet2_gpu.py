@@ -23,7 +23,8 @@ def _cloud(B, N, seed, scale=0.4, dup=0.1, near_origin=3):
 @pytest.mark.parametrize("B,N,M", [
     (1, 1, 1), (2, 7, 7), (3, 100, 33), (2, 1000, 128), (4, 1024, 200), (3, 1025, 64),
     (2, 2048, 196), (2, 3000, 300), (2, 4096, 64), (1, 5000, 100), (1, 8192, 50),
-    (2, 9000, 40), (1, 16384, 64), (1, 20000, 32), (2, 5, 9),
+    (2, 9000, 40), (1, 16384, 64), (3, 16000, 33), (1, 20000, 32), (2, 40000, 20), (1, 70000, 24),
+    (1, 210000, 48), (1, 300000, 8), (2, 5, 9), (80, 9000, 6),
 ])
 def test_fps_bit_exact(pkg, oracle, dev, B, N, M):
     p = _cloud(B, N, seed=N + M)

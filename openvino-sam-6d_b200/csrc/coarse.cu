@@ -359,11 +359,10 @@ select_smallest_kernel(const float *__restrict__ resid, int P1, int P2, int32_t 
 // ------------------------------------------------------------------------------------
 // score_hypotheses
 // ------------------------------------------------------------------------------------
-constexpr int kScThreads = 256;
 constexpr int kScHypsMax = 8;  // hypotheses per CTA (8 for large sweeps, 4 to fill the GPU on small ones)
 constexpr int kScQMax = 8;     // register-held query points per thread
 
-template <int Q>
+template <int Q, int kScThreads>
 __device__ __forceinline__ void score_items(const float4 *__restrict__ s_model, int Nm,
                                             const float *__restrict__ s_Rt,
                                             const int *__restrict__ s_fg,
@@ -401,7 +400,7 @@ __device__ __forceinline__ void score_items(const float4 *__restrict__ s_model, 
     }
 }
 
-template <int kScHyps>
+template <int kScHyps, int kScThreads>
 __global__ void __launch_bounds__(kScThreads)
 score_hypotheses_kernel(const float *__restrict__ R, const float *__restrict__ t,
                         const int32_t *__restrict__ sel, int P, int H,
@@ -445,19 +444,18 @@ score_hypotheses_kernel(const float *__restrict__ R, const float *__restrict__ t
     const int q = (items + kScThreads - 1) / kScThreads;  // block-uniform, <= kScQMax
     switch (q) {
         case 0: break;
-        case 1: score_items<1>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        case 2: score_items<2>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        case 3: score_items<3>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        case 4: score_items<4>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        case 5: score_items<5>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        case 6: score_items<6>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        case 7: score_items<7>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
-        default: score_items<8>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 1: score_items<1, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 2: score_items<2, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 3: score_items<3, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 4: score_items<4, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 5: score_items<5, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 6: score_items<6, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        case 7: score_items<7, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
+        default: score_items<8, kScThreads>(s_model, Nm, s_Rt, s_fg, pb, nfg, items, s_dis); break;
     }
     __syncthreads();
     // deterministic per-hypothesis sum: warp hh sums its nfg distances in a fixed order
-    const int hh = warp_id();
-    if (hh < nh) {
+    for (int hh = warp_id(); hh < nh; hh += kScThreads / 32) {
         float s = 0.f;
         for (int i = lane_id(); i < nfg; i += 32) s += s_dis[hh * nfg + i];
         s = warp_sum(s);
@@ -570,7 +568,7 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     PEM_REQUIRE_PTR(scores);
     PEM_REQUIRE(B > 0 && P > 0 && H > 0 && N1 > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(sel != nullptr || H <= P, PEM_E_SHAPE);
-    PEM_REQUIRE(N1 <= kScThreads, PEM_E_UNSUPPORTED);  // hyps*N1 <= kScQMax*kScThreads
+    PEM_REQUIRE(N1 <= 256, PEM_E_UNSUPPORTED);  // hyps*N1 <= kScQMax*threads in both shapes
     // 8 hypotheses per CTA amortise the model-point staging best; small problems use 4 so the
     // grid still covers every SM several times
     const bool big = (long long)B * ((H + 7) / 8) >= 4LL * PEM_NUM_SMS * 4;
@@ -578,13 +576,14 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     PEM_REQUIRE(smem <= 227 * 1024, PEM_E_UNSUPPORTED);
     if (big) {
         static size_t cached = 0;
-        if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<8>, smem, &cached)) return rc;
-        score_hypotheses_kernel<8><<<dim3((H + 7) / 8, B), kScThreads, smem, pem_cu_stream(stream)>>>(
+        if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<8, 256>, smem, &cached)) return rc;
+        score_hypotheses_kernel<8, 256><<<dim3((H + 7) / 8, B), 256, smem, pem_cu_stream(stream)>>>(
             R, t, sel, P, H, pts1, w1, N1, model, Nm, scores);
     } else {
         static size_t cached = 0;
-        if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<4>, smem, &cached)) return rc;
-        score_hypotheses_kernel<4><<<dim3((H + 3) / 4, B), kScThreads, smem, pem_cu_stream(stream)>>>(
+        // 4 hypotheses x <=196 points over 128 threads: up to 7 register-held queries per thread
+        if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<4, 128>, smem, &cached)) return rc;
+        score_hypotheses_kernel<4, 128><<<dim3((H + 3) / 4, B), 128, smem, pem_cu_stream(stream)>>>(
             R, t, sel, P, H, pts1, w1, N1, model, Nm, scores);
     }
     return pem_launch_status();

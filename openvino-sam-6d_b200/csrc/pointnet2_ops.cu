@@ -524,31 +524,115 @@ transform_points_kernel(const float *__restrict__ p, const float *__restrict__ R
 // scales of one cloud in a single pass over the points (the distance is computed once and
 // compared against both radii).  centre = xyz + eps; channels 0-2 = neighbour - centre,
 // channels 3-5 = neighbour (the "features" of PE are the coordinates themselves).
-// Neighbour rows are staged as uint16 (N <= 65535), row strides odd in 32-bit words.
-__global__ void __launch_bounds__(kBqCentres)
+//
+// Parallel decomposition: with 16 clouds x 2048 centres a thread-per-centre scan exposes only
+// 32k threads, far too few for 148 SMs.  So each centre is scanned by kPeSeg threads, each
+// owning a contiguous quarter of the current 1024-point super-tile and emitting 32-bit hit masks
+// (one word per 32 points per radius) into shared memory laid out [radius][word][centre]
+// (conflict-free both ways).  Because segments are contiguous index ranges, walking the words
+// in order afterwards yields exactly the reference's "first nsample hits in index order".
+// A warp holds 32 consecutive centres of ONE segment, so every point is one LDS.128 broadcast.
+constexpr int kPeCentres = 64;   // centres per CTA
+constexpr int kPeSeg = 4;        // threads per centre
+constexpr int kPeThreads = kPeCentres * kPeSeg;
+constexpr int kPeTile = 1024;    // points per super-tile
+constexpr int kPeWords = kPeTile / 32;
+
+__global__ void __launch_bounds__(kPeThreads)
 pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int ns1,
                  float *__restrict__ out1, float r2b, int ns2, float *__restrict__ out2) {
     extern __shared__ float4 s_dyn[];
-    float4 *s_pts = s_dyn;
-    unsigned short *rows1 = reinterpret_cast<unsigned short *>(s_dyn + kBqTile);
-    const int st1 = ns1 + 2, st2 = ns2 + 2;
-    unsigned short *rows2 = rows1 + kBqCentres * st1;
-    const int b = blockIdx.y, j0 = blockIdx.x * kBqCentres;
+    float4 *s_pts = s_dyn;                                                   // kPeTile
+    unsigned *s_mask = reinterpret_cast<unsigned *>(s_dyn + kPeTile);        // [2][kPeWords][kPeCentres]
+    unsigned short *rows1 = reinterpret_cast<unsigned short *>(s_mask + 2 * kPeWords * kPeCentres);
+    const int st1 = ns1 + 2, st2 = ns2 + 2;                                  // odd strides in 32-bit words
+    unsigned short *rows2 = rows1 + kPeCentres * st1;
+    __shared__ int s_cnt[2][kPeCentres], s_first[2][kPeCentres];
+    const int tid = threadIdx.x, b = blockIdx.y, j0 = blockIdx.x * kPeCentres;
+    const int c = tid & (kPeCentres - 1), seg = tid / kPeCentres;  // seg is warp-uniform
     const float *xyz_b = xyz + (size_t)b * N * 3;
-    NeighbourScan<2, unsigned short> scan;
-    scan.row[0] = rows1 + threadIdx.x * st1;
-    scan.row[1] = rows2 + threadIdx.x * st2;
-    const float r2[2] = {r2a, r2b};
-    const int ns[2] = {ns1, ns2};
-    scan.run(xyz_b, xyz_b, N, N, eps, r2, ns, j0, s_pts);
-    const int rows = min(kBqCentres, N - j0);
+    const int j = j0 + c;
+    const bool active = j < N;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        qx = __fadd_rn(xyz_b[3 * j], eps);
+        qy = __fadd_rn(xyz_b[3 * j + 1], eps);
+        qz = __fadd_rn(xyz_b[3 * j + 2], eps);
+    }
+    if (tid < 2 * kPeCentres) {
+        const int r = tid / kPeCentres, cc = tid - r * kPeCentres;
+        s_cnt[r][cc] = (j0 + cc < N) ? 0 : (r ? ns2 : ns1);
+        s_first[r][cc] = 0;
+    }
+    for (int base = 0; base < N; base += kPeTile) {
+        __syncthreads();  // previous tile (points and masks) fully consumed
+        const int nt = min(kPeTile, N - base);
+        for (int k = tid; k < kPeTile; k += kPeThreads) {
+            if (k < nt) {
+                const float *p = xyz_b + 3 * (size_t)(base + k);
+                s_pts[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+            } else {
+                s_pts[k] = make_float4(3e18f, 3e18f, 3e18f, 0.f);  // d2 = +inf: never a hit
+            }
+        }
+        __syncthreads();
+        // scan this thread's quarter of the tile: kPeWords / kPeSeg words of 32 points
+#pragma unroll 1
+        for (int w = 0; w < kPeWords / kPeSeg; ++w) {
+            const int word = seg * (kPeWords / kPeSeg) + w;
+            const float4 *pp = s_pts + word * 32;
+            unsigned m1 = 0u, m2 = 0u;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                const float4 p = pp[u];
+                const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
+                if (d2 < r2a) m1 |= 1u << u;
+                if (d2 < r2b) m2 |= 1u << u;
+            }
+            s_mask[(0 * kPeWords + word) * kPeCentres + c] = m1;
+            s_mask[(1 * kPeWords + word) * kPeCentres + c] = m2;
+        }
+        __syncthreads();
+        // in-order extraction: one thread per (radius, centre)
+        bool done = true;
+        if (tid < 2 * kPeCentres) {
+            const int r = tid / kPeCentres, cc = tid - r * kPeCentres;
+            const int ns = r ? ns2 : ns1;
+            unsigned short *row = (r ? rows2 + cc * st2 : rows1 + cc * st1);
+            int cnt = s_cnt[r][cc], first = s_first[r][cc];
+            for (int word = 0; word < kPeWords && cnt < ns; ++word) {
+                unsigned m = s_mask[(r * kPeWords + word) * kPeCentres + cc];
+                while (m != 0u && cnt < ns) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const int id = base + word * 32 + bit;
+                    if (cnt == 0) first = id;
+                    row[cnt++] = (unsigned short)id;
+                }
+            }
+            s_cnt[r][cc] = cnt;
+            s_first[r][cc] = first;
+            done = cnt >= ns;
+        }
+        if (__syncthreads_and(done)) break;  // every list of this CTA is full
+    }
+    __syncthreads();
+    if (tid < 2 * kPeCentres) {  // back-fill with the first hit; no hit -> zeros
+        const int r = tid / kPeCentres, cc = tid - r * kPeCentres;
+        const int ns = r ? ns2 : ns1;
+        unsigned short *row = (r ? rows2 + cc * st2 : rows1 + cc * st1);
+        const unsigned short f = (unsigned short)s_first[r][cc];
+        for (int l = s_cnt[r][cc]; l < ns; ++l) row[l] = f;
+    }
+    __syncthreads();
+    const int rows = min(kPeCentres, N - j0);
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
         const int nss = s ? ns2 : ns1, stride = s ? st2 : st1;
         const unsigned short *rw = s ? rows2 : rows1;
         const size_t plane = (size_t)N * nss;
         float *out_b = (s ? out2 : out1) + (size_t)b * 6 * plane + (size_t)j0 * nss;
-        for (int e = threadIdx.x; e < rows * nss; e += kBqCentres) {
+        for (int e = tid; e < rows * nss; e += kPeThreads) {
             const int jj = e / nss, l = e - jj * nss;
             const int a = rw[jj * stride + l];
             const float *p = xyz_b + 3 * (size_t)a;
@@ -705,11 +789,12 @@ extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, f
     PEM_REQUIRE_PTR(out2);
     PEM_REQUIRE(B > 0 && N > 0 && nsample1 > 0 && nsample2 > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(nsample1 <= 128 && nsample2 <= 128 && N <= 65535, PEM_E_UNSUPPORTED);
-    const size_t smem = (size_t)kBqTile * sizeof(float4) +
-                        (size_t)kBqCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
+    const size_t smem = (size_t)kPeTile * sizeof(float4) +
+                        (size_t)2 * kPeWords * kPeCentres * sizeof(unsigned) +
+                        (size_t)kPeCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
     static size_t cached = 0;
     if (int rc = pem_ensure_dyn_smem(pe_group2_kernel, smem, &cached)) return rc;
-    pe_group2_kernel<<<dim3((N + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
+    pe_group2_kernel<<<dim3((N + kPeCentres - 1) / kPeCentres, B), kPeThreads, smem,
                        pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,
                                                 radius2 * radius2, nsample2, out2);
     return pem_launch_status();

@@ -526,28 +526,33 @@ transform_points_kernel(const float *__restrict__ p, const float *__restrict__ R
 // channels 3-5 = neighbour (the "features" of PE are the coordinates themselves).
 //
 // Parallel decomposition: with 16 clouds x 2048 centres a thread-per-centre scan exposes only
-// 32k threads, far too few for 148 SMs.  So each centre is scanned by kPeSeg threads, each
-// owning a contiguous quarter of the current 1024-point super-tile and emitting 32-bit hit masks
-// (one word per 32 points per radius) into shared memory laid out [radius][word][centre]
-// (conflict-free both ways).  Because segments are contiguous index ranges, walking the words
-// in order afterwards yields exactly the reference's "first nsample hits in index order".
-// A warp holds 32 consecutive centres of ONE segment, so every point is one LDS.128 broadcast.
+// 32k threads, far too few for 148 SMs.  So each centre is scanned by kPeSeg threads; thread
+// (centre, seg) owns a contiguous quarter of the current 1024-point tile and keeps its hit
+// masks (one 32-bit word per 32 points per radius) in registers.  Segment hit counts go through
+// shared memory; each thread then knows where its hits start in the centre's neighbour row
+// (hits of earlier tiles + hits of lower segments) and appends them in index order -- exactly
+// the reference's "first nsample hits in index order".  A warp holds 32 consecutive centres
+// of ONE segment, so every point is a single LDS.128 broadcast.
 constexpr int kPeCentres = 64;   // centres per CTA
 constexpr int kPeSeg = 4;        // threads per centre
 constexpr int kPeThreads = kPeCentres * kPeSeg;
-constexpr int kPeTile = 1024;    // points per super-tile
-constexpr int kPeWords = kPeTile / 32;
+constexpr int kPeTile = 1024;    // points per tile
+constexpr int kPeSegWords = kPeTile / 32 / kPeSeg;  // mask words per thread per radius
 
+// CLOUD_IN_SMEM (N <= 4096): the whole cloud, padded to a multiple of kPeTile, is staged once as
+// float4 and serves both the scan and the final gather: a random 16-byte shared-memory read per
+// neighbour instead of three fully divergent global loads (32 L1 wavefronts each).
+template <bool CLOUD_IN_SMEM>
 __global__ void __launch_bounds__(kPeThreads)
 pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int ns1,
                  float *__restrict__ out1, float r2b, int ns2, float *__restrict__ out2) {
     extern __shared__ float4 s_dyn[];
-    float4 *s_pts = s_dyn;                                                   // kPeTile
-    unsigned *s_mask = reinterpret_cast<unsigned *>(s_dyn + kPeTile);        // [2][kPeWords][kPeCentres]
-    unsigned short *rows1 = reinterpret_cast<unsigned short *>(s_mask + 2 * kPeWords * kPeCentres);
+    const int n_pts_smem = CLOUD_IN_SMEM ? (N + kPeTile - 1) / kPeTile * kPeTile : kPeTile;
+    float4 *s_pts = s_dyn;                                                   // n_pts_smem
+    unsigned short *rows1 = reinterpret_cast<unsigned short *>(s_dyn + n_pts_smem);
     const int st1 = ns1 + 2, st2 = ns2 + 2;                                  // odd strides in 32-bit words
     unsigned short *rows2 = rows1 + kPeCentres * st1;
-    __shared__ int s_cnt[2][kPeCentres], s_first[2][kPeCentres];
+    __shared__ int s_seg[2][kPeSeg][kPeCentres];  // hits of (radius, segment, centre) in this tile
     const int tid = threadIdx.x, b = blockIdx.y, j0 = blockIdx.x * kPeCentres;
     const int c = tid & (kPeCentres - 1), seg = tid / kPeCentres;  // seg is warp-uniform
     const float *xyz_b = xyz + (size_t)b * N * 3;
@@ -559,70 +564,84 @@ pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int
         qy = __fadd_rn(xyz_b[3 * j + 1], eps);
         qz = __fadd_rn(xyz_b[3 * j + 2], eps);
     }
-    if (tid < 2 * kPeCentres) {
-        const int r = tid / kPeCentres, cc = tid - r * kPeCentres;
-        s_cnt[r][cc] = (j0 + cc < N) ? 0 : (r ? ns2 : ns1);
-        s_first[r][cc] = 0;
-    }
-    for (int base = 0; base < N; base += kPeTile) {
-        __syncthreads();  // previous tile (points and masks) fully consumed
-        const int nt = min(kPeTile, N - base);
-        for (int k = tid; k < kPeTile; k += kPeThreads) {
-            if (k < nt) {
-                const float *p = xyz_b + 3 * (size_t)(base + k);
+    unsigned short *row1 = rows1 + c * st1, *row2 = rows2 + c * st2;
+    int cnt1 = active ? 0 : ns1, cnt2 = active ? 0 : ns2;  // identical in the 4 threads of a centre
+    if (CLOUD_IN_SMEM) {
+        for (int k = tid; k < n_pts_smem; k += kPeThreads) {
+            if (k < N) {
+                const float *p = xyz_b + 3 * (size_t)k;
                 s_pts[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
             } else {
                 s_pts[k] = make_float4(3e18f, 3e18f, 3e18f, 0.f);  // d2 = +inf: never a hit
             }
         }
-        __syncthreads();
-        // scan this thread's quarter of the tile: kPeWords / kPeSeg words of 32 points
-#pragma unroll 1
-        for (int w = 0; w < kPeWords / kPeSeg; ++w) {
-            const int word = seg * (kPeWords / kPeSeg) + w;
-            const float4 *pp = s_pts + word * 32;
-            unsigned m1 = 0u, m2 = 0u;
+    }
+    for (int base = 0; base < N; base += kPeTile) {
+        if (__syncthreads_and(cnt1 >= ns1 && cnt2 >= ns2)) break;  // every list of this CTA is full
+        if (!CLOUD_IN_SMEM) {
+            const int nt = min(kPeTile, N - base);
+            for (int k = tid; k < kPeTile; k += kPeThreads) {
+                if (k < nt) {
+                    const float *p = xyz_b + 3 * (size_t)(base + k);
+                    s_pts[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+                } else {
+                    s_pts[k] = make_float4(3e18f, 3e18f, 3e18f, 0.f);
+                }
+            }
+            __syncthreads();
+        }
+        const float4 *tile = CLOUD_IN_SMEM ? s_pts + base : s_pts;
+        unsigned m1[kPeSegWords], m2[kPeSegWords];
+        int h1 = 0, h2 = 0;
+#pragma unroll
+        for (int w = 0; w < kPeSegWords; ++w) {
+            const float4 *pp = tile + (seg * kPeSegWords + w) * 32;
+            unsigned a1 = 0u, a2 = 0u;
 #pragma unroll
             for (int u = 0; u < 32; ++u) {
                 const float4 p = pp[u];
                 const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
-                if (d2 < r2a) m1 |= 1u << u;
-                if (d2 < r2b) m2 |= 1u << u;
+                if (d2 < r2a) a1 |= 1u << u;
+                if (d2 < r2b) a2 |= 1u << u;
             }
-            s_mask[(0 * kPeWords + word) * kPeCentres + c] = m1;
-            s_mask[(1 * kPeWords + word) * kPeCentres + c] = m2;
+            m1[w] = a1; m2[w] = a2;
+            h1 += __popc(a1); h2 += __popc(a2);
         }
+        s_seg[0][seg][c] = h1;
+        s_seg[1][seg][c] = h2;
         __syncthreads();
-        // in-order extraction: one thread per (radius, centre)
-        bool done = true;
-        if (tid < 2 * kPeCentres) {
-            const int r = tid / kPeCentres, cc = tid - r * kPeCentres;
-            const int ns = r ? ns2 : ns1;
-            unsigned short *row = (r ? rows2 + cc * st2 : rows1 + cc * st1);
-            int cnt = s_cnt[r][cc], first = s_first[r][cc];
-            for (int word = 0; word < kPeWords && cnt < ns; ++word) {
-                unsigned m = s_mask[(r * kPeWords + word) * kPeCentres + cc];
-                while (m != 0u && cnt < ns) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1u;
-                    const int id = base + word * 32 + bit;
-                    if (cnt == 0) first = id;
-                    row[cnt++] = (unsigned short)id;
-                }
-            }
-            s_cnt[r][cc] = cnt;
-            s_first[r][cc] = first;
-            done = cnt >= ns;
+        // where this thread's hits start, and the centre's new totals
+        int off1 = cnt1, off2 = cnt2, tot1 = cnt1, tot2 = cnt2;
+#pragma unroll
+        for (int sg = 0; sg < kPeSeg; ++sg) {
+            const int a1 = s_seg[0][sg][c], a2 = s_seg[1][sg][c];
+            if (sg < seg) { off1 += a1; off2 += a2; }
+            tot1 += a1; tot2 += a2;
         }
-        if (__syncthreads_and(done)) break;  // every list of this CTA is full
+        const int id0 = base + seg * kPeSegWords * 32;
+#pragma unroll
+        for (int w = 0; w < kPeSegWords; ++w) {
+            unsigned m = m1[w];
+            while (m != 0u && off1 < ns1) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1u;
+                row1[off1++] = (unsigned short)(id0 + w * 32 + bit);
+            }
+            m = m2[w];
+            while (m != 0u && off2 < ns2) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1u;
+                row2[off2++] = (unsigned short)(id0 + w * 32 + bit);
+            }
+        }
+        cnt1 = min(tot1, ns1);
+        cnt2 = min(tot2, ns2);
     }
     __syncthreads();
-    if (tid < 2 * kPeCentres) {  // back-fill with the first hit; no hit -> zeros
-        const int r = tid / kPeCentres, cc = tid - r * kPeCentres;
-        const int ns = r ? ns2 : ns1;
-        unsigned short *row = (r ? rows2 + cc * st2 : rows1 + cc * st1);
-        const unsigned short f = (unsigned short)s_first[r][cc];
-        for (int l = s_cnt[r][cc]; l < ns; ++l) row[l] = f;
+    if (active && seg == 0) {  // back-fill with the first hit; no hit -> zeros
+        const unsigned short f1 = cnt1 ? row1[0] : (unsigned short)0, f2 = cnt2 ? row2[0] : (unsigned short)0;
+        for (int l = cnt1; l < ns1; ++l) row1[l] = f1;
+        for (int l = cnt2; l < ns2; ++l) row2[l] = f2;
     }
     __syncthreads();
     const int rows = min(kPeCentres, N - j0);
@@ -632,15 +651,24 @@ pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int
         const unsigned short *rw = s ? rows2 : rows1;
         const size_t plane = (size_t)N * nss;
         float *out_b = (s ? out2 : out1) + (size_t)b * 6 * plane + (size_t)j0 * nss;
+        const bool pow2 = (nss & (nss - 1)) == 0;
+        const int sh = 31 - __clz(nss);
         for (int e = tid; e < rows * nss; e += kPeThreads) {
-            const int jj = e / nss, l = e - jj * nss;
+            const int jj = pow2 ? (e >> sh) : (e / nss), l = e - jj * nss;
             const int a = rw[jj * stride + l];
-            const float *p = xyz_b + 3 * (size_t)a;
-            const float *q = xyz_b + 3 * (size_t)(j0 + jj);
-            const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
-            out_b[e] = __fsub_rn(px, __fadd_rn(__ldg(q), eps));
-            out_b[plane + e] = __fsub_rn(py, __fadd_rn(__ldg(q + 1), eps));
-            out_b[2 * plane + e] = __fsub_rn(pz, __fadd_rn(__ldg(q + 2), eps));
+            float px, py, pz, cx, cy, cz;
+            if (CLOUD_IN_SMEM) {
+                const float4 p = s_pts[a], q = s_pts[j0 + jj];
+                px = p.x; py = p.y; pz = p.z; cx = q.x; cy = q.y; cz = q.z;
+            } else {
+                const float *p = xyz_b + 3 * (size_t)a;
+                const float *q = xyz_b + 3 * (size_t)(j0 + jj);
+                px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+                cx = __ldg(q); cy = __ldg(q + 1); cz = __ldg(q + 2);
+            }
+            out_b[e] = __fsub_rn(px, __fadd_rn(cx, eps));
+            out_b[plane + e] = __fsub_rn(py, __fadd_rn(cy, eps));
+            out_b[2 * plane + e] = __fsub_rn(pz, __fadd_rn(cz, eps));
             out_b[3 * plane + e] = px;
             out_b[4 * plane + e] = py;
             out_b[5 * plane + e] = pz;
@@ -789,13 +817,21 @@ extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, f
     PEM_REQUIRE_PTR(out2);
     PEM_REQUIRE(B > 0 && N > 0 && nsample1 > 0 && nsample2 > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(nsample1 <= 128 && nsample2 <= 128 && N <= 65535, PEM_E_UNSUPPORTED);
-    const size_t smem = (size_t)kPeTile * sizeof(float4) +
-                        (size_t)2 * kPeWords * kPeCentres * sizeof(unsigned) +
+    const bool in_smem = N <= 4096;  // whole cloud as float4: <= 64 KB
+    const size_t n_pts = in_smem ? (size_t)(N + kPeTile - 1) / kPeTile * kPeTile : (size_t)kPeTile;
+    const size_t smem = n_pts * sizeof(float4) +
                         (size_t)kPeCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
-    static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(pe_group2_kernel, smem, &cached)) return rc;
-    pe_group2_kernel<<<dim3((N + kPeCentres - 1) / kPeCentres, B), kPeThreads, smem,
-                       pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,
-                                                radius2 * radius2, nsample2, out2);
+    const dim3 grid((N + kPeCentres - 1) / kPeCentres, B);
+    if (in_smem) {
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true>, smem, &cached)) return rc;
+        pe_group2_kernel<true><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
+            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2);
+    } else {
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<false>, smem, &cached)) return rc;
+        pe_group2_kernel<false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
+            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2);
+    }
     return pem_launch_status();
 }

@@ -164,3 +164,11 @@ def test_pe_group2_fused_bit_exact(pkg, oracle, dev):
     w2, _ = oracle.query_and_group(xyz.numpy(), (xyz + 1e-8).numpy(), feat.numpy(), 0.6, 128)
     np.testing.assert_array_equal(o1.cpu().numpy(), w1)
     np.testing.assert_array_equal(o2.cpu().numpy(), w2)
+    # cloud larger than the shared-memory staging limit (tiled path with global gathers)
+    xyz = (torch.randn(1, 5000, 3, generator=g) * 0.3).contiguous()
+    o1, o2 = pkg.pointnet2_utils.pe_group2(xyz.to(dev), 0.1, 32, 0.2, 64)
+    feat = xyz.transpose(1, 2).contiguous()
+    w1, _ = oracle.query_and_group(xyz.numpy(), (xyz + 1e-8).numpy(), feat.numpy(), 0.1, 32)
+    w2, _ = oracle.query_and_group(xyz.numpy(), (xyz + 1e-8).numpy(), feat.numpy(), 0.2, 64)
+    np.testing.assert_array_equal(o1.cpu().numpy(), w1)
+    np.testing.assert_array_equal(o2.cpu().numpy(), w2)

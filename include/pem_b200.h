@@ -240,6 +240,14 @@ int pem_weighted_procrustes(const float *src, const float *ref, const float *wei
                             int n, float weight_thresh, float eps, float *R, float *t,
                             pem_stream_t stream);
 
+/*
+ * Pack the per-instance result into the 64-byte record the multi-GPU gather moves
+ * (no reference counterpart): records (B,16) fp32 = R (9) | t (3) | pose_score |
+ * proposal id | instance id | 0.  proposal_id and instance_id may be NULL.
+ */
+int pem_pack_records(const float *R, const float *t, const float *score, const int32_t *proposal_id,
+                     const float *instance_id, int B, float *records, pem_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,12 @@
 // FP32-pipe-bound kernel: model points are staged once per CTA as (-2m, |m|^2) float4 so a
 // pair costs 3 FFMA + 1 FMNMX, each LDS.128 broadcast is reused by up to 8 register-held
 // query points per thread, and background points (w1 = 0) are compacted away up front.
+#include <cooperative_groups.h>
+
 #include "pem_common.cuh"
 #include "svd3.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pem {
 
@@ -176,6 +180,179 @@ coarse_assign_kernel(const float *__restrict__ atten, int N1, int N2, float *__r
     }
 }
 
+// Cluster version: the (N1+1) x (N2+1) matrix is split into kAsgCl row slabs, one per CTA of a
+// thread-block cluster (one cluster per instance), so the front half of compute_coarse_Rt runs on
+// kAsgCl SMs instead of one.  Row statistics are slab-local; column statistics, the column
+// foreground test and the prefix-sum offsets are exchanged through distributed shared memory
+// (four exchanges, each a burst of remote stores + one cluster barrier).  Arithmetic is the
+// reference's: softmax factors exp(s - max)/sum per row and per column, fp64 scan rounded to fp32.
+constexpr int kAsgCl = 4;
+
+__global__ void __launch_bounds__(1024, 1)
+coarse_assign_cluster_kernel(const float *__restrict__ atten, int N1, int N2, float *__restrict__ w1,
+                             float *__restrict__ w2, float *__restrict__ cdf) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / kAsgCl;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int R = N1 + 1, Cn = N2 + 1, tid = threadIdx.x;
+    const int per = (R + kAsgCl - 1) / kAsgCl;
+    const int r0 = rank * per, nr = max(0, min(per, R - r0));  // this CTA owns rows [r0, r0+nr)
+    double *s_scan = reinterpret_cast<double *>(s_raw);          // 34 doubles
+    double *s_tot = s_scan + 34;                                 // kAsgCl slab totals
+    float *S = reinterpret_cast<float *>(s_tot + kAsgCl);        // per*Cn
+    float *xch = S + per * Cn;                                   // [kAsgCl][Cn] exchange buffer A
+    float *xch2 = xch + kAsgCl * Cn;                             // [kAsgCl][Cn] exchange buffer B
+    float *rmax = xch2 + kAsgCl * Cn, *rinv = rmax + per;        // per each
+    float *cmax = rinv + per, *cinv = cmax + Cn, *p0 = cinv + Cn, *w2s = p0 + Cn;  // Cn each
+    float *w1s = w2s + Cn;                                       // per
+
+    const float *A = atten + ((size_t)b * R + r0) * Cn;
+    for (int e = tid; e < nr * Cn; e += 1024) S[e] = __ldg(A + e);
+    __syncthreads();
+
+    // ---- maxima: rows local, columns exchanged -------------------------------------------
+    for (int i = warp_id(); i < nr; i += 32) {
+        float m = -INFINITY;
+        for (int j = lane_id(); j < Cn; j += 32) m = fmaxf(m, S[i * Cn + j]);
+        m = warp_max(m);
+        if (lane_id() == 0) rmax[i] = m;
+    }
+    for (int j = warp_id(); j < Cn; j += 32) {
+        float m = -INFINITY;
+        for (int i = lane_id(); i < nr; i += 32) m = fmaxf(m, S[i * Cn + j]);
+        m = warp_max(m);
+        if (lane_id() < kAsgCl) *cluster.map_shared_rank(&xch[rank * Cn + j], lane_id()) = m;
+    }
+    cluster.sync();
+    for (int j = tid; j < Cn; j += 1024) {
+        float m = xch[j];
+#pragma unroll
+        for (int q = 1; q < kAsgCl; ++q) m = fmaxf(m, xch[q * Cn + j]);
+        cmax[j] = m;
+    }
+    __syncthreads();
+    // ---- sums of exp: rows local, columns exchanged (fixed rank order: deterministic) -------
+    for (int i = warp_id(); i < nr; i += 32) {
+        float sm = 0.f;
+        for (int j = lane_id(); j < Cn; j += 32) sm += expf(S[i * Cn + j] - rmax[i]);
+        sm = warp_sum(sm);
+        if (lane_id() == 0) rinv[i] = sm;
+    }
+    for (int j = warp_id(); j < Cn; j += 32) {
+        float sm = 0.f;
+        for (int i = lane_id(); i < nr; i += 32) sm += expf(S[i * Cn + j] - cmax[j]);
+        sm = warp_sum(sm);
+        if (lane_id() < kAsgCl) *cluster.map_shared_rank(&xch2[rank * Cn + j], lane_id()) = sm;
+    }
+    cluster.sync();
+    for (int j = tid; j < Cn; j += 1024) {
+        float sm = xch2[j];
+#pragma unroll
+        for (int q = 1; q < kAsgCl; ++q) sm += xch2[q * Cn + j];
+        cinv[j] = sm;
+    }
+    __syncthreads();
+    // ---- P = softmax(dim=2) * softmax(dim=1), in place (MU:230) ------------------------------
+    for (int e = tid; e < nr * Cn; e += 1024) {
+        const int i = e / Cn, j = e - i * Cn;
+        const float v = S[e];
+        S[e] = __fdiv_rn(expf(v - rmax[i]), rinv[i]) * __fdiv_rn(expf(v - cmax[j]), cinv[j]);
+    }
+    __syncthreads();
+    // ---- foreground masks (MU:231-234) --------------------------------------------------------
+    for (int i = warp_id(); i < nr; i += 32) {
+        float m = -INFINITY;
+        for (int j = 1 + lane_id(); j < Cn; j += 32) m = fmaxf(m, S[i * Cn + j]);
+        m = warp_max(m);
+        if (lane_id() == 0) {
+            const float f = (m > S[i * Cn]) ? 1.f : 0.f;
+            w1s[i] = f;
+            if (r0 + i >= 1) w1[(size_t)b * N1 + r0 + i - 1] = f;
+        }
+    }
+    for (int j = warp_id(); j < Cn; j += 32) {  // column max over rows >= 1 of this slab; row 0 itself
+        float m = -INFINITY;
+        for (int i = lane_id(); i < nr; i += 32)
+            if (r0 + i >= 1) m = fmaxf(m, S[i * Cn + j]);
+        m = warp_max(m);
+        if (lane_id() < kAsgCl) {
+            *cluster.map_shared_rank(&xch[rank * Cn + j], lane_id()) = m;
+            if (rank == 0) *cluster.map_shared_rank(&p0[j], lane_id()) = S[j];
+        }
+    }
+    cluster.sync();
+    for (int j = tid; j < Cn; j += 1024) {
+        float m = xch[j];
+#pragma unroll
+        for (int q = 1; q < kAsgCl; ++q) m = fmaxf(m, xch[q * Cn + j]);
+        const float f = (j >= 1 && m > p0[j]) ? 1.f : 0.f;
+        w2s[j] = f;
+        if (rank == 0 && j >= 1) w2[(size_t)b * N2 + j - 1] = f;
+    }
+    __syncthreads();
+    // ---- score**1.5 -> fp64 prefix sum rounded to fp32 per element -> / (last + 1e-8) ----------
+    // this slab's share of the flattened [1:,1:] block: rows max(r0,1) .. r0+nr-1
+    const int i_lo = max(r0, 1) - r0;                 // first local row that belongs to the block
+    const int n_el = max(0, nr - i_lo) * N2;          // elements of this slab
+    const int chunk = (n_el + 1023) / 1024;
+    const int e0 = min(n_el, tid * chunk), e1 = min(n_el, e0 + chunk);
+    auto q_at = [&](int il, int j) { return pow15(S[il * Cn + j + 1] * w1s[il] * w2s[j + 1]); };
+    double local = 0.0;
+    {
+        int il = i_lo + e0 / N2, j = e0 - (e0 / N2) * N2;
+        for (int e = e0; e < e1; ++e) {
+            local += (double)q_at(il, j);
+            if (++j == N2) { j = 0; ++il; }
+        }
+    }
+    double inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double nb = __shfl_up_sync(kFull, inc, o);
+        if (lane_id() >= o) inc += nb;
+    }
+    if (lane_id() == 31) s_scan[warp_id()] = inc;
+    __syncthreads();
+    if (warp_id() == 0) {
+        const double v = s_scan[lane_id()];
+        double winc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double nb = __shfl_up_sync(kFull, winc, o);
+            if (lane_id() >= o) winc += nb;
+        }
+        s_scan[lane_id()] = winc - v;
+        if (lane_id() == 31) s_scan[32] = winc;  // slab total
+    }
+    __syncthreads();
+    if (tid < kAsgCl) *cluster.map_shared_rank(&s_tot[rank], tid) = s_scan[32];
+    cluster.sync();
+    double offset = 0.0, total = 0.0;
+#pragma unroll
+    for (int q = 0; q < kAsgCl; ++q) {
+        if (q < rank) offset += s_tot[q];
+        total += s_tot[q];
+    }
+    double run = offset + s_scan[warp_id()] + (inc - local);
+    const float denom = (float)total + 1e-8f;
+    float *out = cdf + (size_t)b * N1 * N2 + (size_t)(max(r0, 1) - 1) * N2;
+    {
+        int il = i_lo + e0 / N2, j = e0 - (e0 / N2) * N2;
+        for (int e = e0; e < e1; ++e) {
+            run += (double)q_at(il, j);
+            out[e] = __fdiv_rn((float)run, denom);
+            if (++j == N2) { j = 0; ++il; }
+        }
+    }
+    cluster.sync();  // keep shared memory alive until every peer's remote stores have landed
+}
+
+static size_t coarse_assign_cluster_smem(int N1, int N2) {
+    const size_t R = N1 + 1, Cn = N2 + 1, per = (R + kAsgCl - 1) / kAsgCl;
+    return (34 + kAsgCl) * sizeof(double) + (per * Cn + 2 * kAsgCl * Cn + 3 * per + 4 * Cn) * sizeof(float);
+}
+
 static size_t coarse_assign_smem(int N1, int N2) {
     const size_t R = N1 + 1, Cn = N2 + 1;
     return 34 * sizeof(double) + (R * Cn + 3 * R + 3 * Cn) * sizeof(float);
@@ -189,17 +366,31 @@ coarse_hypotheses_kernel(const float *__restrict__ cdf, const float *__restrict_
                          const float *__restrict__ pts1, const float *__restrict__ pts2, int N1,
                          int N2, int P1, float *__restrict__ Rout, float *__restrict__ tout,
                          float *__restrict__ resid, int32_t *__restrict__ corr) {
+    // two-level lower bound: a shared-memory index holds every kStride-th cdf entry, so only the
+    // last log2(kStride) probes (one or two cache lines) go to global memory
+    constexpr int kStride = 64, kMaxIdx = 1024;
+    __shared__ float s_idx[kMaxIdx];
     const int b = blockIdx.y, h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= P1) return;
     const int E = N1 * N2;
     const float *c = cdf + (size_t)b * E;
+    const int n_idx = min(kMaxIdx, (E + kStride - 1) / kStride);  // entry k = c[min(E, (k+1)*kStride) - 1]
+    for (int k = threadIdx.x; k < n_idx; k += blockDim.x) s_idx[k] = __ldg(c + min(E, (k + 1) * kStride) - 1);
+    __syncthreads();
+    if (h >= P1) return;
     const size_t hb = (size_t)b * P1 + h;
     float p1[3][3], p2[3][3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const float r = __ldg(rnd + hb * 3 + d);
-        int lo = 0, hi = E;  // first e with c[e] >= r (MU:277-305); none -> 0
-        while (lo < hi) {
+        // first block whose last element is >= r (blocks beyond the index are searched directly)
+        int blo = 0, bhi = n_idx;
+        while (blo < bhi) {
+            const int mid = (blo + bhi) >> 1;
+            if (s_idx[mid] >= r) bhi = mid; else blo = mid + 1;
+        }
+        int lo = blo * kStride, hi = (blo < n_idx) ? min(E, (blo + 1) * kStride) - 1 : E;
+        // invariant: c[hi] >= r when blo < n_idx (hi is a valid answer), everything before lo is < r
+        while (lo < hi) {  // first e with c[e] >= r (MU:277-305); none -> 0
             const int mid = (lo + hi) >> 1;
             if (__ldg(c + mid) >= r) hi = mid; else lo = mid + 1;
         }
@@ -523,6 +714,27 @@ extern "C" int pem_coarse_assign(const float *atten, int B, int N1, int N2, floa
     PEM_REQUIRE_PTR(w2);
     PEM_REQUIRE_PTR(cdf);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0, PEM_E_SHAPE);
+    if (N1 + 1 >= 8 * kAsgCl && (long long)((N1 + kAsgCl) / kAsgCl) * (N2 + 1) <= 40000) {
+        // thread-block cluster: kAsgCl SMs per instance
+        const size_t smem = coarse_assign_cluster_smem(N1, N2);
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(coarse_assign_cluster_kernel, smem, &cached)) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(B * kAsgCl);
+        cfg.blockDim = dim3(1024);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = pem_cu_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kAsgCl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, coarse_assign_cluster_kernel, atten, N1, N2, w1, w2, cdf);
+        if (e != cudaSuccess) return (int)e;
+        return pem_launch_status();
+    }
     PEM_REQUIRE((long long)(N1 + 1) * (N2 + 1) <= 50176, PEM_E_UNSUPPORTED);
     const size_t smem = coarse_assign_smem(N1, N2);
     static size_t cached = 0;

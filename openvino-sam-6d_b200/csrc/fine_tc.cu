@@ -477,9 +477,16 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------- prep / finish
 // One warp per padded row: x / max(|x|,1e-12) split into bf16 hi and lo.
 __global__ void __launch_bounds__(256)
-tc_prep_kernel(const float *__restrict__ f, int B, int rows, int rows_p, int C, int normalize,
-               __nv_bfloat16 *__restrict__ out /* (2, B*rows_p, C) */) {
-    const int gr = blockIdx.x * (blockDim.x >> 5) + warp_id();
+tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloat16 *__restrict__ outa,
+               const float *__restrict__ fb, int rows_b, int rows_pb, __nv_bfloat16 *__restrict__ outb,
+               int B, int C, int normalize) {
+    // both operands in one launch: warps [0, B*rows_pa) prepare A', the rest prepare B'
+    int gr = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const bool second = gr >= B * rows_pa;
+    if (second) gr -= B * rows_pa;
+    const float *f = second ? fb : fa;
+    const int rows = second ? rows_b : rows_a, rows_p = second ? rows_pb : rows_pa;
+    __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
     if (gr >= B * rows_p) return;
     const int b = gr / rows_p, i = gr - b * rows_p;
     __nv_bfloat16 *hi = out + (size_t)gr * C, *lo = out + ((size_t)B * rows_p + gr) * C;
@@ -715,8 +722,8 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
                 PEM_E_WORKSPACE);
     cudaStream_t st = pem_cu_stream(stream);
     Ws w = carve(workspace, B, N1p - 1, N2p - 1, C);
-    tc_prep_kernel<<<(B * p.Mp + 7) / 8, 256, 0, st>>>(f1, B, p.R, p.Mp, C, normalize, w.A);
-    tc_prep_kernel<<<(B * p.Np + 7) / 8, 256, 0, st>>>(f2, B, p.Cn, p.Np, C, normalize, w.Bm);
+    tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
+                                                                 C, normalize);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
@@ -749,8 +756,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     float *rsA = rowsum_out ? rowsum_out : w.rowsumA;
     float *pred = pred_out ? pred_out : w.pred;
 
-    tc_prep_kernel<<<(B * p.Mp + 7) / 8, 256, 0, st>>>(f1, B, p.R, p.Mp, C, 1, w.A);
-    tc_prep_kernel<<<(B * p.Np + 7) / 8, 256, 0, st>>>(f2, B, p.Cn, p.Np, C, 1, w.Bm);
+    tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
+                                                                 C, 1);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;

@@ -687,6 +687,9 @@ static size_t bq_smem_bytes(int ns) {
 // ------------------------------------------------------------------------------------
 using namespace pem;
 
+static int g_fps_variant = 0;
+extern "C" void pem_dev_set_fps_variant(int v) { g_fps_variant = v; }
+
 extern "C" size_t pem_fps_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 16 * 16384) return 0;
     return (size_t)B * N * sizeof(float);
@@ -700,7 +703,14 @@ extern "C" int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t
     cudaStream_t st = pem_cu_stream(stream);
     const int skip = (flags & PEM_FPS_SKIP_NEAR_ORIGIN) ? 1 : 0;
     if (N <= 1024) return launch_fps_cta<128, 8, true>(xyz, B, N, M, skip, idx, st);
-    if (N <= 2048) return launch_fps_cta<256, 8, true>(xyz, B, N, M, skip, idx, st);
+    if (N <= 2048) {
+        switch (g_fps_variant) {  // development knob (pem_dev_set_fps_variant); 0 = shipped choice
+            case 2: return launch_fps_cta<512, 4, true>(xyz, B, N, M, skip, idx, st);
+            case 3: return launch_fps_cta<1024, 2, true>(xyz, B, N, M, skip, idx, st);
+            case 4: return launch_fps_cta<256, 8, true>(xyz, B, N, M, skip, idx, st);
+            default: return launch_fps_cta<128, 16, true>(xyz, B, N, M, skip, idx, st);  // fewest warps to synchronise
+        }
+    }
     if (N <= 4096) return launch_fps_cta<512, 8, true>(xyz, B, N, M, skip, idx, st);
     if (N <= 8192) return launch_fps_cta<1024, 8, true>(xyz, B, N, M, skip, idx, st);
     // larger clouds: thread-block clusters (slabs of <= 8192 points in registers), as long as the
@@ -833,5 +843,35 @@ extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, f
         pe_group2_kernel<false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
             xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2);
     }
+    return pem_launch_status();
+}
+
+// 64-byte per-instance pose records (R 9 | t 3 | score | proposal id | instance id | pad): the
+// unit the multi-GPU gather moves.
+__global__ void pack_records_kernel(const float *__restrict__ R, const float *__restrict__ t,
+                                    const float *__restrict__ score, const int32_t *__restrict__ pid,
+                                    const float *__restrict__ inst, int B, float *__restrict__ rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 16) return;
+    const int b = i >> 4, k = i & 15;
+    float v = 0.f;
+    if (k < 9) v = R[b * 9 + k];
+    else if (k < 12) v = t[b * 3 + k - 9];
+    else if (k == 12) v = score[b];
+    else if (k == 13) v = pid ? (float)pid[b] : 0.f;
+    else if (k == 14) v = inst ? inst[b] : (float)b;
+    rec[i] = v;
+}
+
+extern "C" int pem_pack_records(const float *R, const float *t, const float *score,
+                                const int32_t *proposal_id, const float *instance_id, int B,
+                                float *records, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(R);
+    PEM_REQUIRE_PTR(t);
+    PEM_REQUIRE_PTR(score);
+    PEM_REQUIRE_PTR(records);
+    PEM_REQUIRE(B > 0, PEM_E_SHAPE);
+    pack_records_kernel<<<(B * 16 + 255) / 256, 256, 0, pem_cu_stream(stream)>>>(R, t, score, proposal_id,
+                                                                                instance_id, B, records);
     return pem_launch_status();
 }

@@ -152,17 +152,13 @@ class GeometricStage:
             ck(L.pem_fine_fused(p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]),
                                 p(self.model), B, N, N, C, Nm, self.temp, self.dis_thres, p(self.R),
                                 p(self.t), p(self.score), None, None, None, None, p(self.ws),
-                                self.ws_bytes, st), "fine_fused"); n += 11
+                                self.ws_bytes, st), "fine_fused"); n += 10
         else:
             self._enqueue_fine_materialised(); n += 12
         self.stream.wait_stream(self.side)  # join
         # 64-byte records
-        self.records[:, 0:9].copy_(self.R)
-        self.records[:, 9:12].copy_(self.t)
-        self.records[:, 12].copy_(self.score)
-        self.records[:, 13].copy_(self.proposal_id)
-        self.records[:, 14].copy_(self.instance_ids)
-        n += 5
+        ck(L.pem_pack_records(p(self.R), p(self.t), p(self.score), p(self.proposal_id),
+                              p(self.instance_ids), B, p(self.records), st), "pack_records"); n += 1
         self.kernels_per_step = n
 
     def _enqueue_fine_materialised(self):

@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu(pkg):
     assert lib.pem_fps(p, 1, 300000, 2, 1, p, None, 0, None) == -4      # needs a workspace
     assert lib.pem_gather(p, p, 1, 0, 8, 2, p, None) == -2
     assert lib.pem_ball_query(p, p, 1, 4, 4, 0.1, 500, p, None) == -3   # nsample > 128
-    assert lib.pem_coarse_assign(p, 1, 300, 300, p, p, p, None) == -3   # matrix exceeds one SM
+    assert lib.pem_coarse_assign(p, 1, 500, 500, p, p, p, None) == -3   # matrix exceeds the cluster capacity
     assert lib.pem_select_smallest(p, 1, 10, 11, p, None) == -2         # P2 > P1
     assert lib.pem_fine_Rt(p, p, p, p, 1, 8, 8, 8, 0.15, p, p, p, None, None, None, None, None, 0, None) == -4
     assert lib.pem_fps_workspace_bytes(4, 2048) == 0

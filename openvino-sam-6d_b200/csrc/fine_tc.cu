@@ -474,6 +474,366 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// =========================================================================================
+// TS-mode variant: the RESIDENT operand lives in tensor memory and is the MMA's A operand
+// (tcgen05.mma ... [d_tmem], [a_tmem], b_desc), so each MMA fetches only the streamed operand
+// from shared memory (4 KB per 64 cycles instead of 8 KB).  In SS mode operand fetch alone asks
+// for the SM's full 128 B/clk shared-memory bandwidth, and TMA writes (42 B/clk) push it over.
+//
+// TMEM budget (512 columns): accumulators 2 x 128, resident strip hi 128 + lo 128 (two bf16 per
+// 32-bit column, lane = row).  The freed shared memory becomes a 12-stage ring.
+// Orientation: lanes (threads) index the resident strip.  Passes 1-2 run on the TRANSPOSED
+// problem (resident = 128 columns of S, i.e. rows of B'; streamed = rows of S) so that the column
+// statistics are thread-local across the task and the row statistics are per-tile cross-lane
+// folds written as per-strip partials -- the same outputs as the SS kernel, so the finish kernels
+// are shared.  Pass 3 runs direct (resident = rows of S): its four per-row sums are thread-local.
+// Warps: 0 TMA, 1 MMA + TMEM alloc, 2-5 strip loaders (global -> registers -> tcgen05.st), 6-13
+// epilogue (two per lane quadrant, 64 tile columns each).
+constexpr int kTsStages = 12;
+constexpr int kTsThreads = 32 * 14;
+constexpr int kTsTmemCols = 512;
+constexpr int kTsAccCols = 0, kTsAhiCols = 256, kTsAloCols = 384;
+
+struct TsParams {
+    int B, KC, C;
+    int res_valid, str_valid;   // valid rows of the resident / streamed operand per instance
+    int res_pad, str_pad;       // padded rows per instance
+    int n_res_strips, n_str_tiles;
+    float c1, c2, temp;
+    const __nv_bfloat16 *res_op;  // prepped (2, B*res_pad, C): hi rows then lo rows
+    // kStats / kLabel (transposed: resident index = column j of S, streamed index = row i of S)
+    float *res_acc;         // (B,res_pad): colsum (kStats) or colmax over i>=1 (kLabel)
+    float *str_part;        // (B,n_res_strips,str_pad): rowpart / rowmaxpart
+    const float *res_const; // kLabel: lcs (B,res_pad)
+    const float *str_const; // kLabel: lrs (B,str_pad)
+    float *res_bg;          // kLabel: bgrow (B,res_pad): value at streamed index 0
+    float *str_bg;          // kLabel: bgcol (B,str_pad): value at resident index 0
+    // kWsum / kStore (direct: resident index = row i of S, streamed index = column j)
+    const float4 *G;        // (B,str_pad)
+    const float *w1;        // (B,res_valid-1)
+    const float *inv_rowsum;  // (B,res_pad)
+    float *rowsumA, *pred;  // (B,res_valid-1), (B,res_valid-1,3)
+    float *atten;           // kStore: (B,res_valid,str_valid)
+};
+
+struct TsSmem {
+    uint8_t b[kTsStages][kChunkBytes];
+    float4 tilec[2][BN];      // per-tile constants of the streamed index (kLabel: .x = lrs; kWsum: G)
+    float colred[2][4][BN];   // per-quadrant folds of the streamed index, double buffered
+    float red[2][BM];         // combine the two column halves of thread-local accumulators
+    uint64_t full[kTsStages], empty[kTsStages], a_full, a_free, tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void ts_epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kTsThreads, 1)
+fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    TsSmem &sm = *reinterpret_cast<TsSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = warp_id(), lane = lane_id();
+    const int n_tasks = p.B * p.n_res_strips;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTsStages; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), 1);
+        }
+        mbar_init(smem_u32(&sm.a_full), 4);  // one arrival per loader warp
+        mbar_init(smem_u32(&sm.a_free), 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&sm.tmem_full[a]), 1);
+            mbar_init(smem_u32(&sm.tmem_empty[a]), kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&sm.tmem_base)),
+                     "r"((uint32_t)kTsTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer: streamed operand ================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            const int b = task / p.n_res_strips;
+            for (int m = 0; m < p.n_str_tiles; ++m) {
+                const int row = b * p.str_pad + m * BN;
+                for (int kc = 0; kc < p.KC; ++kc) {
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl) {
+                        mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
+                            tma_load_2d(&tmStr, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]), kc * BK,
+                                        hl * p.B * p.str_pad + row);
+                        }
+                        __syncwarp();
+                        if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, a_phase = 0, acc_phase = 0;
+        const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
+        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            mbar_wait(smem_u32(&sm.a_full), a_phase);  // resident strip is in TMEM
+            a_phase ^= 1;
+            tc_fence_after();
+            for (int m = 0; m < p.n_str_tiles; ++m) {
+                mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(kTsAccCols + acc * BN);
+                for (int kc = 0; kc < p.KC; ++kc) {
+                    const uint32_t ah = tmem_base + (uint32_t)(kTsAhiCols + kc * 32);
+                    const uint32_t al = tmem_base + (uint32_t)(kTsAloCols + kc * 32);
+                    // streamed hi chunk: A_hi*B_hi + A_lo*B_hi
+                    mbar_wait(smem_u32(&sm.full[stage]), phase);
+                    tc_fence_after();
+                    uint64_t bd = desc(smem_u32(sm.b[stage]));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {  // K=16 bf16 = 8 TMEM columns / 32 smem bytes
+                            tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, (kc | k) != 0);
+                            tc_mma_bf16_ts(d, al + 8 * k, bd + 2 * k, kIdesc, 1);
+                        }
+                        tc_commit(smem_u32(&sm.empty[stage]));
+                    }
+                    __syncwarp();
+                    if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                    // streamed lo chunk: A_hi*B_lo
+                    mbar_wait(smem_u32(&sm.full[stage]), phase);
+                    tc_fence_after();
+                    bd = desc(smem_u32(sm.b[stage]));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, 1);
+                        tc_commit(smem_u32(&sm.empty[stage]));
+                        if (kc == p.KC - 1) {
+                            tc_commit(smem_u32(&sm.tmem_full[acc]));
+                            if (m == p.n_str_tiles - 1) tc_commit(smem_u32(&sm.a_free));  // strip may be replaced
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp < 6) {
+        // ================================ resident-strip loaders =======================
+        const int quad = warp & 3, row = quad * 32 + lane;
+        uint32_t free_phase = 0;
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            const int b = task / p.n_res_strips, s = task - b * p.n_res_strips;
+            mbar_wait(smem_u32(&sm.a_free), free_phase ^ 1);  // previous task's MMAs have retired
+            free_phase ^= 1;
+            tc_fence_after();
+            const size_t grow = (size_t)b * p.res_pad + (size_t)s * BM + row;
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {  // hi, lo
+                const uint4 *src = reinterpret_cast<const uint4 *>(
+                    p.res_op + ((size_t)part * p.B * p.res_pad + grow) * p.C);
+                for (int gq = 0; gq < p.KC; ++gq) {  // 64 bf16 = 32 packed columns per group
+                    uint32_t r[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 v = __ldg(src + gq * 8 + q);
+                        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+                    }
+                    tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                  (uint32_t)((part ? kTsAloCols : kTsAhiCols) + gq * 32), r);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.a_full));
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int quad = warp & 3;
+        const int half = (warp - 6) >> 2;
+        const int et = quad * 32 + lane;            // resident row owned by this thread
+        const int ep_tid = (warp - 6) * 32 + lane;  // 0..255
+        const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            const int b = task / p.n_res_strips, s = task - b * p.n_res_strips;
+            const int gr = s * BM + et;                 // resident index within the instance
+            const bool res_ok = gr < p.res_valid;
+            // thread constants / accumulators
+            float racc = (MODE == kLabel) ? -INFINITY : 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+            float rconst = 0.f, rconst_true = 0.f;
+            if (MODE == kStats) rconst = res_ok ? kc2 : INFINITY;
+            if (MODE == kLabel) {
+                rconst_true = res_ok ? p.res_const[(size_t)b * p.res_pad + gr] : INFINITY;
+                rconst = (res_ok && gr >= 1) ? rconst_true : INFINITY;  // index 0 (background) excluded
+            }
+            const float str0_true = (MODE == kLabel) ? p.str_const[(size_t)b * p.str_pad] : 0.f;
+            // per-tile constants of the streamed index for tile 0
+            auto stage_tilec = [&](int m, int buf) {
+                if (ep_tid < BN) {
+                    const int gs = m * BN + ep_tid;
+                    const size_t o = (size_t)b * p.str_pad + gs;
+                    if (MODE == kLabel)
+                        sm.tilec[buf][ep_tid] =
+                            make_float4((gs >= 1 && gs < p.str_valid) ? p.str_const[o] : INFINITY, 0.f, 0.f, 0.f);
+                    if (MODE == kWsum) sm.tilec[buf][ep_tid] = p.G[o];
+                }
+            };
+            if (MODE == kLabel || MODE == kWsum) {
+                stage_tilec(0, 0);
+                ts_epi_barrier();
+            }
+            for (int m = 0; m < p.n_str_tiles; ++m) {
+                const int buf = m & 1;
+                if ((MODE == kLabel || MODE == kWsum) && m + 1 < p.n_str_tiles) stage_tilec(m + 1, buf ^ 1);
+                const int s0 = m * BN + half * kHalfCols;      // first streamed index of this warp
+                const int nvalid = min(kHalfCols, p.str_valid - s0);
+                mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < kHalfCols / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                  (uint32_t)(kTsAccCols + acc * BN + half * kHalfCols + c * 32), v);
+                    if (MODE == kStore) {
+                        if (res_ok) {
+                            float *dst = p.atten + ((size_t)b * p.res_valid + gr) * p.str_valid + s0 + c * 32;
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (c * 32 + q < nvalid) dst[q] = __fdiv_rn(v[q], ktemp);
+                        }
+                    } else if (MODE == kStats) {
+                        if (nvalid >= kHalfCols) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) { v[q] = ex2(fmaf(v[q], kc1, -rconst)); racc += v[q]; }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                v[q] = (c * 32 + q < nvalid) ? ex2(fmaf(v[q], kc1, -rconst)) : 0.f;
+                                racc += v[q];
+                            }
+                        }
+                        sm.colred[buf][quad][half * kHalfCols + c * 32 + lane] = warp_transpose_reduce<false>(v);
+                    } else if (MODE == kLabel) {
+                        if (m == 0 && half == 0 && c == 0 && res_ok)   // streamed index 0 = background row of S
+                            p.res_bg[(size_t)b * p.res_pad + gr] = fmaf(v[0], kc2x, -str0_true);
+                        if (gr == 0) {                                  // resident index 0 = background column
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (c * 32 + q < nvalid)
+                                    p.str_bg[(size_t)b * p.str_pad + s0 + c * 32 + q] = fmaf(v[q], kc2x, -rconst_true);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const float x = v[q] * kc2x;
+                            racc = fmaxf(racc, x - sm.tilec[buf][half * kHalfCols + c * 32 + q].x);
+                            v[q] = x - rconst;
+                        }
+                        sm.colred[buf][quad][half * kHalfCols + c * 32 + lane] = warp_transpose_reduce<true>(v);
+                    } else {  // kWsum
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const float e = ex2(fmaf(v[q], kc1, -kc2));
+                            const float u = e * e;
+                            const float4 g = sm.tilec[buf][half * kHalfCols + c * 32 + q];
+                            racc = fmaf(u, g.w, racc);
+                            r1 = fmaf(u, g.x, r1);
+                            r2 = fmaf(u, g.y, r2);
+                            r3 = fmaf(u, g.z, r3);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (MODE != kStore) ts_epi_barrier();  // colred[buf] complete; tilec[buf^1] staged
+                if (MODE == kStats || MODE == kLabel) {
+                    if (ep_tid < BN) {
+                        float x = sm.colred[buf][0][ep_tid];
+#pragma unroll
+                        for (int w = 1; w < 4; ++w)
+                            x = (MODE == kLabel) ? fmaxf(x, sm.colred[buf][w][ep_tid]) : x + sm.colred[buf][w][ep_tid];
+                        p.str_part[((size_t)b * p.n_res_strips + s) * p.str_pad + m * BN + ep_tid] = x;
+                    }
+                }
+            }
+            // thread-local accumulators: combine the two column halves, then store
+            if (MODE == kStats || MODE == kLabel) {
+                sm.red[half][et] = racc;
+                ts_epi_barrier();
+                if (half == 0 && res_ok) {
+                    const float a = sm.red[0][et], c2v = sm.red[1][et];
+                    p.res_acc[(size_t)b * p.res_pad + gr] = (MODE == kLabel) ? fmaxf(a, c2v) : a + c2v;
+                }
+                ts_epi_barrier();
+            } else if (MODE == kWsum) {
+                float4 *r4 = reinterpret_cast<float4 *>(&sm.colred[0][0][0]);  // 2 x 128 float4 of scratch
+                r4[half * BM + et] = make_float4(r1, r2, r3, racc);
+                ts_epi_barrier();
+                if (half == 0 && res_ok && gr >= 1) {
+                    const float4 a = r4[et], c4 = r4[BM + et];
+                    const size_t ri = (size_t)b * (p.res_valid - 1) + gr - 1;
+                    const float f = p.w1[ri] * p.inv_rowsum[(size_t)b * p.res_pad + gr];
+                    const float sA = (a.w + c4.w) * f;
+                    p.rowsumA[ri] = sA;                      // assignment_score (MU:330)
+                    const float inv = 1.0f / (sA + 1e-6f);   // MU:327
+                    p.pred[ri * 3 + 0] = (a.x + c4.x) * f * inv;
+                    p.pred[ri * 3 + 1] = (a.y + c4.y) * f * inv;
+                    p.pred[ri * 3 + 2] = (a.z + c4.z) * f * inv;
+                }
+                ts_epi_barrier();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)kTsTmemCols)
+                     : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------- prep / finish
 // One warp per padded row: x / max(|x|,1e-12) split into bf16 hi and lo.
 __global__ void __launch_bounds__(256)
@@ -676,6 +1036,18 @@ static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Par
     return pem_launch_status();
 }
 
+template <int MODE>
+static int launch_ts_pass(const CUtensorMap &tmStr, const TsParams &p, cudaStream_t st) {
+    const size_t smem = sizeof(TsSmem) + 1024;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(fine_ts_kernel<MODE>, smem, &cached)) return rc;
+    const int grid = min(num_sms(), p.B * p.n_res_strips);
+    fine_ts_kernel<MODE><<<grid, kTsThreads, smem, st>>>(tmStr, p);
+    return pem_launch_status();
+}
+
+static int g_fine_variant = 0;  // development knob: 0 = SS-mode kernel, 1 = TS-mode kernel
+
 static int fill_common(Params &p, int B, int N1, int N2, int C, float temp) {
     if (C % BK != 0 || C > BK * kMaxKC) return PEM_E_UNSUPPORTED;
     if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
@@ -693,6 +1065,8 @@ static int fill_common(Params &p, int B, int N1, int N2, int C, float temp) {
 
 using namespace pem;
 using namespace pem::tc;
+
+extern "C" void pem_dev_set_fine_variant(int v) { g_fine_variant = v; }
 
 // fine.cu
 namespace pem {
@@ -727,6 +1101,15 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
+    if (g_fine_variant == 1) {
+        TsParams q{};
+        q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
+        q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
+        q.n_res_strips = p.Mp / BM; q.n_str_tiles = p.Np / BN;
+        q.res_op = w.A;
+        q.atten = atten;
+        return launch_ts_pass<kStore>(tmB, q, st);
+    }
     p.atten = atten;
     return launch_pass<kStore>(tmA, tmB, p, st);
 }
@@ -762,8 +1145,39 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
 
-    const int n_part = 2 * p.n_strips;
     const int mx = max(p.Mp, p.Np);
+    if (g_fine_variant == 1) {
+        TsParams q{};
+        q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
+        const int n_part = p.n_strips;
+        // passes 1-2 on the transposed problem: resident = column strip of S (rows of B'),
+        // streamed = rows of S (tiles of A')
+        q.res_valid = p.Cn; q.str_valid = p.R; q.res_pad = p.Np; q.str_pad = p.Mp;
+        q.n_res_strips = p.Np / BM; q.n_str_tiles = p.Mp / BN;
+        q.res_op = w.Bm;
+        q.res_acc = w.colA;       // colsum
+        q.str_part = w.rowpart;   // (B, n_part, Mp)
+        if (int rc = launch_ts_pass<kStats>(tmA, q, st)) return rc;
+        tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+            w.rowpart, w.colA, p.R, p.Cn, p.Mp, p.Np, n_part, w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
+        q.res_const = w.lcs; q.str_const = w.lrs;
+        q.res_acc = w.colA;       // colmax
+        q.res_bg = w.colB;        // bgrow
+        q.str_bg = w.bgcol;
+        if (int rc = launch_ts_pass<kLabel>(tmA, q, st)) return rc;
+        tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+            w.rowpart, w.bgcol, w.colA, w.colB, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part, w1,
+            w2_out, w.G);
+        // pass 3 direct: resident = row strip of S (rows of A'), streamed = column tiles (B')
+        q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
+        q.n_res_strips = p.Mp / BM; q.n_str_tiles = p.Np / BN;
+        q.res_op = w.A;
+        q.G = w.G; q.w1 = w1; q.inv_rowsum = w.inv_rowsum; q.rowsumA = rsA; q.pred = pred;
+        if (int rc = launch_ts_pass<kWsum>(tmB, q, st)) return rc;
+        return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
+                                score, st);
+    }
+    const int n_part = 2 * p.n_strips;
     // pass 1: softmax statistics
     p.rowpart = w.rowpart;
     p.colsum = w.colA;

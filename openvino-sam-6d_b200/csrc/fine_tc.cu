@@ -124,6 +124,29 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// TMA load multicast to every CTA in `mask` (same shared-memory offset and mbarrier offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0,
+                                               int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -547,18 +570,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void ts_epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int MODE>
+// MC: clusters of two CTAs work on two resident strips of the SAME instance in lockstep and share
+// every streamed chunk: each CTA fetches half of it (64 rows, 8 KB) and multicasts it into both
+// CTAs' rings, halving the L2 -> SM traffic that otherwise bounds the kernel (~5.6 TB/s).
+template <int MODE, bool MC>
 __global__ void __launch_bounds__(kTsThreads, 1)
 fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
     extern __shared__ uint8_t smem_raw[];
     TsSmem &sm = *reinterpret_cast<TsSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id();
     const int n_tasks = p.B * p.n_res_strips;
+    // task walk: CTA-strided when alone; with MC the cluster walks pairs (2c, 2c+1) of strips
+    const int crank = MC ? (int)cluster_ctarank() : 0;
+    const int task0 = MC ? 2 * (int)(blockIdx.x >> 1) + crank : (int)blockIdx.x;
+    const int task_step = MC ? (int)gridDim.x : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTsStages; ++s) {
             mbar_init(smem_u32(&sm.full[s]), 1);
-            mbar_init(smem_u32(&sm.empty[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), MC ? 2 : 1);  // MC: both CTAs' MMAs must release a slot
         }
         mbar_init(smem_u32(&sm.a_full), 4);  // one arrival per loader warp
         mbar_init(smem_u32(&sm.a_free), 1);
@@ -579,12 +609,13 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+    if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
 
     if (warp == 0) {
         // ================================ TMA producer: streamed operand ================
         int stage = 0;
         uint32_t phase = 0;
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        for (int task = task0; task < n_tasks; task += task_step) {
             const int b = task / p.n_res_strips;
             for (int m = 0; m < p.n_str_tiles; ++m) {
                 const int row = b * p.str_pad + m * BN;
@@ -594,8 +625,13 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
                         mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
-                            tma_load_2d(&tmStr, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]), kc * BK,
-                                        hl * p.B * p.str_pad + row);
+                            if (MC)  // my half of the chunk (64 rows = 8 KB) into both CTAs
+                                tma_load_2d_mc(&tmStr, smem_u32(&sm.full[stage]),
+                                               smem_u32(sm.b[stage]) + crank * (kChunkBytes / 2), kc * BK,
+                                               hl * p.B * p.str_pad + row + crank * (BN / 2), (uint16_t)3);
+                            else
+                                tma_load_2d(&tmStr, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]), kc * BK,
+                                            hl * p.B * p.str_pad + row);
                         }
                         __syncwarp();
                         if (++stage == kTsStages) { stage = 0; phase ^= 1; }
@@ -609,7 +645,7 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
         uint32_t phase = 0, a_phase = 0, acc_phase = 0;
         const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
         auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        for (int task = task0; task < n_tasks; task += task_step) {
             mbar_wait(smem_u32(&sm.a_full), a_phase);  // resident strip is in TMEM
             a_phase ^= 1;
             tc_fence_after();
@@ -630,7 +666,8 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
                             tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, (kc | k) != 0);
                             tc_mma_bf16_ts(d, al + 8 * k, bd + 2 * k, kIdesc, 1);
                         }
-                        tc_commit(smem_u32(&sm.empty[stage]));
+                        if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
+                        else tc_commit(smem_u32(&sm.empty[stage]));
                     }
                     __syncwarp();
                     if (++stage == kTsStages) { stage = 0; phase ^= 1; }
@@ -641,7 +678,8 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, 1);
-                        tc_commit(smem_u32(&sm.empty[stage]));
+                        if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
+                        else tc_commit(smem_u32(&sm.empty[stage]));
                         if (kc == p.KC - 1) {
                             tc_commit(smem_u32(&sm.tmem_full[acc]));
                             if (m == p.n_str_tiles - 1) tc_commit(smem_u32(&sm.a_free));  // strip may be replaced
@@ -657,7 +695,7 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
         // ================================ resident-strip loaders =======================
         const int quad = warp & 3, row = quad * 32 + lane;
         uint32_t free_phase = 0;
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        for (int task = task0; task < n_tasks; task += task_step) {
             const int b = task / p.n_res_strips, s = task - b * p.n_res_strips;
             mbar_wait(smem_u32(&sm.a_free), free_phase ^ 1);  // previous task's MMAs have retired
             free_phase ^= 1;
@@ -692,7 +730,7 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
         const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        for (int task = task0; task < n_tasks; task += task_step) {
             const int b = task / p.n_res_strips, s = task - b * p.n_res_strips;
             const int gr = s * BM + et;                 // resident index within the instance
             const bool res_ok = gr < p.res_valid;
@@ -826,6 +864,7 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
 
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // the peer may still multicast into this CTA / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -961,12 +1000,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2D bf16 tensor (rows x C), box = 128 rows x 64 columns, SWIZZLE_128B
-static int make_operand_map(CUtensorMap *map, const void *base, size_t rows, int C) {
+static int make_operand_map(CUtensorMap *map, const void *base, size_t rows, int C, int box_rows = BM) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return PEM_E_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -983,10 +1022,11 @@ struct Ws {
     size_t bytes;
 };
 
-static int pad128(int x) { return (x + 127) / 128 * 128; }
+static int pad_to(int x, int g) { return (x + g - 1) / g * g; }
 
-static Ws carve(void *base, int B, int N1, int N2, int C) {
-    const size_t Mp = pad128(N1 + 1), Np = pad128(N2 + 1), ns = Np / 128;
+// g = row padding granularity of the operands: 128, or 256 for the multicast variant (strips in pairs)
+static Ws carve(void *base, int B, int N1, int N2, int C, int g) {
+    const size_t Mp = pad_to(N1 + 1, g), Np = pad_to(N2 + 1, g), ns = Np / 128;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t o = off;
@@ -1036,23 +1076,43 @@ static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Par
     return pem_launch_status();
 }
 
-template <int MODE>
+template <int MODE, bool MC>
 static int launch_ts_pass(const CUtensorMap &tmStr, const TsParams &p, cudaStream_t st) {
     const size_t smem = sizeof(TsSmem) + 1024;
     static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(fine_ts_kernel<MODE>, smem, &cached)) return rc;
-    const int grid = min(num_sms(), p.B * p.n_res_strips);
-    fine_ts_kernel<MODE><<<grid, kTsThreads, smem, st>>>(tmStr, p);
+    if (int rc = pem_ensure_dyn_smem(fine_ts_kernel<MODE, MC>, smem, &cached)) return rc;
+    if (!MC) {
+        const int grid = min(num_sms(), p.B * p.n_res_strips);
+        fine_ts_kernel<MODE, false><<<grid, kTsThreads, smem, st>>>(tmStr, p);
+        return pem_launch_status();
+    }
+    // clusters of 2: one cluster per SM pair, each walking pairs of strips
+    const int n_pairs = p.B * p.n_res_strips / 2;
+    const int n_clusters = min(num_sms() / 2, n_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_clusters);
+    cfg.blockDim = dim3(kTsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fine_ts_kernel<MODE, true>, tmStr, p);
+    if (e != cudaSuccess) return (int)e;
     return pem_launch_status();
 }
 
 static int g_fine_variant = 0;  // development knob: 0 = SS-mode kernel, 1 = TS-mode kernel
 
-static int fill_common(Params &p, int B, int N1, int N2, int C, float temp) {
+static int fill_common(Params &p, int B, int N1, int N2, int C, float temp, int g = 128) {
     if (C % BK != 0 || C > BK * kMaxKC) return PEM_E_UNSUPPORTED;
     if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
     p.B = B; p.R = N1 + 1; p.Cn = N2 + 1;
-    p.Mp = pad128(N1 + 1); p.Np = pad128(N2 + 1);
+    p.Mp = pad_to(N1 + 1, g); p.Np = pad_to(N2 + 1, g);
     p.n_mtiles = p.Mp / BM; p.n_strips = p.Np / BN; p.KC = C / BK;
     p.temp = temp;
     p.c1 = 1.4426950408889634f / temp;
@@ -1077,7 +1137,7 @@ int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA,
 
 extern "C" size_t pem_fine_fused_workspace_bytes(int B, int N1, int N2, int C) {
     if (B <= 0 || N1 <= 0 || N2 <= 0 || C <= 0) return 0;
-    return carve(nullptr, B, N1, N2, C).bytes;
+    return carve(nullptr, B, N1, N2, C, 256).bytes;
 }
 
 // features already carry the background token in row 0: f1 (B,N1+1,C), f2 (B,N2+1,C)
@@ -1090,25 +1150,31 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
     PEM_REQUIRE_PTR(atten);
     PEM_REQUIRE(B > 0 && N1p > 0 && N2p > 0 && C > 0, PEM_E_SHAPE);
     Params p{};
-    if (int rc = fill_common(p, B, N1p - 1, N2p - 1, C, temp)) return rc;
+    const int g = g_fine_variant == 2 ? 256 : 128;
+    if (int rc = fill_common(p, B, N1p - 1, N2p - 1, C, temp, g)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1p - 1, N2p - 1, C),
                 PEM_E_WORKSPACE);
     cudaStream_t st = pem_cu_stream(stream);
-    Ws w = carve(workspace, B, N1p - 1, N2p - 1, C);
+    Ws w = carve(workspace, B, N1p - 1, N2p - 1, C, g);
     tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
                                                                  C, normalize);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
-    if (g_fine_variant == 1) {
+    if (g_fine_variant >= 1) {
         TsParams q{};
         q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
         q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
-        q.n_res_strips = p.Mp / BM; q.n_str_tiles = p.Np / BN;
+        q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
         q.res_op = w.A;
         q.atten = atten;
-        return launch_ts_pass<kStore>(tmB, q, st);
+        if (g_fine_variant == 2) {
+            CUtensorMap tmBh;
+            if (int rc = make_operand_map(&tmBh, w.Bm, (size_t)2 * B * p.Np, C, BN / 2)) return rc;
+            return launch_ts_pass<kStore, true>(tmBh, q, st);
+        }
+        return launch_ts_pass<kStore, false>(tmB, q, st);
     }
     p.atten = atten;
     return launch_pass<kStore>(tmA, tmB, p, st);
@@ -1129,12 +1195,13 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     PEM_REQUIRE_PTR(score);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     Params p{};
-    if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;
+    const int g = g_fine_variant == 2 ? 256 : 128;
+    if (int rc = fill_common(p, B, N1, N2, C, temp, g)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
     cudaStream_t st = pem_cu_stream(stream);
-    Ws w = carve(workspace, B, N1, N2, C);
+    Ws w = carve(workspace, B, N1, N2, C, g);
     float *w1 = w1_out ? w1_out : w.w1;
     float *rsA = rowsum_out ? rowsum_out : w.rowsumA;
     float *pred = pred_out ? pred_out : w.pred;
@@ -1146,34 +1213,43 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
 
     const int mx = max(p.Mp, p.Np);
-    if (g_fine_variant == 1) {
+    if (g_fine_variant >= 1) {
+        const bool mc = g_fine_variant == 2;
+        CUtensorMap tmAs = tmA, tmBs = tmB;  // streamed-operand maps (64-row boxes when multicasting)
+        if (mc) {
+            if (int rc = make_operand_map(&tmAs, w.A, (size_t)2 * B * p.Mp, C, BN / 2)) return rc;
+            if (int rc = make_operand_map(&tmBs, w.Bm, (size_t)2 * B * p.Np, C, BN / 2)) return rc;
+        }
         TsParams q{};
         q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
-        const int n_part = p.n_strips;
         // passes 1-2 on the transposed problem: resident = column strip of S (rows of B'),
         // streamed = rows of S (tiles of A')
         q.res_valid = p.Cn; q.str_valid = p.R; q.res_pad = p.Np; q.str_pad = p.Mp;
-        q.n_res_strips = p.Np / BM; q.n_str_tiles = p.Mp / BN;
+        q.n_res_strips = p.Np / BM; q.n_str_tiles = (p.R + BN - 1) / BN;
+        const int n_part = q.n_res_strips;
         q.res_op = w.Bm;
         q.res_acc = w.colA;       // colsum
         q.str_part = w.rowpart;   // (B, n_part, Mp)
-        if (int rc = launch_ts_pass<kStats>(tmA, q, st)) return rc;
+        if (int rc = mc ? launch_ts_pass<kStats, true>(tmAs, q, st) : launch_ts_pass<kStats, false>(tmAs, q, st))
+            return rc;
         tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
             w.rowpart, w.colA, p.R, p.Cn, p.Mp, p.Np, n_part, w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
         q.res_const = w.lcs; q.str_const = w.lrs;
         q.res_acc = w.colA;       // colmax
         q.res_bg = w.colB;        // bgrow
         q.str_bg = w.bgcol;
-        if (int rc = launch_ts_pass<kLabel>(tmA, q, st)) return rc;
+        if (int rc = mc ? launch_ts_pass<kLabel, true>(tmAs, q, st) : launch_ts_pass<kLabel, false>(tmAs, q, st))
+            return rc;
         tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
             w.rowpart, w.bgcol, w.colA, w.colB, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part, w1,
             w2_out, w.G);
         // pass 3 direct: resident = row strip of S (rows of A'), streamed = column tiles (B')
         q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
-        q.n_res_strips = p.Mp / BM; q.n_str_tiles = p.Np / BN;
+        q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
         q.res_op = w.A;
         q.G = w.G; q.w1 = w1; q.inv_rowsum = w.inv_rowsum; q.rowsumA = rsA; q.pred = pred;
-        if (int rc = launch_ts_pass<kWsum>(tmB, q, st)) return rc;
+        if (int rc = mc ? launch_ts_pass<kWsum, true>(tmBs, q, st) : launch_ts_pass<kWsum, false>(tmBs, q, st))
+            return rc;
         return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
                                 score, st);
     }

@@ -570,46 +570,98 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void ts_epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// MC: clusters of two CTAs work on two resident strips of the SAME instance in lockstep and share
-// every streamed chunk: each CTA fetches half of it (64 rows, 8 KB) and multicasts it into both
-// CTAs' rings, halving the L2 -> SM traffic that otherwise bounds the kernel (~5.6 TB/s).
-template <int MODE, bool MC>
+// CG selects how CTAs cooperate:
+//   0  independent CTAs (one 128-row resident strip each);
+//   1  clusters of two CTAs on two strips of the SAME instance, every streamed chunk fetched half by
+//      each CTA and TMA-multicast into both rings (measured: no gain -- at cluster size 2 the L2 ->
+//      SM fabric still delivers the same bytes into every SM);
+//   2  CTA PAIRS (tcgen05 cta_group::2): one M=256 x N=128 MMA per K step spans both SMs.  Each CTA
+//      keeps its own 128 resident rows in its TMEM and loads only ITS HALF (64 rows) of every
+//      streamed chunk, so the bytes each SM ingests per tile are halved -- the kernel is otherwise
+//      bound by L2 -> SM delivery (~5.9 TB/s chip-wide), not by the tensor pipe.  The leader CTA
+//      (cluster rank 0) issues all MMAs; TMA completions, strip-ready and accumulator-drained
+//      signals of both CTAs converge on the leader's mbarriers; tcgen05.commit multicasts the
+//      slot-free / accumulator-ready / strip-free signals back to both.
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t leader_bar, uint32_t dst,
+                                                 int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                    uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on BOTH CTAs' barrier at this offset
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in cluster rank `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared address (cute::Sm100MmaPeerBitMask)
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)(256 >> 4) << 24);  // M = 256 across the pair
+
+template <int MODE, int CG>
 __global__ void __launch_bounds__(kTsThreads, 1)
 fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
     extern __shared__ uint8_t smem_raw[];
     TsSmem &sm = *reinterpret_cast<TsSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id();
     const int n_tasks = p.B * p.n_res_strips;
-    // task walk: CTA-strided when alone; with MC the cluster walks pairs (2c, 2c+1) of strips
-    const int crank = MC ? (int)cluster_ctarank() : 0;
-    const int task0 = MC ? 2 * (int)(blockIdx.x >> 1) + crank : (int)blockIdx.x;
-    const int task_step = MC ? (int)gridDim.x : (int)gridDim.x;
-
+    constexpr bool MC = (CG == 1), PAIR = (CG == 2);
+    // task walk: CTA-strided when alone; clusters walk pairs (2c, 2c+1) of strips of one instance
+    const int crank = (CG != 0) ? (int)cluster_ctarank() : 0;
+    const int task0 = (CG != 0) ? 2 * (int)(blockIdx.x >> 1) + crank : (int)blockIdx.x;
+    const int task_step = (int)gridDim.x;
+    // ring stage = one 16 KB slot: a whole 128-row chunk (hi or lo) when alone / multicasting, or
+    // this CTA's 64-row halves of the hi AND lo chunk of one K-chunk in pair mode
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTsStages; ++s) {
             mbar_init(smem_u32(&sm.full[s]), 1);
             mbar_init(smem_u32(&sm.empty[s]), MC ? 2 : 1);  // MC: both CTAs' MMAs must release a slot
         }
-        mbar_init(smem_u32(&sm.a_full), 4);  // one arrival per loader warp
+        mbar_init(smem_u32(&sm.a_full), PAIR ? 8 : 4);      // one arrival per loader warp (of both CTAs)
         mbar_init(smem_u32(&sm.a_free), 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&sm.tmem_full[a]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[a]), kEpiWarps);
+            mbar_init(smem_u32(&sm.tmem_empty[a]), PAIR ? 2 * kEpiWarps : kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&sm.tmem_base)),
-                     "r"((uint32_t)kTsTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&sm.tmem_base)),
+                         "r"((uint32_t)kTsTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&sm.tmem_base)),
+                         "r"((uint32_t)kTsTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
-    if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
+    if (CG != 0) cluster_sync_all();  // the peer's barriers / TMEM exist before anything targets them
 
     if (warp == 0) {
         // ================================ TMA producer: streamed operand ================
@@ -620,75 +672,116 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
             for (int m = 0; m < p.n_str_tiles; ++m) {
                 const int row = b * p.str_pad + m * BN;
                 for (int kc = 0; kc < p.KC; ++kc) {
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {
+                    if (PAIR) {
                         mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
-                            if (MC)  // my half of the chunk (64 rows = 8 KB) into both CTAs
-                                tma_load_2d_mc(&tmStr, smem_u32(&sm.full[stage]),
-                                               smem_u32(sm.b[stage]) + crank * (kChunkBytes / 2), kc * BK,
-                                               hl * p.B * p.str_pad + row + crank * (BN / 2), (uint16_t)3);
-                            else
-                                tma_load_2d(&tmStr, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]), kc * BK,
-                                            hl * p.B * p.str_pad + row);
+                            const uint32_t lbar = smem_u32(&sm.full[stage]) & kPeerBitMask;  // leader's barrier
+                            if (crank == 0) mbar_expect_tx(smem_u32(&sm.full[stage]), 2u * kChunkBytes);
+#pragma unroll
+                            for (int hl = 0; hl < 2; ++hl)
+                                tma_load_2d_pair(&tmStr, lbar, smem_u32(sm.b[stage]) + hl * (kChunkBytes / 2),
+                                                 kc * BK, hl * p.B * p.str_pad + row + crank * (BN / 2));
                         }
                         __syncwarp();
                         if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                    } else {
+#pragma unroll
+                        for (int hl = 0; hl < 2; ++hl) {
+                            mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
+                                if (MC)  // my half of the chunk (64 rows = 8 KB) into both CTAs
+                                    tma_load_2d_mc(&tmStr, smem_u32(&sm.full[stage]),
+                                                   smem_u32(sm.b[stage]) + crank * (kChunkBytes / 2), kc * BK,
+                                                   hl * p.B * p.str_pad + row + crank * (BN / 2), (uint16_t)3);
+                                else
+                                    tma_load_2d(&tmStr, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]),
+                                                kc * BK, hl * p.B * p.str_pad + row);
+                            }
+                            __syncwarp();
+                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
+        // (pair mode: only the leader CTA issues; its MMAs drive both SMs' tensor cores)
         int stage = 0, acc = 0;
         uint32_t phase = 0, a_phase = 0, acc_phase = 0;
         const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
         auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
-        for (int task = task0; task < n_tasks; task += task_step) {
-            mbar_wait(smem_u32(&sm.a_full), a_phase);  // resident strip is in TMEM
-            a_phase ^= 1;
-            tc_fence_after();
-            for (int m = 0; m < p.n_str_tiles; ++m) {
-                mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
+        if (!PAIR || crank == 0) {
+            for (int task = task0; task < n_tasks; task += task_step) {
+                mbar_wait(smem_u32(&sm.a_full), a_phase);  // resident strip(s) are in TMEM
+                a_phase ^= 1;
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(kTsAccCols + acc * BN);
-                for (int kc = 0; kc < p.KC; ++kc) {
-                    const uint32_t ah = tmem_base + (uint32_t)(kTsAhiCols + kc * 32);
-                    const uint32_t al = tmem_base + (uint32_t)(kTsAloCols + kc * 32);
-                    // streamed hi chunk: A_hi*B_hi + A_lo*B_hi
-                    mbar_wait(smem_u32(&sm.full[stage]), phase);
+                for (int m = 0; m < p.n_str_tiles; ++m) {
+                    mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
                     tc_fence_after();
-                    uint64_t bd = desc(smem_u32(sm.b[stage]));
-                    if (elect_one()) {
+                    const uint32_t d = tmem_base + (uint32_t)(kTsAccCols + acc * BN);
+                    for (int kc = 0; kc < p.KC; ++kc) {
+                        const uint32_t ah = tmem_base + (uint32_t)(kTsAhiCols + kc * 32);
+                        const uint32_t al = tmem_base + (uint32_t)(kTsAloCols + kc * 32);
+                        const bool last = (kc == p.KC - 1);
+                        if (PAIR) {
+                            mbar_wait(smem_u32(&sm.full[stage]), phase);
+                            tc_fence_after();
+                            const uint64_t bh = desc(smem_u32(sm.b[stage]));
+                            const uint64_t bl = desc(smem_u32(sm.b[stage]) + kChunkBytes / 2);
+                            if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {  // K=16 bf16 = 8 TMEM columns / 32 smem bytes
-                            tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, (kc | k) != 0);
-                            tc_mma_bf16_ts(d, al + 8 * k, bd + 2 * k, kIdesc, 1);
-                        }
-                        if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
-                        else tc_commit(smem_u32(&sm.empty[stage]));
-                    }
-                    __syncwarp();
-                    if (++stage == kTsStages) { stage = 0; phase ^= 1; }
-                    // streamed lo chunk: A_hi*B_lo
-                    mbar_wait(smem_u32(&sm.full[stage]), phase);
-                    tc_fence_after();
-                    bd = desc(smem_u32(sm.b[stage]));
-                    if (elect_one()) {
+                                for (int k = 0; k < BK / 16; ++k) {  // K=16: 8 TMEM columns / 32 smem bytes
+                                    tc_mma_bf16_ts_pair(d, ah + 8 * k, bh + 2 * k, kIdescPair, (kc | k) != 0);
+                                    tc_mma_bf16_ts_pair(d, al + 8 * k, bh + 2 * k, kIdescPair, 1);
+                                    tc_mma_bf16_ts_pair(d, ah + 8 * k, bl + 2 * k, kIdescPair, 1);
+                                }
+                                tc_commit_pair(smem_u32(&sm.empty[stage]));
+                                if (last) {
+                                    tc_commit_pair(smem_u32(&sm.tmem_full[acc]));
+                                    if (m == p.n_str_tiles - 1) tc_commit_pair(smem_u32(&sm.a_free));
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                        } else {
+                            // streamed hi chunk: A_hi*B_hi + A_lo*B_hi
+                            mbar_wait(smem_u32(&sm.full[stage]), phase);
+                            tc_fence_after();
+                            uint64_t bd = desc(smem_u32(sm.b[stage]));
+                            if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, 1);
-                        if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
-                        else tc_commit(smem_u32(&sm.empty[stage]));
-                        if (kc == p.KC - 1) {
-                            tc_commit(smem_u32(&sm.tmem_full[acc]));
-                            if (m == p.n_str_tiles - 1) tc_commit(smem_u32(&sm.a_free));  // strip may be replaced
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, (kc | k) != 0);
+                                    tc_mma_bf16_ts(d, al + 8 * k, bd + 2 * k, kIdesc, 1);
+                                }
+                                if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
+                                else tc_commit(smem_u32(&sm.empty[stage]));
+                            }
+                            __syncwarp();
+                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                            // streamed lo chunk: A_hi*B_lo
+                            mbar_wait(smem_u32(&sm.full[stage]), phase);
+                            tc_fence_after();
+                            bd = desc(smem_u32(sm.b[stage]));
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, 1);
+                                if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
+                                else tc_commit(smem_u32(&sm.empty[stage]));
+                                if (last) {
+                                    tc_commit(smem_u32(&sm.tmem_full[acc]));
+                                    if (m == p.n_str_tiles - 1) tc_commit(smem_u32(&sm.a_free));
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
                         }
                     }
-                    __syncwarp();
-                    if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp < 6) {
@@ -719,7 +812,10 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.a_full));
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_remote(smem_u32(&sm.a_full), 0);  // the leader CTA issues the MMAs
+                else mbar_arrive(smem_u32(&sm.a_full));
+            }
         }
     } else {
         // ================================ epilogue ====================================
@@ -820,7 +916,10 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_remote(smem_u32(&sm.tmem_empty[acc]), 0);
+                    else mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 if (MODE != kStore) ts_epi_barrier();  // colred[buf] complete; tilec[buf^1] staged
                 if (MODE == kStats || MODE == kLabel) {
@@ -864,12 +963,17 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (MC) cluster_sync_all();  // the peer may still multicast into this CTA / arrive on its barriers
+    if (CG != 0) cluster_sync_all();  // the peer may still multicast into this CTA / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)kTsTmemCols)
-                     : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)kTsTmemCols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)kTsTmemCols)
+                         : "memory");
     }
 }
 
@@ -1076,14 +1180,14 @@ static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Par
     return pem_launch_status();
 }
 
-template <int MODE, bool MC>
+template <int MODE, int CG>
 static int launch_ts_pass(const CUtensorMap &tmStr, const TsParams &p, cudaStream_t st) {
     const size_t smem = sizeof(TsSmem) + 1024;
     static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(fine_ts_kernel<MODE, MC>, smem, &cached)) return rc;
-    if (!MC) {
+    if (int rc = pem_ensure_dyn_smem(fine_ts_kernel<MODE, CG>, smem, &cached)) return rc;
+    if (CG == 0) {
         const int grid = min(num_sms(), p.B * p.n_res_strips);
-        fine_ts_kernel<MODE, false><<<grid, kTsThreads, smem, st>>>(tmStr, p);
+        fine_ts_kernel<MODE, 0><<<grid, kTsThreads, smem, st>>>(tmStr, p);
         return pem_launch_status();
     }
     // clusters of 2: one cluster per SM pair, each walking pairs of strips
@@ -1101,7 +1205,7 @@ static int launch_ts_pass(const CUtensorMap &tmStr, const TsParams &p, cudaStrea
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fine_ts_kernel<MODE, true>, tmStr, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fine_ts_kernel<MODE, CG>, tmStr, p);
     if (e != cudaSuccess) return (int)e;
     return pem_launch_status();
 }
@@ -1150,7 +1254,7 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
     PEM_REQUIRE_PTR(atten);
     PEM_REQUIRE(B > 0 && N1p > 0 && N2p > 0 && C > 0, PEM_E_SHAPE);
     Params p{};
-    const int g = g_fine_variant == 2 ? 256 : 128;
+    const int g = g_fine_variant >= 2 ? 256 : 128;
     if (int rc = fill_common(p, B, N1p - 1, N2p - 1, C, temp, g)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1p - 1, N2p - 1, C),
@@ -1169,12 +1273,13 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
         q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
         q.res_op = w.A;
         q.atten = atten;
-        if (g_fine_variant == 2) {
+        if (g_fine_variant >= 2) {
             CUtensorMap tmBh;
             if (int rc = make_operand_map(&tmBh, w.Bm, (size_t)2 * B * p.Np, C, BN / 2)) return rc;
-            return launch_ts_pass<kStore, true>(tmBh, q, st);
+            return g_fine_variant == 2 ? launch_ts_pass<kStore, 1>(tmBh, q, st)
+                                       : launch_ts_pass<kStore, 2>(tmBh, q, st);
         }
-        return launch_ts_pass<kStore, false>(tmB, q, st);
+        return launch_ts_pass<kStore, 0>(tmB, q, st);
     }
     p.atten = atten;
     return launch_pass<kStore>(tmA, tmB, p, st);
@@ -1195,7 +1300,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     PEM_REQUIRE_PTR(score);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     Params p{};
-    const int g = g_fine_variant == 2 ? 256 : 128;
+    const int g = g_fine_variant >= 2 ? 256 : 128;
     if (int rc = fill_common(p, B, N1, N2, C, temp, g)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
@@ -1214,7 +1319,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
 
     const int mx = max(p.Mp, p.Np);
     if (g_fine_variant >= 1) {
-        const bool mc = g_fine_variant == 2;
+        const bool mc = g_fine_variant >= 2;
+        const int cgv = g_fine_variant - 1;  // 0 alone, 1 multicast, 2 CTA pairs
         CUtensorMap tmAs = tmA, tmBs = tmB;  // streamed-operand maps (64-row boxes when multicasting)
         if (mc) {
             if (int rc = make_operand_map(&tmAs, w.A, (size_t)2 * B * p.Mp, C, BN / 2)) return rc;
@@ -1230,7 +1336,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         q.res_op = w.Bm;
         q.res_acc = w.colA;       // colsum
         q.str_part = w.rowpart;   // (B, n_part, Mp)
-        if (int rc = mc ? launch_ts_pass<kStats, true>(tmAs, q, st) : launch_ts_pass<kStats, false>(tmAs, q, st))
+        if (int rc = cgv == 2 ? launch_ts_pass<kStats, 2>(tmAs, q, st)
+                     : cgv == 1 ? launch_ts_pass<kStats, 1>(tmAs, q, st) : launch_ts_pass<kStats, 0>(tmAs, q, st))
             return rc;
         tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
             w.rowpart, w.colA, p.R, p.Cn, p.Mp, p.Np, n_part, w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
@@ -1238,7 +1345,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         q.res_acc = w.colA;       // colmax
         q.res_bg = w.colB;        // bgrow
         q.str_bg = w.bgcol;
-        if (int rc = mc ? launch_ts_pass<kLabel, true>(tmAs, q, st) : launch_ts_pass<kLabel, false>(tmAs, q, st))
+        if (int rc = cgv == 2 ? launch_ts_pass<kLabel, 2>(tmAs, q, st)
+                     : cgv == 1 ? launch_ts_pass<kLabel, 1>(tmAs, q, st) : launch_ts_pass<kLabel, 0>(tmAs, q, st))
             return rc;
         tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
             w.rowpart, w.bgcol, w.colA, w.colB, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part, w1,
@@ -1248,7 +1356,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
         q.res_op = w.A;
         q.G = w.G; q.w1 = w1; q.inv_rowsum = w.inv_rowsum; q.rowsumA = rsA; q.pred = pred;
-        if (int rc = mc ? launch_ts_pass<kWsum, true>(tmBs, q, st) : launch_ts_pass<kWsum, false>(tmBs, q, st))
+        if (int rc = cgv == 2 ? launch_ts_pass<kWsum, 2>(tmBs, q, st)
+                     : cgv == 1 ? launch_ts_pass<kWsum, 1>(tmBs, q, st) : launch_ts_pass<kWsum, 0>(tmBs, q, st))
             return rc;
         return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
                                 score, st);

@@ -17,7 +17,7 @@ f1d, f2d = f1.to(dev), f2.to(dev)
 big = {k: v.to(dev) for k, v in pkg.synth.replicate_batch(pkg.synth.make_batch(list(range(4))), 4).items()}
 bgb = big["bg"][:, None, :]
 F1, F2 = torch.cat([bgb, big["dense_fm"]], 1).contiguous(), torch.cat([bgb, big["dense_fo"]], 1).contiguous()
-for variant in (0, 1, 2):
+for variant in (0, 1, 3):
     L.pem_dev_set_fine_variant(variant)
     got = mu.compute_feature_similarity(f1d, f2d, "cosine", 0.1, True, backend="tc").cpu()
     print("variant", variant, "similarity max err", (got - atten).abs().max().item())

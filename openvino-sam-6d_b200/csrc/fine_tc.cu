@@ -52,7 +52,7 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 256;              // 2 accumulators x 128 columns
 constexpr int kHalfCols = BN / 2;           // columns per epilogue warp
 
-enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3 };
+enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3, kNoop = 4, kLoadOnly = 5 };  // 4,5: timing experiments
 
 struct Params {
     int B, R, Cn;          // instances, valid rows (N1+1), valid columns (N2+1)
@@ -863,10 +863,16 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < kHalfCols / 32; ++c) {
+                    if (MODE == kNoop) break;
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
                                   (uint32_t)(kTsAccCols + acc * BN + half * kHalfCols + c * 32), v);
-                    if (MODE == kStore) {
+                    if (MODE == kLoadOnly) {
+                        float sacc = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) sacc += v[q];
+                        if (sacc == 123456.789f) p.atten[0] = sacc;  // keep the loads alive
+                    } else if (MODE == kStore) {
                         if (res_ok) {
                             float *dst = p.atten + ((size_t)b * p.res_valid + gr) * p.str_valid + s0 + c * 32;
 #pragma unroll
@@ -921,7 +927,7 @@ fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
                     else mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (MODE != kStore) ts_epi_barrier();  // colred[buf] complete; tilec[buf^1] staged
+                if (MODE != kStore && MODE != kNoop && MODE != kLoadOnly) ts_epi_barrier();  // colred[buf] complete; tilec[buf^1] staged
                 if (MODE == kStats || MODE == kLabel) {
                     if (ep_tid < BN) {
                         float x = sm.colred[buf][0][ep_tid];
@@ -1389,4 +1395,29 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     // weighted Procrustes + pose score (fine.cu)
     return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
                             score, st);
+}
+
+// Development: run one GEMM pass of the TS kernel with a stub epilogue (mode 4: none, 5: TMEM loads
+// only) on already prepared operands, to separate tensor-pipe time from epilogue interference.
+extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
+                                 int mode, int cg, float *scratch, void *workspace, size_t workspace_bytes,
+                                 pem_stream_t stream) {
+    Params p{};
+    const int g = cg >= 1 ? 256 : 128;
+    if (int rc = fill_common(p, B, N1, N2, C, temp, g)) return rc;
+    cudaStream_t st = pem_cu_stream(stream);
+    Ws w = carve(workspace, B, N1, N2, C, g);
+    if (workspace_bytes < w.bytes) return PEM_E_WORKSPACE;
+    tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B, C, 1);
+    CUtensorMap tm;
+    if (int rc = make_operand_map(&tm, w.Bm, (size_t)2 * B * p.Np, C, cg >= 1 ? BN / 2 : BN)) return rc;
+    TsParams q{};
+    q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
+    q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
+    q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
+    q.res_op = w.A;
+    q.atten = scratch;
+    if (mode == 4) return cg == 2 ? launch_ts_pass<kNoop, 2>(tm, q, st) : launch_ts_pass<kNoop, 0>(tm, q, st);
+    if (mode == 5) return cg == 2 ? launch_ts_pass<kLoadOnly, 2>(tm, q, st) : launch_ts_pass<kLoadOnly, 0>(tm, q, st);
+    return cg == 2 ? launch_ts_pass<kWsum, 2>(tm, q, st) : launch_ts_pass<kWsum, 0>(tm, q, st);
 }

@@ -25,6 +25,7 @@ __device__ __forceinline__ bool elect_one() {
 
 // mode: 0 SS same accumulator, 1 SS two alternating accumulators, 2 TS same accumulator,
 //       3 SS four alternating accumulators
+__device__ int g_random_fill = 0;
 template <int N, int MODE>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long *cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -32,7 +33,15 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long *cycl
     __shared__ uint32_t tmem_base_s;
     uint8_t *sm = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += 128) ((uint32_t *)sm)[i] = 0x3c003c00u;
+    for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += 128) {
+        uint32_t v = 0x3c003c00u;
+        if (g_random_fill) {  // pseudo-random bf16 pairs in (-1,1): realistic switching activity
+            uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            v = (h & 0x807f807fu) | 0x3c003c00u | ((h >> 3) & 0x03000300u);
+        }
+        ((uint32_t *)sm)[i] = v;
+    }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -76,9 +85,82 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long *cycl
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
 }
 
+// The issue pattern of a pipelined GEMM: BATCH MMAs, tcgen05.commit, then the bookkeeping that
+// precedes the next batch (mbarrier probe that succeeds at once, tcgen05 fence, elect).
+template <int BATCH>
+__global__ void __launch_bounds__(128, 1) batch_kernel(int iters, long long *cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, bar2, ready;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *sm = (uint8_t *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (16384 * 2) / 4; i += 128) ((uint32_t *)sm)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ready)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (8u << 24);
+    if (warp == 1) {
+        const uint64_t a = desc_sw128(smem_u32(sm)), b = desc_sw128(smem_u32(sm + 16384));
+        long long t0 = clock64();
+        for (int i = 0; i < iters; i += BATCH) {
+            // probe a barrier whose awaited phase is already complete (parity 1 on a fresh barrier)
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 1;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&ready)) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BATCH; ++k) mma_ss(tb, a + 2 * (k & 3), b + 2 * (k & 3), idesc, 1);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+            }
+            __syncwarp();
+        }
+        if (elect_one()) {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+            cycles[blockIdx.x] = clock64() - t0;
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
+template <int BATCH>
+void run_batch(int grid) {
+    const int iters = 24576;
+    long long *d;
+    cudaMalloc(&d, grid * sizeof(long long));
+    const size_t smem = 32768 + 2048;
+    cudaFuncSetAttribute(batch_kernel<BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    batch_kernel<BATCH><<<grid, 128, smem>>>(iters, d);
+    batch_kernel<BATCH><<<grid, 128, smem>>>(iters, d);
+    cudaError_t err = cudaDeviceSynchronize();
+    long long h = 0;
+    cudaMemcpy(&h, d, sizeof(long long), cudaMemcpyDeviceToHost);
+    printf("batches of %2d MMAs + commit/probe/fence/elect: %7.1f cycles/MMA  [%s]\n", BATCH, (double)h / iters,
+           cudaGetErrorString(err));
+    cudaFree(d);
+}
+
 template <int N, int MODE>
 void run(const char *name, int grid) {
-    const int iters = 4096;
+    const int iters = 65536;
     long long *d;
     cudaMalloc(&d, grid * sizeof(long long));
     const size_t smem = 16384 + N * 128 + 2048;
@@ -100,7 +182,11 @@ void run(const char *name, int grid) {
 }
 
 int main() {
-    for (int grid : {1, 148}) {
+    run_batch<4>(148); run_batch<8>(148); run_batch<12>(148); run_batch<24>(148);
+    for (int rnd : {0, 1}) {
+    cudaMemcpyToSymbol(g_random_fill, &rnd, sizeof(int));
+    printf("---- operands: %s\n", rnd ? "pseudo-random bf16" : "constant");
+    for (int grid : {148}) {
         run<128, 0>("SS N=128 same accumulator", grid);
         run<128, 1>("SS N=128 two alternating accumulators", grid);
         run<128, 3>("SS N=128 four alternating accumulators", grid);
@@ -109,6 +195,7 @@ int main() {
         run<256, 1>("SS N=256 two alternating accumulators", grid);
         run<64, 0>("SS N=64 same accumulator", grid);
         run<64, 1>("SS N=64 two alternating accumulators", grid);
+    }
     }
     return 0;
 }

@@ -4,7 +4,10 @@
 // utils/model_utils.py.)
 //
 //   prep      normalise rows (F.normalize, eps 1e-12) and split every fp32 value into
-//             bf16 hi + bf16 lo; operands are stored row-padded to a multiple of 128.
+//             bf16 hi + bf16 lo; operands are stored row-padded to a multiple of 256.  The
+//             background token (row 0 of both feature sets) stays OUT of the GEMM: its row and
+//             column of the similarity matrix are 2 x 2049 exact fp32 dot products computed
+//             here, so the GEMM is exactly 2048 x 2048 per instance (no 2049 -> 2304 padding).
 //   GEMM x3   S = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (split-bf16: ~2^-17 relative, i.e.
 //             fp32-class logits; plain bf16 would move the pose by up to 0.05 deg) with the
 //             accumulator in TMEM, recomputed in three passes whose epilogues reduce
@@ -18,23 +21,32 @@
 //             replaces the running max of a streaming softmax.
 //   then the weighted Procrustes + pose score kernels of fine.cu.
 //
-// Kernel anatomy (one persistent CTA per SM, 320 threads).  A task = (instance, 128-COLUMN
-// strip); the CTA walks all 128-row tiles of that strip:
-//   warp 0      TMA producer: the column strip of B' (hi+lo, 128 KB) is loaded once per task
-//               and stays resident in shared memory; row tiles of A' stream through a 5-stage
-//               ring of 16 KB SWIZZLE_128B chunks (mbarrier full/empty pairs).
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=128, K=16,
-//               kind::f16, bf16 in / fp32 accumulate), tcgen05.commit to free ring slots and
-//               to hand the accumulator to the epilogue; two 128-column TMEM accumulators
-//               are double-buffered so MMAs of tile m+1 overlap the epilogue of tile m.
+// Kernel anatomy (persistent, one CTA per SM, 320 threads, CTAs grouped in PAIRS = clusters of 2
+// driving tcgen05 cta_group::2).  A task = (instance, 256-COLUMN strip, a few 256-row steps) and
+// belongs to a pair, which issues one M=256 x N=256 x K=16 MMA per K step:
+//   - each CTA keeps ITS 128 columns of the strip of B' (hi+lo, 128 KB) resident in shared memory
+//     (the MMA reads the peer's half over DSMEM) and streams ITS 128 rows of every step of A'
+//     through a 5-stage ring of 16 KB SWIZZLE_128B chunks; its TMEM holds the 128 x 256
+//     accumulator of its rows, double buffered (all 512 columns).
+//   - why pairs: with independent CTAs (N = 128 resident columns) every 16 KB streamed chunk
+//     feeds only 256..512 tensor cycles, i.e. 43 B/clk per SM or ~6300 B/clk chip-wide -- exactly
+//     the L2 -> SM delivery cap.  A pair does twice the MMA work per streamed byte.
+//   - the resident strip is replaced chunk by chunk (one full/empty barrier pair per 64-wide K
+//     chunk): the next task's chunk kc is requested as soon as the last step of the current
+//     task is done with chunk kc, so strip loads hide behind the remaining MMAs and tasks can
+//     be short (steps per task is chosen on the host to balance the pairs).
+//   warp 0      TMA producer (both CTAs; completions are signalled on the LEADER's mbarriers).
+//   warp 1      TMEM allocator; in the leader CTA (cluster rank 0) the single-thread tcgen05.mma
+//               issuer.  tcgen05.commit multicasts slot-free / accumulator-ready / chunk-free
+//               to both CTAs.
 //   warps 2-9   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread, two
-//               warps per lane quadrant, 64 columns each).  Reductions along the columns of
+//               warps per lane quadrant, 128 columns each).  Reductions along the columns of
 //               a tile are thread-local and leave as per-(row, strip-half) partials; reductions
-//               along the rows accumulate in 64 registers per thread ACROSS the row tiles of
-//               the task and are folded across lanes only once per task (31-shuffle transpose
-//               reduce per 32 columns + a 4-quadrant combine in shared memory).  Validity
-//               masks are folded into the per-row / per-column constants (+inf offsets).
-// Tasks are dealt round-robin to the CTAs (B*17 tasks at the default shapes).
+//               along the rows accumulate in 128 registers per thread ACROSS the steps of the
+//               task and are folded across lanes once per task (31-shuffle transpose reduce per
+//               32 columns + a 4-quadrant combine in shared memory) into one partial plane per
+//               (row split, CTA).  Validity masks are folded into the per-row / per-column
+//               constants (+inf offsets).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -43,39 +55,41 @@
 namespace pem {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64;  // BK bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int BM = 128, BN = 128, BK = 64;  // per-CTA operand tile; BK bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int TM = 2 * BM, TN = 2 * BN;     // rows per step / columns per strip of a CTA pair
+constexpr int WC = TN / 2;                  // accumulator columns per epilogue warp
 constexpr int kChunkBytes = BM * BK * 2;    // 16 KB
 constexpr int kStages = 5;
 constexpr int kMaxKC = 4;                   // C <= 256
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kTmemCols = 256;              // 2 accumulators x 128 columns
-constexpr int kHalfCols = BN / 2;           // columns per epilogue warp
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr uint32_t kTmemCols = 2 * TN;      // double-buffered 128 x 256 accumulator: all of TMEM
 
-enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3, kNoop = 4, kLoadOnly = 5 };  // 4,5: timing experiments
+enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3 };
 
 struct Params {
-    int B, R, Cn;          // instances, valid rows (N1+1), valid columns (N2+1)
-    int Mp, Np;            // padded rows of A' / B' per instance
-    int n_mtiles, n_strips; // Mp/128 row tiles, Np/128 column strips
+    int B, R, Cn;          // instances, valid rows and columns of the GEMM
+    int Mp, Np;            // padded rows of A' / B' per instance (multiples of 256)
+    int n_msteps, n_strips; // Mp / 256 row steps, Np / 256 column strips
+    int spt, n_splits;     // row steps per task, tasks per (instance, strip)
     int KC;                // C / 64
     float temp;            // logits = cos / temp
     float c1, c2;          // e = exp2(cos * c1 - c2)
-    // kStore
-    float *atten;          // (B,R,Cn)
+    // kStore: element (i,j) of the GEMM goes to atten[b][i + off][j + off], row length Cn + off
+    float *atten;
+    int off;
     // kStats
     float *rowpart;        // (B, 2*n_strips, Mp): row sums per column half-strip
-    float *colsum;         // (B,Np), complete
+    float *colpart;        // (2*n_splits, B, Np): column sums (kStats) / maxima (kLabel) per plane
     // kLabel (log2 domain)
     const float *lrs;      // (B,Mp)  log2(rowsum_i); +inf for padded rows
     const float *lcs;      // (B,Np)  log2(colsum_j); +inf for padded columns
-    float *rowmaxpart;     // (B, 2*n_strips, Mp): max over columns j>=1 of the half-strip
-    float *bgcol;          // (B,Mp): value of column 0
-    float *colmax;         // (B,Np): max over rows i>=1, complete
-    float *bgrow;          // (B,Np): value of row 0
+    float *rowmaxpart;     // (B, 2*n_strips, Mp): max over the columns of the half-strip
     // kWsum
-    const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for j = 0 / padding
+    const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for padding
     float *rowpart4;       // (B, 2*n_strips, 4, Mp)
+    int dev;               // timing experiments: 1 no MMAs, 2 no streamed loads, 4 no epilogue math
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -124,21 +138,6 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-// TMA load multicast to every CTA in `mask` (same shared-memory offset and mbarrier offset in each)
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0,
-                                               int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-        "h"(mask)
-        : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -184,6 +183,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16-column variant (lower register pressure for the epilogues that keep column accumulators)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+// explicit shared-window loads (the aligned Smem reference is a generic pointer to the compiler)
+__device__ __forceinline__ float4 lds_f4(const void *p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(smem_u32(p)));
+    return v;
+}
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -199,8 +223,44 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- CTA pairs (tcgen05 cta_group::2): one MMA spans two SMs of a cluster
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (`leader_bar` = own barrier
+// address with the CTA-parity bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t leader_bar, uint32_t dst,
+                                                 int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on BOTH CTAs' barrier at this shared-memory offset once the MMAs issued so far retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in cluster rank `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared address (cute::Sm100MmaPeerBitMask)
 
 // Sum (or max) over the 32 lanes of v[c], c = 0..31; lane L ends up holding column L.
 template <bool IS_MAX>
@@ -222,227 +282,255 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
 
 struct Smem {
     // operand buffers first: SWIZZLE_128B needs 1024-byte alignment
-    uint8_t b_hi[kMaxKC][kChunkBytes];   // resident column strip of B'
+    uint8_t b_hi[kMaxKC][kChunkBytes];   // resident: this CTA's 128 columns of the strip of B'
     uint8_t b_lo[kMaxKC][kChunkBytes];
-    uint8_t a[kStages][kChunkBytes];     // streamed row-tile chunks of A' (hi or lo)
-    float4 G[BN];                        // per-column constants of the task (kWsum)
-    float colc[BN];                      // per-column constants of the task (kLabel: log2 colsum)
-    float colred[4][BN];                 // per-quadrant column results
-    uint64_t full[kStages], empty[kStages], b_full, b_empty, tmem_full[2], tmem_empty[2];
+    uint8_t a[kStages][kChunkBytes];     // streamed: this CTA's 128 rows of a step of A' (hi or lo)
+    float4 G[TN];                        // per-column constants of the task (kWsum)
+    alignas(16) float colc[TN];          // per-column constants of the task (kLabel: log2 colsum)
+    float colred[4][TN];                 // per-quadrant column results
+    uint64_t full[kStages], empty[kStages], b_full[kMaxKC], b_empty[kMaxKC], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void epi_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+}
+
+struct Task {
+    int b, n, m0, m1;  // instance, column strip, row steps [m0, m1)
+};
+__device__ __forceinline__ Task decode_task(const Params &p, int task) {
+    Task t;
+    const int split = task % p.n_splits, bn = task / p.n_splits;
+    t.b = bn / p.n_strips;
+    t.n = bn - t.b * p.n_strips;
+    t.m0 = split * p.spt;
+    t.m1 = min(p.n_msteps, t.m0 + p.spt);
+    return t;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const Params p) {
+    constexpr uint32_t kIdesc = make_idesc(TM, TN);
+
     extern __shared__ uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id();
-    const int n_tasks = p.B * p.n_strips;
+    const int crank = (int)cluster_ctarank();  // 0 = leader CTA of the pair
+    const int n_tasks = p.B * p.n_strips * p.n_splits;
+    const int task0 = (int)blockIdx.x >> 1, task_step = (int)gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(smem_u32(&sm.full[s]), 1);
             mbar_init(smem_u32(&sm.empty[s]), 1);
         }
-        mbar_init(smem_u32(&sm.b_full), 1);
-        mbar_init(smem_u32(&sm.b_empty), 1);
+        for (int kc = 0; kc < kMaxKC; ++kc) {
+            mbar_init(smem_u32(&sm.b_full[kc]), 1);
+            mbar_init(smem_u32(&sm.b_empty[kc]), 1);
+        }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&sm.tmem_full[a]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[a]), kEpiWarps);  // one arrival per epilogue warp
+            mbar_init(smem_u32(&sm.tmem_empty[a]), 2 * kEpiWarps);  // one arrival per epilogue warp of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM allocation is warp-collective
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+    if (warp == 1) {  // TMEM allocation is warp-collective (the same warp of both CTAs)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&sm.tmem_base)),
-                     "r"((uint32_t)kTmemCols)
+                     "r"(kTmemCols)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+    cluster_sync_all();  // the peer's barriers and TMEM exist before anything targets them
 
     // Both single-issuer roles run with warp-uniform control flow (all 32 lanes loop and wait);
     // only the instruction issue is predicated on an elected lane, so addresses and
     // descriptors stay in uniform registers (no per-instruction uniformisation loops).
     if (warp == 0) {
         // ================================ TMA producer ================================
+        // Every completion is counted on the LEADER's full barriers (it alone arms them, for
+        // both CTAs' bytes); a peer completion that lands before the leader's expect_tx only
+        // drives the transaction count negative for a moment.
         int stage = 0;
         uint32_t phase = 0, b_phase = 0;
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-            const int b = task / p.n_strips, n = task - b * p.n_strips;
-            mbar_wait(smem_u32(&sm.b_empty), b_phase ^ 1);
-            b_phase ^= 1;
-            const int rowB = b * p.Np + n * BN;
-            if (elect_one()) {
-                mbar_expect_tx(smem_u32(&sm.b_full), 2u * p.KC * kChunkBytes);
+        for (int task = task0; task < n_tasks; task += task_step) {
+            const Task t = decode_task(p, task);
+            const int rowB = t.b * p.Np + t.n * TN + crank * BN;
+            for (int m = t.m0; m < t.m1; ++m) {
+                const int rowA = t.b * p.Mp + m * TM + crank * BM;
                 for (int kc = 0; kc < p.KC; ++kc) {
-                    tma_load_2d(&tmB, smem_u32(&sm.b_full), smem_u32(sm.b_hi[kc]), kc * BK, rowB);
-                    tma_load_2d(&tmB, smem_u32(&sm.b_full), smem_u32(sm.b_lo[kc]), kc * BK,
-                                p.B * p.Np + rowB);
-                }
-            }
-            __syncwarp();
-            for (int m = 0; m < p.n_mtiles; ++m) {
-                const int rowA = b * p.Mp + m * BM;
-                for (int kc = 0; kc < p.KC; ++kc) {
+                    if (m == t.m0) {  // replace chunk kc of the resident strip
+                        mbar_wait(smem_u32(&sm.b_empty[kc]), b_phase ^ 1);
+                        if (elect_one()) {
+                            const uint32_t bar = smem_u32(&sm.b_full[kc]);
+                            if (crank == 0) mbar_expect_tx(bar, 4u * kChunkBytes);
+                            tma_load_2d_pair(&tmB, bar & kPeerBitMask, smem_u32(sm.b_hi[kc]), kc * BK, rowB);
+                            tma_load_2d_pair(&tmB, bar & kPeerBitMask, smem_u32(sm.b_lo[kc]), kc * BK,
+                                             p.B * p.Np + rowB);
+                        }
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int hl = 0; hl < 2; ++hl) {
                         mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
-                            tma_load_2d(&tmA, smem_u32(&sm.full[stage]), smem_u32(sm.a[stage]), kc * BK,
-                                        hl * p.B * p.Mp + rowA);
+                            const uint32_t bar = smem_u32(&sm.full[stage]);
+                            if (p.dev & 2) {  // timing experiment: no streamed loads
+                                if (crank == 0) mbar_arrive(bar);
+                            } else {
+                                if (crank == 0) mbar_expect_tx(bar, 2u * kChunkBytes);
+                                tma_load_2d_pair(&tmA, bar & kPeerBitMask, smem_u32(sm.a[stage]), kc * BK,
+                                                 hl * p.B * p.Mp + rowA);
+                            }
                         }
                         __syncwarp();
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
+            b_phase ^= 1;
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, b_phase = 0, acc_phase = 0;
-        // descriptor high word is constant; the low word is (address >> 4) | LBO
-        const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
-        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-            mbar_wait(smem_u32(&sm.b_full), b_phase);
-            b_phase ^= 1;
-            tc_fence_after();
-            for (int m = 0; m < p.n_mtiles; ++m) {
-                mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-                for (int kc = 0; kc < p.KC; ++kc) {
-                    const uint64_t bh = desc(smem_u32(sm.b_hi[kc])), bl = desc(smem_u32(sm.b_lo[kc]));
-                    // A_hi chunk: A_hi*B_hi + A_hi*B_lo
-                    mbar_wait(smem_u32(&sm.full[stage]), phase);
+        // ================================ MMA issuer (leader CTA) =====================
+        if (crank == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, b_phase = 0, acc_phase = 0;
+            // descriptor high word is constant; the low word is (address >> 4) | LBO
+            const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
+            auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
+            for (int task = task0; task < n_tasks; task += task_step) {
+                const Task t = decode_task(p, task);
+                for (int m = t.m0; m < t.m1; ++m) {
+                    mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
                     tc_fence_after();
-                    uint64_t ad = desc(smem_u32(sm.a[stage]));
-                    if (elect_one()) {
+                    const uint32_t d = tmem_base + (uint32_t)(acc * TN);
+                    for (int kc = 0; kc < p.KC; ++kc) {
+                        if (m == t.m0) mbar_wait(smem_u32(&sm.b_full[kc]), b_phase);
+                        const uint64_t bh = desc(smem_u32(sm.b_hi[kc])), bl = desc(smem_u32(sm.b_lo[kc]));
+                        // A_hi chunk: A_hi*B_hi + A_hi*B_lo
+                        mbar_wait(smem_u32(&sm.full[stage]), phase);
+                        tc_fence_after();
+                        uint64_t ad = desc(smem_u32(sm.a[stage]));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {  // +32 bytes per K=16 step: +2 in the address field
-                            tc_mma_bf16(d, ad + 2 * k, bh + 2 * k, kIdesc, (kc | k) != 0);
-                            tc_mma_bf16(d, ad + 2 * k, bl + 2 * k, kIdesc, 1);
+                            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes per K=16 step: +2 in the address field
+                                if (p.dev & 1) break;
+                                tc_mma_bf16_pair(d, ad + 2 * k, bh + 2 * k, kIdesc, (kc | k) != 0);
+                                tc_mma_bf16_pair(d, ad + 2 * k, bl + 2 * k, kIdesc, 1);
+                            }
+                            tc_commit_pair(smem_u32(&sm.empty[stage]));  // frees the slot once these retire
                         }
-                        tc_commit(smem_u32(&sm.empty[stage]));
-                    }
-                    __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    // A_lo chunk: A_lo*B_hi
-                    mbar_wait(smem_u32(&sm.full[stage]), phase);
-                    tc_fence_after();
-                    ad = desc(smem_u32(sm.a[stage]));
-                    if (elect_one()) {
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        // A_lo chunk: A_lo*B_hi
+                        mbar_wait(smem_u32(&sm.full[stage]), phase);
+                        tc_fence_after();
+                        ad = desc(smem_u32(sm.a[stage]));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) tc_mma_bf16(d, ad + 2 * k, bh + 2 * k, kIdesc, 1);
-                        tc_commit(smem_u32(&sm.empty[stage]));
-                        if (kc == p.KC - 1) tc_commit(smem_u32(&sm.tmem_full[acc]));  // accumulator ready
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (p.dev & 1) break;
+                                tc_mma_bf16_pair(d, ad + 2 * k, bh + 2 * k, kIdesc, 1);
+                            }
+                            tc_commit_pair(smem_u32(&sm.empty[stage]));
+                            // last step of the task: chunk kc of the strip may be replaced
+                            if (m == t.m1 - 1) tc_commit_pair(smem_u32(&sm.b_empty[kc]));
+                            if (kc == p.KC - 1) tc_commit_pair(smem_u32(&sm.tmem_full[acc]));  // accumulator ready
+                        }
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                b_phase ^= 1;
             }
-            if (elect_one()) tc_commit(smem_u32(&sm.b_empty));  // all MMAs reading the B strip retired
-            __syncwarp();
         }
     } else {
         // ================================ epilogue ====================================
         const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
-        const int half = (warp - 2) >> 2;          // columns [64*half, 64*half+64) of the tile
-        const int et = quad * 32 + lane;           // row of the 128-row tile owned by this thread
+        const int half = (warp - 2) >> 2;          // columns [WC*half, WC*half+WC) of the tile
+        const int et = quad * 32 + lane;           // row of this CTA's 128 rows owned by this thread
         const int ep_tid = (warp - 2) * 32 + lane; // 0..255
         const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-            const int b = task / p.n_strips, n = task - b * p.n_strips;
-            const int j0 = n * BN + half * kHalfCols;     // first global column of this warp
-            const int ncols = min(kHalfCols, p.Cn - j0);  // valid columns (<= 0: none)
-            float colacc[kHalfCols];
+        for (int task = task0; task < n_tasks; task += task_step) {
+            const Task t = decode_task(p, task);
+            const int b = t.b, n = t.n;
+            const int j0 = n * TN + half * WC;     // first column of this warp
+            const int ncols = min(WC, p.Cn - j0);  // valid columns (<= 0: none)
+            float colacc[WC];
 #pragma unroll
-            for (int q = 0; q < kHalfCols; ++q) colacc[q] = (MODE == kLabel) ? -INFINITY : 0.f;
-            // per-column constants of the task
-            if (MODE == kLabel && ep_tid < BN) {
-                const int j = n * BN + ep_tid;
-                // excluded from the row max: padded columns and the background column 0
-                sm.colc[ep_tid] = (j >= 1 && j < p.Cn) ? p.lcs[(size_t)b * p.Np + j] : INFINITY;
-            }
-            if (MODE == kWsum && ep_tid < BN) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * BN + ep_tid];
+            for (int q = 0; q < WC; ++q) colacc[q] = (MODE == kLabel) ? -INFINITY : 0.f;
+            // per-column constants of the task (+inf keeps padded columns out of the row max)
+            if (MODE == kLabel) sm.colc[ep_tid] = p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
+            if (MODE == kWsum) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * TN + ep_tid];
             if (MODE == kLabel || MODE == kWsum) epi_barrier();
-            const float lcs0 = (MODE == kLabel && j0 == 0) ? p.lcs[(size_t)b * p.Np] : 0.f;
 
-            for (int m = 0; m < p.n_mtiles; ++m) {
-                const int gi = m * BM + et;
+            for (int m = t.m0; m < t.m1; ++m) {
+                const int gi = m * TM + crank * BM + et;
                 const bool row_ok = gi < p.R;
                 float rowc = 0.f;  // per-row constant of this tile
-                if (MODE == kStats) rowc = row_ok ? kc2 : INFINITY;             // e = 0 for padded rows
-                if (MODE == kLabel) rowc = (row_ok && gi >= 1) ? p.lrs[(size_t)b * p.Mp + gi] : INFINITY;
+                if (MODE == kStats) rowc = row_ok ? kc2 : INFINITY;  // e = 0 for padded rows
+                if (MODE == kLabel) rowc = p.lrs[(size_t)b * p.Mp + gi];  // +inf for padded rows
                 float r0 = (MODE == kLabel) ? -INFINITY : 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
                 mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
                 tc_fence_after();
+                // columns per TMEM load: 16 where 128 column accumulators already fill the registers
+                constexpr int CW = (MODE == kStats || MODE == kLabel) ? 16 : 32;
 #pragma unroll
-                for (int c = 0; c < kHalfCols / 32; ++c) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                  (uint32_t)(acc * BN + half * kHalfCols + c * 32), v);
+                for (int c = 0; c < WC / CW; ++c) {
+                    if (p.dev & 4) break;
+                    float v[CW];
+                    tmem_ld(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                (uint32_t)(acc * TN + half * WC + c * CW), v);
                     if (MODE == kStore) {
                         if (row_ok) {
-                            float *dst = p.atten + ((size_t)b * p.R + gi) * p.Cn + j0 + c * 32;
+                            float *dst = p.atten + ((size_t)b * (p.R + p.off) + gi + p.off) * (p.Cn + p.off) +
+                                         p.off + j0 + c * CW;
 #pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (c * 32 + q < ncols) dst[q] = __fdiv_rn(v[q], ktemp);
+                            for (int q = 0; q < CW; ++q)
+                                if (c * CW + q < ncols) dst[q] = __fdiv_rn(v[q], ktemp);
                         }
                     } else if (MODE == kStats) {
-                        if (ncols >= kHalfCols) {
+                        if (ncols >= WC) {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) {
+                            for (int q = 0; q < CW; ++q) {
                                 const float e = ex2(fmaf(v[q], kc1, -rowc));
                                 r0 += e;
-                                colacc[c * 32 + q] += e;
+                                colacc[c * CW + q] += e;
                             }
                         } else {  // last strip: mask padded columns
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) {
-                                const float e = (c * 32 + q < ncols) ? ex2(fmaf(v[q], kc1, -rowc)) : 0.f;
+                            for (int q = 0; q < CW; ++q) {
+                                const float e = (c * CW + q < ncols) ? ex2(fmaf(v[q], kc1, -rowc)) : 0.f;
                                 r0 += e;
-                                colacc[c * 32 + q] += e;
+                                colacc[c * CW + q] += e;
                             }
                         }
                     } else if (MODE == kLabel) {
-                        const float c2x = kc2x;
-                        if (gi == 0) {  // background row: record it, keep it out of the column max
 #pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (c * 32 + q < ncols)
-                                    p.bgrow[(size_t)b * p.Np + j0 + c * 32 + q] =
-                                        fmaf(v[q], c2x, -p.lrs[(size_t)b * p.Mp]);
-                        }
-                        if (c == 0 && j0 == 0 && row_ok)  // background column of this row
-                            p.bgcol[(size_t)b * p.Mp + gi] = fmaf(v[0], c2x, -lcs0);
+                        for (int q = 0; q < CW; q += 4) {
+                            const float4 cc = lds_f4(&sm.colc[half * WC + c * CW + q]);
+                            // 2 s/temp - log colsum_j (row side), 2 s/temp - log rowsum_i (column side)
+                            r0 = fmaxf(fmaxf(r0, fmaf(v[q], kc2x, -cc.x)), fmaf(v[q + 1], kc2x, -cc.y));
+                            r0 = fmaxf(fmaxf(r0, fmaf(v[q + 2], kc2x, -cc.z)), fmaf(v[q + 3], kc2x, -cc.w));
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const float x = v[q] * c2x;
-                            r0 = fmaxf(r0, x - sm.colc[half * kHalfCols + c * 32 + q]);
-                            colacc[c * 32 + q] = fmaxf(colacc[c * 32 + q], x - rowc);
+                            for (int u = 0; u < 4; ++u)
+                                colacc[c * CW + q + u] = fmaxf(colacc[c * CW + q + u], fmaf(v[q + u], kc2x, -rowc));
                         }
                     } else {  // kWsum
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const float e = ex2(fmaf(v[q], kc1, -kc2));
-                            const float u = e * e;
-                            const float4 g = sm.G[half * kHalfCols + c * 32 + q];
+                        for (int q = 0; q < CW; ++q) {
+                            const float u = ex2(fmaf(v[q], kc2x, -2.0f * kc2));  // e^2
+                            const float4 g = lds_f4(&sm.G[half * WC + c * CW + q]);
                             r0 = fmaf(u, g.w, r0);
                             r1 = fmaf(u, g.x, r1);
                             r2 = fmaf(u, g.y, r2);
@@ -450,10 +538,10 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                // accumulator fully read: hand the TMEM buffer back to the MMA warp of the leader
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
+                if (lane == 0) mbar_arrive_remote(smem_u32(&sm.tmem_empty[acc]), 0);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // per-(row, half-strip) partials: consecutive lanes = consecutive rows
                 const size_t pr = ((size_t)b * 2 * p.n_strips + 2 * n + half);
@@ -464,24 +552,23 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     dst[0] = r0; dst[p.Mp] = r1; dst[2 * p.Mp] = r2; dst[3 * p.Mp] = r3;
                 }
             }
-            // fold the column accumulators across the 32 lanes, then across the 4 quadrants
+            // fold the column accumulators across the 32 lanes, then across the 4 quadrants;
+            // every (row split, CTA of the pair) leaves its own plane
             if (MODE == kStats || MODE == kLabel) {
 #pragma unroll
-                for (int c = 0; c < kHalfCols / 32; ++c) {
+                for (int c = 0; c < WC / 32; ++c) {
                     float v[32];
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = colacc[c * 32 + q];
-                    sm.colred[quad][half * kHalfCols + c * 32 + lane] =
-                        warp_transpose_reduce<MODE == kLabel>(v);
+                    sm.colred[quad][half * WC + c * 32 + lane] = warp_transpose_reduce<MODE == kLabel>(v);
                 }
                 epi_barrier();
-                if (ep_tid < BN && n * BN + ep_tid < p.Cn) {
-                    float x = sm.colred[0][ep_tid];
+                float s = sm.colred[0][ep_tid];
 #pragma unroll
-                    for (int w = 1; w < 4; ++w)
-                        x = (MODE == kLabel) ? fmaxf(x, sm.colred[w][ep_tid]) : x + sm.colred[w][ep_tid];
-                    ((MODE == kLabel) ? p.colmax : p.colsum)[(size_t)b * p.Np + n * BN + ep_tid] = x;
-                }
+                for (int w = 1; w < 4; ++w)
+                    s = (MODE == kLabel) ? fmaxf(s, sm.colred[w][ep_tid]) : s + sm.colred[w][ep_tid];
+                const int plane = 2 * (t.m0 / p.spt) + crank;
+                p.colpart[((size_t)plane * p.B + b) * p.Np + n * TN + ep_tid] = s;
             }
             epi_barrier();  // shared per-task constants / colred are reused by the next task
         }
@@ -489,580 +576,166 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)kTmemCols)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
                      : "memory");
     }
 }
 
-// =========================================================================================
-// TS-mode variant: the RESIDENT operand lives in tensor memory and is the MMA's A operand
-// (tcgen05.mma ... [d_tmem], [a_tmem], b_desc), so each MMA fetches only the streamed operand
-// from shared memory (4 KB per 64 cycles instead of 8 KB).  In SS mode operand fetch alone asks
-// for the SM's full 128 B/clk shared-memory bandwidth, and TMA writes (42 B/clk) push it over.
-//
-// TMEM budget (512 columns): accumulators 2 x 128, resident strip hi 128 + lo 128 (two bf16 per
-// 32-bit column, lane = row).  The freed shared memory becomes a 12-stage ring.
-// Orientation: lanes (threads) index the resident strip.  Passes 1-2 run on the TRANSPOSED
-// problem (resident = 128 columns of S, i.e. rows of B'; streamed = rows of S) so that the column
-// statistics are thread-local across the task and the row statistics are per-tile cross-lane
-// folds written as per-strip partials -- the same outputs as the SS kernel, so the finish kernels
-// are shared.  Pass 3 runs direct (resident = rows of S): its four per-row sums are thread-local.
-// Warps: 0 TMA, 1 MMA + TMEM alloc, 2-5 strip loaders (global -> registers -> tcgen05.st), 6-13
-// epilogue (two per lane quadrant, 64 tile columns each).
-constexpr int kTsStages = 12;
-constexpr int kTsThreads = 32 * 14;
-constexpr int kTsTmemCols = 512;
-constexpr int kTsAccCols = 0, kTsAhiCols = 256, kTsAloCols = 384;
-
-struct TsParams {
-    int B, KC, C;
-    int res_valid, str_valid;   // valid rows of the resident / streamed operand per instance
-    int res_pad, str_pad;       // padded rows per instance
-    int n_res_strips, n_str_tiles;
-    float c1, c2, temp;
-    const __nv_bfloat16 *res_op;  // prepped (2, B*res_pad, C): hi rows then lo rows
-    // kStats / kLabel (transposed: resident index = column j of S, streamed index = row i of S)
-    float *res_acc;         // (B,res_pad): colsum (kStats) or colmax over i>=1 (kLabel)
-    float *str_part;        // (B,n_res_strips,str_pad): rowpart / rowmaxpart
-    const float *res_const; // kLabel: lcs (B,res_pad)
-    const float *str_const; // kLabel: lrs (B,str_pad)
-    float *res_bg;          // kLabel: bgrow (B,res_pad): value at streamed index 0
-    float *str_bg;          // kLabel: bgcol (B,str_pad): value at resident index 0
-    // kWsum / kStore (direct: resident index = row i of S, streamed index = column j)
-    const float4 *G;        // (B,str_pad)
-    const float *w1;        // (B,res_valid-1)
-    const float *inv_rowsum;  // (B,res_pad)
-    float *rowsumA, *pred;  // (B,res_valid-1), (B,res_valid-1,3)
-    float *atten;           // kStore: (B,res_valid,str_valid)
-};
-
-struct TsSmem {
-    uint8_t b[kTsStages][kChunkBytes];
-    float4 tilec[2][BN];      // per-tile constants of the streamed index (kLabel: .x = lrs; kWsum: G)
-    float colred[2][4][BN];   // per-quadrant folds of the streamed index, double buffered
-    float red[2][BM];         // combine the two column halves of thread-local accumulators
-    uint64_t full[kTsStages], empty[kTsStages], a_full, a_free, tmem_full[2], tmem_empty[2];
-    uint32_t tmem_base;
-};
-
-__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                               uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void ts_epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// CG selects how CTAs cooperate:
-//   0  independent CTAs (one 128-row resident strip each);
-//   1  clusters of two CTAs on two strips of the SAME instance, every streamed chunk fetched half by
-//      each CTA and TMA-multicast into both rings (measured: no gain -- at cluster size 2 the L2 ->
-//      SM fabric still delivers the same bytes into every SM);
-//   2  CTA PAIRS (tcgen05 cta_group::2): one M=256 x N=128 MMA per K step spans both SMs.  Each CTA
-//      keeps its own 128 resident rows in its TMEM and loads only ITS HALF (64 rows) of every
-//      streamed chunk, so the bytes each SM ingests per tile are halved -- the kernel is otherwise
-//      bound by L2 -> SM delivery (~5.9 TB/s chip-wide), not by the tensor pipe.  The leader CTA
-//      (cluster rank 0) issues all MMAs; TMA completions, strip-ready and accumulator-drained
-//      signals of both CTAs converge on the leader's mbarriers; tcgen05.commit multicasts the
-//      slot-free / accumulator-ready / strip-free signals back to both.
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t leader_bar, uint32_t dst,
-                                                 int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                                    uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on BOTH CTAs' barrier at this offset
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-        "h"((uint16_t)3)
-        : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in cluster rank `rank`
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared address (cute::Sm100MmaPeerBitMask)
-constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                ((uint32_t)(256 >> 4) << 24);  // M = 256 across the pair
-
-template <int MODE, int CG>
-__global__ void __launch_bounds__(kTsThreads, 1)
-fine_ts_kernel(const __grid_constant__ CUtensorMap tmStr, const TsParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    TsSmem &sm = *reinterpret_cast<TsSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int warp = warp_id(), lane = lane_id();
-    const int n_tasks = p.B * p.n_res_strips;
-    constexpr bool MC = (CG == 1), PAIR = (CG == 2);
-    // task walk: CTA-strided when alone; clusters walk pairs (2c, 2c+1) of strips of one instance
-    const int crank = (CG != 0) ? (int)cluster_ctarank() : 0;
-    const int task0 = (CG != 0) ? 2 * (int)(blockIdx.x >> 1) + crank : (int)blockIdx.x;
-    const int task_step = (int)gridDim.x;
-    // ring stage = one 16 KB slot: a whole 128-row chunk (hi or lo) when alone / multicasting, or
-    // this CTA's 64-row halves of the hi AND lo chunk of one K-chunk in pair mode
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kTsStages; ++s) {
-            mbar_init(smem_u32(&sm.full[s]), 1);
-            mbar_init(smem_u32(&sm.empty[s]), MC ? 2 : 1);  // MC: both CTAs' MMAs must release a slot
-        }
-        mbar_init(smem_u32(&sm.a_full), PAIR ? 8 : 4);      // one arrival per loader warp (of both CTAs)
-        mbar_init(smem_u32(&sm.a_free), 1);
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(smem_u32(&sm.tmem_full[a]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[a]), PAIR ? 2 * kEpiWarps : kEpiWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                             smem_u32(&sm.tmem_base)),
-                         "r"((uint32_t)kTsTmemCols)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                             smem_u32(&sm.tmem_base)),
-                         "r"((uint32_t)kTsTmemCols)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = sm.tmem_base;
-    if (CG != 0) cluster_sync_all();  // the peer's barriers / TMEM exist before anything targets them
-
-    if (warp == 0) {
-        // ================================ TMA producer: streamed operand ================
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int task = task0; task < n_tasks; task += task_step) {
-            const int b = task / p.n_res_strips;
-            for (int m = 0; m < p.n_str_tiles; ++m) {
-                const int row = b * p.str_pad + m * BN;
-                for (int kc = 0; kc < p.KC; ++kc) {
-                    if (PAIR) {
-                        mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
-                        if (elect_one()) {
-                            const uint32_t lbar = smem_u32(&sm.full[stage]) & kPeerBitMask;  // leader's barrier
-                            if (crank == 0) mbar_expect_tx(smem_u32(&sm.full[stage]), 2u * kChunkBytes);
-#pragma unroll
-                            for (int hl = 0; hl < 2; ++hl)
-                                tma_load_2d_pair(&tmStr, lbar, smem_u32(sm.b[stage]) + hl * (kChunkBytes / 2),
-                                                 kc * BK, hl * p.B * p.str_pad + row + crank * (BN / 2));
-                        }
-                        __syncwarp();
-                        if (++stage == kTsStages) { stage = 0; phase ^= 1; }
-                    } else {
-#pragma unroll
-                        for (int hl = 0; hl < 2; ++hl) {
-                            mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
-                            if (elect_one()) {
-                                mbar_expect_tx(smem_u32(&sm.full[stage]), kChunkBytes);
-                                if (MC)  // my half of the chunk (64 rows = 8 KB) into both CTAs
-                                    tma_load_2d_mc(&tmStr, smem_u32(&sm.full[stage]),
-                                                   smem_u32(sm.b[stage]) + crank * (kChunkBytes / 2), kc * BK,
-                                                   hl * p.B * p.str_pad + row + crank * (BN / 2), (uint16_t)3);
-                                else
-                                    tma_load_2d(&tmStr, smem_u32(&sm.full[stage]), smem_u32(sm.b[stage]),
-                                                kc * BK, hl * p.B * p.str_pad + row);
-                            }
-                            __syncwarp();
-                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
-        // (pair mode: only the leader CTA issues; its MMAs drive both SMs' tensor cores)
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, a_phase = 0, acc_phase = 0;
-        const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);
-        auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
-        if (!PAIR || crank == 0) {
-            for (int task = task0; task < n_tasks; task += task_step) {
-                mbar_wait(smem_u32(&sm.a_full), a_phase);  // resident strip(s) are in TMEM
-                a_phase ^= 1;
-                tc_fence_after();
-                for (int m = 0; m < p.n_str_tiles; ++m) {
-                    mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)(kTsAccCols + acc * BN);
-                    for (int kc = 0; kc < p.KC; ++kc) {
-                        const uint32_t ah = tmem_base + (uint32_t)(kTsAhiCols + kc * 32);
-                        const uint32_t al = tmem_base + (uint32_t)(kTsAloCols + kc * 32);
-                        const bool last = (kc == p.KC - 1);
-                        if (PAIR) {
-                            mbar_wait(smem_u32(&sm.full[stage]), phase);
-                            tc_fence_after();
-                            const uint64_t bh = desc(smem_u32(sm.b[stage]));
-                            const uint64_t bl = desc(smem_u32(sm.b[stage]) + kChunkBytes / 2);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < BK / 16; ++k) {  // K=16: 8 TMEM columns / 32 smem bytes
-                                    tc_mma_bf16_ts_pair(d, ah + 8 * k, bh + 2 * k, kIdescPair, (kc | k) != 0);
-                                    tc_mma_bf16_ts_pair(d, al + 8 * k, bh + 2 * k, kIdescPair, 1);
-                                    tc_mma_bf16_ts_pair(d, ah + 8 * k, bl + 2 * k, kIdescPair, 1);
-                                }
-                                tc_commit_pair(smem_u32(&sm.empty[stage]));
-                                if (last) {
-                                    tc_commit_pair(smem_u32(&sm.tmem_full[acc]));
-                                    if (m == p.n_str_tiles - 1) tc_commit_pair(smem_u32(&sm.a_free));
-                                }
-                            }
-                            __syncwarp();
-                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
-                        } else {
-                            // streamed hi chunk: A_hi*B_hi + A_lo*B_hi
-                            mbar_wait(smem_u32(&sm.full[stage]), phase);
-                            tc_fence_after();
-                            uint64_t bd = desc(smem_u32(sm.b[stage]));
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < BK / 16; ++k) {
-                                    tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, (kc | k) != 0);
-                                    tc_mma_bf16_ts(d, al + 8 * k, bd + 2 * k, kIdesc, 1);
-                                }
-                                if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
-                                else tc_commit(smem_u32(&sm.empty[stage]));
-                            }
-                            __syncwarp();
-                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
-                            // streamed lo chunk: A_hi*B_lo
-                            mbar_wait(smem_u32(&sm.full[stage]), phase);
-                            tc_fence_after();
-                            bd = desc(smem_u32(sm.b[stage]));
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < BK / 16; ++k)
-                                    tc_mma_bf16_ts(d, ah + 8 * k, bd + 2 * k, kIdesc, 1);
-                                if (MC) tc_commit_mc(smem_u32(&sm.empty[stage]), (uint16_t)3);
-                                else tc_commit(smem_u32(&sm.empty[stage]));
-                                if (last) {
-                                    tc_commit(smem_u32(&sm.tmem_full[acc]));
-                                    if (m == p.n_str_tiles - 1) tc_commit(smem_u32(&sm.a_free));
-                                }
-                            }
-                            __syncwarp();
-                            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
-                        }
-                    }
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp < 6) {
-        // ================================ resident-strip loaders =======================
-        const int quad = warp & 3, row = quad * 32 + lane;
-        uint32_t free_phase = 0;
-        for (int task = task0; task < n_tasks; task += task_step) {
-            const int b = task / p.n_res_strips, s = task - b * p.n_res_strips;
-            mbar_wait(smem_u32(&sm.a_free), free_phase ^ 1);  // previous task's MMAs have retired
-            free_phase ^= 1;
-            tc_fence_after();
-            const size_t grow = (size_t)b * p.res_pad + (size_t)s * BM + row;
-#pragma unroll 1
-            for (int part = 0; part < 2; ++part) {  // hi, lo
-                const uint4 *src = reinterpret_cast<const uint4 *>(
-                    p.res_op + ((size_t)part * p.B * p.res_pad + grow) * p.C);
-                for (int gq = 0; gq < p.KC; ++gq) {  // 64 bf16 = 32 packed columns per group
-                    uint32_t r[32];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint4 v = __ldg(src + gq * 8 + q);
-                        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-                    }
-                    tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                  (uint32_t)((part ? kTsAloCols : kTsAhiCols) + gq * 32), r);
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (PAIR) mbar_arrive_remote(smem_u32(&sm.a_full), 0);  // the leader CTA issues the MMAs
-                else mbar_arrive(smem_u32(&sm.a_full));
-            }
-        }
-    } else {
-        // ================================ epilogue ====================================
-        const int quad = warp & 3;
-        const int half = (warp - 6) >> 2;
-        const int et = quad * 32 + lane;            // resident row owned by this thread
-        const int ep_tid = (warp - 6) * 32 + lane;  // 0..255
-        const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int task = task0; task < n_tasks; task += task_step) {
-            const int b = task / p.n_res_strips, s = task - b * p.n_res_strips;
-            const int gr = s * BM + et;                 // resident index within the instance
-            const bool res_ok = gr < p.res_valid;
-            // thread constants / accumulators
-            float racc = (MODE == kLabel) ? -INFINITY : 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-            float rconst = 0.f, rconst_true = 0.f;
-            if (MODE == kStats) rconst = res_ok ? kc2 : INFINITY;
-            if (MODE == kLabel) {
-                rconst_true = res_ok ? p.res_const[(size_t)b * p.res_pad + gr] : INFINITY;
-                rconst = (res_ok && gr >= 1) ? rconst_true : INFINITY;  // index 0 (background) excluded
-            }
-            const float str0_true = (MODE == kLabel) ? p.str_const[(size_t)b * p.str_pad] : 0.f;
-            // per-tile constants of the streamed index for tile 0
-            auto stage_tilec = [&](int m, int buf) {
-                if (ep_tid < BN) {
-                    const int gs = m * BN + ep_tid;
-                    const size_t o = (size_t)b * p.str_pad + gs;
-                    if (MODE == kLabel)
-                        sm.tilec[buf][ep_tid] =
-                            make_float4((gs >= 1 && gs < p.str_valid) ? p.str_const[o] : INFINITY, 0.f, 0.f, 0.f);
-                    if (MODE == kWsum) sm.tilec[buf][ep_tid] = p.G[o];
-                }
-            };
-            if (MODE == kLabel || MODE == kWsum) {
-                stage_tilec(0, 0);
-                ts_epi_barrier();
-            }
-            for (int m = 0; m < p.n_str_tiles; ++m) {
-                const int buf = m & 1;
-                if ((MODE == kLabel || MODE == kWsum) && m + 1 < p.n_str_tiles) stage_tilec(m + 1, buf ^ 1);
-                const int s0 = m * BN + half * kHalfCols;      // first streamed index of this warp
-                const int nvalid = min(kHalfCols, p.str_valid - s0);
-                mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < kHalfCols / 32; ++c) {
-                    if (MODE == kNoop) break;
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                  (uint32_t)(kTsAccCols + acc * BN + half * kHalfCols + c * 32), v);
-                    if (MODE == kLoadOnly) {
-                        float sacc = 0.f;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) sacc += v[q];
-                        if (sacc == 123456.789f) p.atten[0] = sacc;  // keep the loads alive
-                    } else if (MODE == kStore) {
-                        if (res_ok) {
-                            float *dst = p.atten + ((size_t)b * p.res_valid + gr) * p.str_valid + s0 + c * 32;
-#pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (c * 32 + q < nvalid) dst[q] = __fdiv_rn(v[q], ktemp);
-                        }
-                    } else if (MODE == kStats) {
-                        if (nvalid >= kHalfCols) {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) { v[q] = ex2(fmaf(v[q], kc1, -rconst)); racc += v[q]; }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) {
-                                v[q] = (c * 32 + q < nvalid) ? ex2(fmaf(v[q], kc1, -rconst)) : 0.f;
-                                racc += v[q];
-                            }
-                        }
-                        sm.colred[buf][quad][half * kHalfCols + c * 32 + lane] = warp_transpose_reduce<false>(v);
-                    } else if (MODE == kLabel) {
-                        if (m == 0 && half == 0 && c == 0 && res_ok)   // streamed index 0 = background row of S
-                            p.res_bg[(size_t)b * p.res_pad + gr] = fmaf(v[0], kc2x, -str0_true);
-                        if (gr == 0) {                                  // resident index 0 = background column
-#pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (c * 32 + q < nvalid)
-                                    p.str_bg[(size_t)b * p.str_pad + s0 + c * 32 + q] = fmaf(v[q], kc2x, -rconst_true);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const float x = v[q] * kc2x;
-                            racc = fmaxf(racc, x - sm.tilec[buf][half * kHalfCols + c * 32 + q].x);
-                            v[q] = x - rconst;
-                        }
-                        sm.colred[buf][quad][half * kHalfCols + c * 32 + lane] = warp_transpose_reduce<true>(v);
-                    } else {  // kWsum
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const float e = ex2(fmaf(v[q], kc1, -kc2));
-                            const float u = e * e;
-                            const float4 g = sm.tilec[buf][half * kHalfCols + c * 32 + q];
-                            racc = fmaf(u, g.w, racc);
-                            r1 = fmaf(u, g.x, r1);
-                            r2 = fmaf(u, g.y, r2);
-                            r3 = fmaf(u, g.z, r3);
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (PAIR) mbar_arrive_remote(smem_u32(&sm.tmem_empty[acc]), 0);
-                    else mbar_arrive(smem_u32(&sm.tmem_empty[acc]));
-                }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (MODE != kStore && MODE != kNoop && MODE != kLoadOnly) ts_epi_barrier();  // colred[buf] complete; tilec[buf^1] staged
-                if (MODE == kStats || MODE == kLabel) {
-                    if (ep_tid < BN) {
-                        float x = sm.colred[buf][0][ep_tid];
-#pragma unroll
-                        for (int w = 1; w < 4; ++w)
-                            x = (MODE == kLabel) ? fmaxf(x, sm.colred[buf][w][ep_tid]) : x + sm.colred[buf][w][ep_tid];
-                        p.str_part[((size_t)b * p.n_res_strips + s) * p.str_pad + m * BN + ep_tid] = x;
-                    }
-                }
-            }
-            // thread-local accumulators: combine the two column halves, then store
-            if (MODE == kStats || MODE == kLabel) {
-                sm.red[half][et] = racc;
-                ts_epi_barrier();
-                if (half == 0 && res_ok) {
-                    const float a = sm.red[0][et], c2v = sm.red[1][et];
-                    p.res_acc[(size_t)b * p.res_pad + gr] = (MODE == kLabel) ? fmaxf(a, c2v) : a + c2v;
-                }
-                ts_epi_barrier();
-            } else if (MODE == kWsum) {
-                float4 *r4 = reinterpret_cast<float4 *>(&sm.colred[0][0][0]);  // 2 x 128 float4 of scratch
-                r4[half * BM + et] = make_float4(r1, r2, r3, racc);
-                ts_epi_barrier();
-                if (half == 0 && res_ok && gr >= 1) {
-                    const float4 a = r4[et], c4 = r4[BM + et];
-                    const size_t ri = (size_t)b * (p.res_valid - 1) + gr - 1;
-                    const float f = p.w1[ri] * p.inv_rowsum[(size_t)b * p.res_pad + gr];
-                    const float sA = (a.w + c4.w) * f;
-                    p.rowsumA[ri] = sA;                      // assignment_score (MU:330)
-                    const float inv = 1.0f / (sA + 1e-6f);   // MU:327
-                    p.pred[ri * 3 + 0] = (a.x + c4.x) * f * inv;
-                    p.pred[ri * 3 + 1] = (a.y + c4.y) * f * inv;
-                    p.pred[ri * 3 + 2] = (a.z + c4.z) * f * inv;
-                }
-                ts_epi_barrier();
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (CG != 0) cluster_sync_all();  // the peer may still multicast into this CTA / arrive on its barriers
-    if (warp == 1) {
-        tc_fence_after();
-        if (PAIR)
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)kTsTmemCols)
-                         : "memory");
-        else
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)kTsTmemCols)
-                         : "memory");
-    }
-}
-
 // ---------------------------------------------------------------------------- prep / finish
-// One warp per padded row: x / max(|x|,1e-12) split into bf16 hi and lo.
+// One warp per padded row of the GEMM operands: x / max(|x|,1e-12) split into bf16 hi and lo.
+// The first `skip` rows of every instance (the background token) stay out of the operands; with
+// skip = 1 the warp also leaves the fp32 cosine of its row with the OTHER set's background
+// token, i.e. the background column (bg_a) / row (bg_b) of the similarity matrix, and their
+// corner s00.  C <= 256 and C % 64 == 0: a lane holds C/32 values of the row in registers
+// (float2 loads, bf16x2 stores: every access of the warp is one contiguous 256 / 128 byte run).
 __global__ void __launch_bounds__(256)
 tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloat16 *__restrict__ outa,
                const float *__restrict__ fb, int rows_b, int rows_pb, __nv_bfloat16 *__restrict__ outb,
-               int B, int C, int normalize) {
+               int B, int C, int normalize, int skip, float *__restrict__ bg_a /* (B,rows_pa) */,
+               float *__restrict__ bg_b /* (B,rows_pb) */, float *__restrict__ s00 /* (B) */) {
     // both operands in one launch: warps [0, B*rows_pa) prepare A', the rest prepare B'
     int gr = blockIdx.x * (blockDim.x >> 5) + warp_id();
     const bool second = gr >= B * rows_pa;
     if (second) gr -= B * rows_pa;
-    const float *f = second ? fb : fa;
+    const float *f = second ? fb : fa, *fo = second ? fa : fb;
     const int rows = second ? rows_b : rows_a, rows_p = second ? rows_pb : rows_pa;
+    const int rows_o = second ? rows_a : rows_b;
     __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
     if (gr >= B * rows_p) return;
-    const int b = gr / rows_p, i = gr - b * rows_p;
-    __nv_bfloat16 *hi = out + (size_t)gr * C, *lo = out + ((size_t)B * rows_p + gr) * C;
+    const int b = gr / rows_p, i = gr - b * rows_p, lane = lane_id();
+    const int nit = C >> 6;  // float2 per lane
+    __nv_bfloat162 *hi = reinterpret_cast<__nv_bfloat162 *>(out + (size_t)gr * C),
+                   *lo = reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)B * rows_p + gr) * C);
+    float *bg = second ? bg_b : bg_a;
     if (i >= rows) {
-        for (int c = lane_id(); c < C; c += 32) { hi[c] = __float2bfloat16(0.f); lo[c] = hi[c]; }
+        for (int it = 0; it < nit; ++it) {
+            hi[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
+            lo[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
+        }
+        if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
         return;
     }
-    const float *src = f + ((size_t)b * rows + i) * C;
-    float inv = 1.f;
-    if (normalize) {
+    // a row as kMaxKC float2 per lane, and 1 / max(|row|, 1e-12) (1 when not normalising)
+    auto load_row = [&](const float *row, float2 (&x)[kMaxKC]) {
         float s = 0.f;
-        for (int c = lane_id(); c < C; c += 32) { const float v = __ldg(src + c); s = fmaf(v, v, s); }
-        s = warp_sum(s);
-        inv = fmaxf(sqrtf(s), 1e-12f);
+#pragma unroll
+        for (int it = 0; it < kMaxKC; ++it) {
+            x[it] = it < nit ? __ldg(reinterpret_cast<const float2 *>(row) + it * 32 + lane) : make_float2(0.f, 0.f);
+            s = fmaf(x[it].x, x[it].x, s);
+            s = fmaf(x[it].y, x[it].y, s);
+        }
+        return normalize ? fmaxf(sqrtf(warp_sum(s)), 1e-12f) : 1.f;
+    };
+    float2 x[kMaxKC], tk[kMaxKC];
+    const float inv = load_row(f + ((size_t)b * (rows + skip) + skip + i) * C, x);
+    float dot = 0.f;
+    const float *tok = fo + (size_t)b * (rows_o + skip) * C;  // the other set's background token
+    float inv_tok = 1.f;
+    if (skip) inv_tok = load_row(tok, tk);
+#pragma unroll
+    for (int it = 0; it < kMaxKC; ++it) {
+        if (it >= nit) break;
+        float2 v = x[it];
+        if (normalize) { v.x = __fdiv_rn(v.x, inv); v.y = __fdiv_rn(v.y, inv); }
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+        const float2 hf = __bfloat1622float2(h);
+        hi[it * 32 + lane] = h;
+        lo[it * 32 + lane] = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+        if (skip) { dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot); }
     }
-    for (int c = lane_id(); c < C; c += 32) {
-        const float v = normalize ? __fdiv_rn(__ldg(src + c), inv) : __ldg(src + c);
-        const __nv_bfloat16 h = __float2bfloat16(v);
-        hi[c] = h;
-        lo[c] = __float2bfloat16(v - __bfloat162float(h));
+    if (!skip) return;
+    dot = __fdiv_rn(warp_sum(dot), inv_tok);
+    if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
+    if (!second && i == 0) {  // the corner: background token x background token
+        float2 own[kMaxKC];
+        const float inv_own = load_row(f + (size_t)b * (rows + skip) * C, own);
+        float d0 = 0.f;
+#pragma unroll
+        for (int it = 0; it < kMaxKC; ++it) { d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0); }
+        d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
+        if (lane == 0) s00[b] = d0;
     }
 }
 
-// after pass 1: row sums from their per-half-strip partials (fixed order: deterministic),
-// reciprocals and log2 of both sums; +inf logs mark padded rows / columns
+// kStore only: the background row and column of the logits (the GEMM writes the interior)
 __global__ void __launch_bounds__(256)
-tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restrict__ colsum, int R,
-                       int Cn, int Mp, int Np, int n_part, float *__restrict__ inv_rowsum,
-                       float *__restrict__ lrs, float *__restrict__ inv_colsum,
-                       float *__restrict__ lcs) {
+tc_store_bg_kernel(const float *__restrict__ bg_a, const float *__restrict__ bg_b,
+                   const float *__restrict__ s00, int R, int Cn, int Mp, int Np, float temp,
+                   float *__restrict__ atten /* (B,R+1,Cn+1) */) {
     const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    float *dst = atten + (size_t)b * (R + 1) * (Cn + 1);
+    if (k == 0) dst[0] = __fdiv_rn(s00[b], temp);
+    if (k < R) dst[(size_t)(k + 1) * (Cn + 1)] = __fdiv_rn(bg_a[(size_t)b * Mp + k], temp);
+    if (k < Cn) dst[k + 1] = __fdiv_rn(bg_b[(size_t)b * Np + k], temp);
+}
+
+// after pass 1: row / column sums from their partials (fixed order: deterministic) plus the
+// background column / row term, reciprocals and log2; +inf logs mark padded rows / columns
+__global__ void __launch_bounds__(256)
+tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restrict__ colpart,
+                       const float *__restrict__ bg_a, const float *__restrict__ bg_b, int R, int Cn,
+                       int Mp, int Np, int n_part, int planes, float c1, float c2,
+                       float *__restrict__ inv_rowsum, float *__restrict__ lrs,
+                       float *__restrict__ inv_colsum, float *__restrict__ lcs) {
+    const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < Mp) {
         float s = 0.f;
-        for (int t = 0; t < n_part; ++t) s += rowpart[((size_t)b * n_part + t) * Mp + k];
+        if (k < R) {
+            for (int t = 0; t < n_part; ++t) s += rowpart[((size_t)b * n_part + t) * Mp + k];
+            s += ex2(fmaf(bg_a[(size_t)b * Mp + k], c1, -c2));
+        }
         const bool ok = k < R && s > 0.f;
         inv_rowsum[(size_t)b * Mp + k] = ok ? 1.0f / s : 0.f;
         lrs[(size_t)b * Mp + k] = ok ? log2f(s) : INFINITY;
     }
     if (k < Np) {
-        const float s = k < Cn ? colsum[(size_t)b * Np + k] : 0.f;
+        float s = 0.f;
+        if (k < Cn) {
+            for (int q = 0; q < planes; ++q) s += colpart[((size_t)q * B + b) * Np + k];
+            s += ex2(fmaf(bg_b[(size_t)b * Np + k], c1, -c2));
+        }
         const bool ok = k < Cn && s > 0.f;
         inv_colsum[(size_t)b * Np + k] = ok ? 1.0f / s : 0.f;
         lcs[(size_t)b * Np + k] = ok ? log2f(s) : INFINITY;
     }
 }
 
-// after pass 2: w1_i, w2_j and the per-column constants of pass 3
+// after pass 2: w1_i, w2_j and the per-column constants of pass 3.  A point is foreground when its
+// best match beats the background entry (MU:321-322); the background row / column sums are reduced
+// here from the 2 x 2049 exact cosines of the prep kernel.
 __global__ void __launch_bounds__(256)
-tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__restrict__ bgcol,
-                       const float *__restrict__ colmax, const float *__restrict__ bgrow,
-                       const float *__restrict__ inv_colsum, const float *__restrict__ pts2, int R,
-                       int Cn, int Mp, int Np, int n_part, float *__restrict__ w1 /* (B,R-1) */,
-                       float *__restrict__ w2_out /* (B,Cn-1) or null */, float4 *__restrict__ G) {
-    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 1 && k < R) {
+tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__restrict__ colpart,
+                       const float *__restrict__ bg_a, const float *__restrict__ bg_b,
+                       const float *__restrict__ s00, const float *__restrict__ inv_colsum,
+                       const float *__restrict__ pts2, int R, int Cn, int Mp, int Np, int n_part,
+                       int planes, float c1, float c2, float *__restrict__ w1 /* (B,R) */,
+                       float *__restrict__ w2_out /* (B,Cn) or null */, float4 *__restrict__ G) {
+    __shared__ float red[32];
+    const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    float sr = 0.f, sc = 0.f;  // background row sum (over columns), background column sum (over rows)
+    for (int j = threadIdx.x; j < Cn; j += blockDim.x) sr += ex2(fmaf(bg_b[(size_t)b * Np + j], c1, -c2));
+    for (int i = threadIdx.x; i < R; i += blockDim.x) sc += ex2(fmaf(bg_a[(size_t)b * Mp + i], c1, -c2));
+    const float e00 = ex2(fmaf(s00[b], c1, -c2));
+    const float lrs0 = log2f(block_sum(sr, red) + e00), lcs0 = log2f(block_sum(sc, red) + e00);
+    const float c2x = 2.0f * c1;
+    if (k < R) {
         float m = -INFINITY;
         for (int t = 0; t < n_part; ++t) m = fmaxf(m, rowmaxpart[((size_t)b * n_part + t) * Mp + k]);
-        w1[(size_t)b * (R - 1) + k - 1] = m > bgcol[(size_t)b * Mp + k] ? 1.f : 0.f;  // label1 > 0
+        w1[(size_t)b * R + k] = m > fmaf(bg_a[(size_t)b * Mp + k], c2x, -lcs0) ? 1.f : 0.f;  // label1 > 0
     }
     if (k < Np) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k >= 1 && k < Cn) {
-            const bool fg = colmax[(size_t)b * Np + k] > bgrow[(size_t)b * Np + k];  // label2 > 0
-            if (w2_out) w2_out[(size_t)b * (Cn - 1) + k - 1] = fg ? 1.f : 0.f;
+        if (k < Cn) {
+            float cm = -INFINITY;
+            for (int q = 0; q < planes; ++q) cm = fmaxf(cm, colpart[((size_t)q * B + b) * Np + k]);
+            const bool fg = cm > fmaf(bg_b[(size_t)b * Np + k], c2x, -lrs0);  // label2 > 0
+            if (w2_out) w2_out[(size_t)b * Cn + k] = fg ? 1.f : 0.f;
             if (fg) {
                 const float ic = inv_colsum[(size_t)b * Np + k];
-                const float *q = pts2 + ((size_t)b * (Cn - 1) + k - 1) * 3;
+                const float *q = pts2 + ((size_t)b * Cn + k) * 3;
                 g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
             }
         }
@@ -1075,13 +748,13 @@ __global__ void __launch_bounds__(256)
 tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restrict__ inv_rowsum,
                       const float *__restrict__ w1, int R, int Mp, int n_part,
                       float *__restrict__ rowsumA, float *__restrict__ pred) {
-    const int b = blockIdx.y, i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     float a[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = 0; t < n_part; ++t)
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] += rowpart4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
-    const size_t ri = (size_t)b * (R - 1) + i - 1;
+    const size_t ri = (size_t)b * R + i;
     const float f = w1[ri] * inv_rowsum[(size_t)b * Mp + i];
     const float sA = a[0] * f;
     rowsumA[ri] = sA;                       // assignment_score (MU:330)
@@ -1126,7 +799,9 @@ static int make_operand_map(CUtensorMap *map, const void *base, size_t rows, int
 struct Ws {
     __nv_bfloat16 *A, *Bm;
     float *rowpart;  // (B, 2*n_strips, 4, Mp): the largest of the per-pass row partial layouts
-    float *colA, *colB, *inv_rowsum, *lrs, *inv_colsum, *lcs, *bgcol, *w1, *w2, *rowsumA, *pred;
+    float *colpart;  // (2*n_msteps, B, Np): column partial planes (sums, then maxima)
+    float *bg_a, *bg_b, *s00;  // background column / row of the cosine matrix and their corner
+    float *inv_rowsum, *lrs, *inv_colsum, *lcs, *w1, *w2, *rowsumA, *pred;
     float4 *G;
     int *counters;
     size_t bytes;
@@ -1134,9 +809,9 @@ struct Ws {
 
 static int pad_to(int x, int g) { return (x + g - 1) / g * g; }
 
-// g = row padding granularity of the operands: 128, or 256 for the multicast variant (strips in pairs)
-static Ws carve(void *base, int B, int N1, int N2, int C, int g) {
-    const size_t Mp = pad_to(N1 + 1, g), Np = pad_to(N2 + 1, g), ns = Np / 128;
+// rows = GEMM rows / columns per instance (without the background token)
+static Ws carve(void *base, int B, int rows1, int rows2, int C) {
+    const size_t Mp = pad_to(rows1, TM), Np = pad_to(rows2, TN), ns = Np / TN, nm = Mp / TM;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t o = off;
@@ -1147,17 +822,18 @@ static Ws carve(void *base, int B, int N1, int N2, int C, int g) {
     w.A = (__nv_bfloat16 *)take(2 * B * Mp * C * 2);
     w.Bm = (__nv_bfloat16 *)take(2 * B * Np * C * 2);
     w.rowpart = (float *)take(B * 2 * ns * 4 * Mp * 4);
-    w.colA = (float *)take(B * Np * 4);   // colsum, then colmax
-    w.colB = (float *)take(B * Np * 4);   // bgrow
+    w.colpart = (float *)take(2 * nm * B * Np * 4);
+    w.bg_a = (float *)take(B * Mp * 4);
+    w.bg_b = (float *)take(B * Np * 4);
+    w.s00 = (float *)take(B * 4);
     w.inv_rowsum = (float *)take(B * Mp * 4);
     w.lrs = (float *)take(B * Mp * 4);
     w.inv_colsum = (float *)take(B * Np * 4);
     w.lcs = (float *)take(B * Np * 4);
-    w.bgcol = (float *)take(B * Mp * 4);
-    w.w1 = (float *)take((size_t)B * N1 * 4);
-    w.w2 = (float *)take((size_t)B * N2 * 4);
-    w.rowsumA = (float *)take((size_t)B * N1 * 4);
-    w.pred = (float *)take((size_t)B * N1 * 12);
+    w.w1 = (float *)take((size_t)B * rows1 * 4);
+    w.w2 = (float *)take((size_t)B * rows2 * 4);
+    w.rowsumA = (float *)take((size_t)B * rows1 * 4);
+    w.pred = (float *)take((size_t)B * rows1 * 12);
     w.G = (float4 *)take(B * Np * 16);
     w.counters = (int *)take(B * 3 * 4);
     w.bytes = off;
@@ -1175,59 +851,45 @@ static int num_sms() {
     return n;
 }
 
-template <int MODE>
-static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p,
-                       cudaStream_t st) {
-    const size_t smem = sizeof(Smem) + 1024;
-    static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE>, smem, &cached)) return rc;
-    const int grid = min(num_sms(), p.B * p.n_strips);
-    fine_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
-    return pem_launch_status();
-}
+static int g_steps_per_task = 0;  // development knob: 0 = choose automatically
 
-template <int MODE, int CG>
-static int launch_ts_pass(const CUtensorMap &tmStr, const TsParams &p, cudaStream_t st) {
-    const size_t smem = sizeof(TsSmem) + 1024;
-    static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(fine_ts_kernel<MODE, CG>, smem, &cached)) return rc;
-    if (CG == 0) {
-        const int grid = min(num_sms(), p.B * p.n_res_strips);
-        fine_ts_kernel<MODE, 0><<<grid, kTsThreads, smem, st>>>(tmStr, p);
-        return pem_launch_status();
-    }
-    // clusters of 2: one cluster per SM pair, each walking pairs of strips
-    const int n_pairs = p.B * p.n_res_strips / 2;
-    const int n_clusters = min(num_sms() / 2, n_pairs);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * n_clusters);
-    cfg.blockDim = dim3(kTsThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fine_ts_kernel<MODE, CG>, tmStr, p);
-    if (e != cudaSuccess) return (int)e;
-    return pem_launch_status();
-}
-
-static int g_fine_variant = 0;  // development knob: 0 = SS-mode kernel, 1 = TS-mode kernel
-
-static int fill_common(Params &p, int B, int N1, int N2, int C, float temp, int g = 128) {
+// rows1 x rows2 GEMM per instance
+static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp) {
     if (C % BK != 0 || C > BK * kMaxKC) return PEM_E_UNSUPPORTED;
     if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
-    p.B = B; p.R = N1 + 1; p.Cn = N2 + 1;
-    p.Mp = pad_to(N1 + 1, g); p.Np = pad_to(N2 + 1, g);
-    p.n_mtiles = p.Mp / BM; p.n_strips = p.Np / BN; p.KC = C / BK;
+    p.B = B; p.R = rows1; p.Cn = rows2;
+    p.Mp = pad_to(rows1, TM); p.Np = pad_to(rows2, TN);
+    p.n_msteps = p.Mp / TM; p.n_strips = p.Np / TN; p.KC = C / BK;
+    // Row steps per task: short tasks balance the CTA pairs (a pair runs ceil(tasks / pairs) of
+    // them) at the price of one strip reload (hidden) and one column fold per task.
+    const int pairs = max(1, num_sms() / 2);
+    int best = p.n_msteps;
+    double best_cost = 1e30;
+    for (int spt = p.n_msteps; spt >= 1; --spt) {
+        const int splits = (p.n_msteps + spt - 1) / spt;
+        const long tasks = (long)B * p.n_strips * splits;
+        const long rounds = (tasks + pairs - 1) / pairs;
+        const double cost = (double)rounds * (spt + 0.25);
+        if (cost < best_cost) { best_cost = cost; best = spt; }
+    }
+    p.spt = g_steps_per_task > 0 ? min(g_steps_per_task, p.n_msteps) : best;
+    p.n_splits = (p.n_msteps + p.spt - 1) / p.spt;
     p.temp = temp;
     p.c1 = 1.4426950408889634f / temp;
     p.c2 = 1.4426950408889634f / temp;
     return PEM_OK;
+}
+
+template <int MODE>
+static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
+    static_assert(kEpiThreads == TN, "one epilogue thread per strip column");
+    const size_t smem = sizeof(Smem) + 1024;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE>, smem, &cached)) return rc;
+    const int n_tasks = p.B * p.n_strips * p.n_splits;
+    const int pairs = min(max(1, num_sms() / 2), n_tasks);  // one cluster of two CTAs per SM pair
+    fine_tc_kernel<MODE><<<2 * pairs, kThreads, smem, st>>>(tmA, tmB, p);
+    return pem_launch_status();
 }
 
 }  // namespace tc
@@ -1236,7 +898,7 @@ static int fill_common(Params &p, int B, int N1, int N2, int C, float temp, int 
 using namespace pem;
 using namespace pem::tc;
 
-extern "C" void pem_dev_set_fine_variant(int v) { g_fine_variant = v; }
+extern "C" void pem_dev_set_fine_steps_per_task(int v) { g_steps_per_task = v; }
 
 // fine.cu
 namespace pem {
@@ -1247,10 +909,10 @@ int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA,
 
 extern "C" size_t pem_fine_fused_workspace_bytes(int B, int N1, int N2, int C) {
     if (B <= 0 || N1 <= 0 || N2 <= 0 || C <= 0) return 0;
-    return carve(nullptr, B, N1, N2, C, 256).bytes;
+    return carve(nullptr, B, N1 + 1, N2 + 1, C).bytes;  // covers both entry points
 }
 
-// features already carry the background token in row 0: f1 (B,N1+1,C), f2 (B,N2+1,C)
+// f1 (B,N1p,C), f2 (B,N2p,C) -> logits (B,N1p,N2p); every row takes part in the GEMM
 extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B, int N1p, int N2p,
                                          int C, float temp, int normalize, float *atten,
                                          void *workspace, size_t workspace_bytes,
@@ -1260,34 +922,19 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
     PEM_REQUIRE_PTR(atten);
     PEM_REQUIRE(B > 0 && N1p > 0 && N2p > 0 && C > 0, PEM_E_SHAPE);
     Params p{};
-    const int g = g_fine_variant >= 2 ? 256 : 128;
-    if (int rc = fill_common(p, B, N1p - 1, N2p - 1, C, temp, g)) return rc;
+    if (int rc = fill_common(p, B, N1p, N2p, C, temp)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1p - 1, N2p - 1, C),
                 PEM_E_WORKSPACE);
     cudaStream_t st = pem_cu_stream(stream);
-    Ws w = carve(workspace, B, N1p - 1, N2p - 1, C, g);
+    Ws w = carve(workspace, B, N1p, N2p, C);
     tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
-                                                                 C, normalize);
+                                                                 C, normalize, 0, nullptr, nullptr, nullptr);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
-    if (g_fine_variant >= 1) {
-        TsParams q{};
-        q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
-        q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
-        q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
-        q.res_op = w.A;
-        q.atten = atten;
-        if (g_fine_variant >= 2) {
-            CUtensorMap tmBh;
-            if (int rc = make_operand_map(&tmBh, w.Bm, (size_t)2 * B * p.Np, C, BN / 2)) return rc;
-            return g_fine_variant == 2 ? launch_ts_pass<kStore, 1>(tmBh, q, st)
-                                       : launch_ts_pass<kStore, 2>(tmBh, q, st);
-        }
-        return launch_ts_pass<kStore, 0>(tmB, q, st);
-    }
     p.atten = atten;
+    p.off = 0;
     return launch_pass<kStore>(tmA, tmB, p, st);
 }
 
@@ -1306,86 +953,39 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     PEM_REQUIRE_PTR(score);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     Params p{};
-    const int g = g_fine_variant >= 2 ? 256 : 128;
-    if (int rc = fill_common(p, B, N1, N2, C, temp, g)) return rc;
+    if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;  // the background token stays out of the GEMM
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
     cudaStream_t st = pem_cu_stream(stream);
-    Ws w = carve(workspace, B, N1, N2, C, g);
+    Ws w = carve(workspace, B, N1, N2, C);
     float *w1 = w1_out ? w1_out : w.w1;
     float *rsA = rowsum_out ? rowsum_out : w.rowsumA;
     float *pred = pred_out ? pred_out : w.pred;
 
     tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
-                                                                 C, 1);
+                                                                 C, 1, 1, w.bg_a, w.bg_b, w.s00);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
 
     const int mx = max(p.Mp, p.Np);
-    if (g_fine_variant >= 1) {
-        const bool mc = g_fine_variant >= 2;
-        const int cgv = g_fine_variant - 1;  // 0 alone, 1 multicast, 2 CTA pairs
-        CUtensorMap tmAs = tmA, tmBs = tmB;  // streamed-operand maps (64-row boxes when multicasting)
-        if (mc) {
-            if (int rc = make_operand_map(&tmAs, w.A, (size_t)2 * B * p.Mp, C, BN / 2)) return rc;
-            if (int rc = make_operand_map(&tmBs, w.Bm, (size_t)2 * B * p.Np, C, BN / 2)) return rc;
-        }
-        TsParams q{};
-        q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
-        // passes 1-2 on the transposed problem: resident = column strip of S (rows of B'),
-        // streamed = rows of S (tiles of A')
-        q.res_valid = p.Cn; q.str_valid = p.R; q.res_pad = p.Np; q.str_pad = p.Mp;
-        q.n_res_strips = p.Np / BM; q.n_str_tiles = (p.R + BN - 1) / BN;
-        const int n_part = q.n_res_strips;
-        q.res_op = w.Bm;
-        q.res_acc = w.colA;       // colsum
-        q.str_part = w.rowpart;   // (B, n_part, Mp)
-        if (int rc = cgv == 2 ? launch_ts_pass<kStats, 2>(tmAs, q, st)
-                     : cgv == 1 ? launch_ts_pass<kStats, 1>(tmAs, q, st) : launch_ts_pass<kStats, 0>(tmAs, q, st))
-            return rc;
-        tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-            w.rowpart, w.colA, p.R, p.Cn, p.Mp, p.Np, n_part, w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
-        q.res_const = w.lcs; q.str_const = w.lrs;
-        q.res_acc = w.colA;       // colmax
-        q.res_bg = w.colB;        // bgrow
-        q.str_bg = w.bgcol;
-        if (int rc = cgv == 2 ? launch_ts_pass<kLabel, 2>(tmAs, q, st)
-                     : cgv == 1 ? launch_ts_pass<kLabel, 1>(tmAs, q, st) : launch_ts_pass<kLabel, 0>(tmAs, q, st))
-            return rc;
-        tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-            w.rowpart, w.bgcol, w.colA, w.colB, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part, w1,
-            w2_out, w.G);
-        // pass 3 direct: resident = row strip of S (rows of A'), streamed = column tiles (B')
-        q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
-        q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
-        q.res_op = w.A;
-        q.G = w.G; q.w1 = w1; q.inv_rowsum = w.inv_rowsum; q.rowsumA = rsA; q.pred = pred;
-        if (int rc = cgv == 2 ? launch_ts_pass<kWsum, 2>(tmBs, q, st)
-                     : cgv == 1 ? launch_ts_pass<kWsum, 1>(tmBs, q, st) : launch_ts_pass<kWsum, 0>(tmBs, q, st))
-            return rc;
-        return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
-                                score, st);
-    }
-    const int n_part = 2 * p.n_strips;
+    const int n_part = 2 * p.n_strips, planes = 2 * p.n_splits;
     // pass 1: softmax statistics
     p.rowpart = w.rowpart;
-    p.colsum = w.colA;
+    p.colpart = w.colpart;
     if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
     tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-        w.rowpart, w.colA, p.R, p.Cn, p.Mp, p.Np, n_part, w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
+        w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
+        w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
     // pass 2: foreground labels
     p.lrs = w.lrs;
     p.lcs = w.lcs;
     p.rowmaxpart = w.rowpart;
-    p.bgcol = w.bgcol;
-    p.colmax = w.colA;
-    p.bgrow = w.colB;
     if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
     tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-        w.rowpart, w.bgcol, w.colA, w.colB, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part, w1,
-        w2_out, w.G);
+        w.rowpart, w.colpart, w.bg_a, w.bg_b, w.s00, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
+        planes, p.c1, p.c2, w1, w2_out, w.G);
     // pass 3: weighted row sums -> correspondences
     p.G = w.G;
     p.rowpart4 = w.rowpart;
@@ -1397,27 +997,28 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
                             score, st);
 }
 
-// Development: run one GEMM pass of the TS kernel with a stub epilogue (mode 4: none, 5: TMEM loads
-// only) on already prepared operands, to separate tensor-pipe time from epilogue interference.
+// Development: time one GEMM pass (mode 1 stats, 2 label, 3 wsum) with parts of the kernel disabled
+// (Params::dev).  Modes 2-3 read the constants a previous pem_fine_fused call left in `workspace`.
 extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
-                                 int mode, int cg, float *scratch, void *workspace, size_t workspace_bytes,
+                                 int flags, int mode, int prep, void *workspace, size_t workspace_bytes,
                                  pem_stream_t stream) {
     Params p{};
-    const int g = cg >= 1 ? 256 : 128;
-    if (int rc = fill_common(p, B, N1, N2, C, temp, g)) return rc;
+    if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;
     cudaStream_t st = pem_cu_stream(stream);
-    Ws w = carve(workspace, B, N1, N2, C, g);
+    Ws w = carve(workspace, B, N1, N2, C);
     if (workspace_bytes < w.bytes) return PEM_E_WORKSPACE;
-    tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B, C, 1);
-    CUtensorMap tm;
-    if (int rc = make_operand_map(&tm, w.Bm, (size_t)2 * B * p.Np, C, cg >= 1 ? BN / 2 : BN)) return rc;
-    TsParams q{};
-    q.B = B; q.KC = p.KC; q.C = C; q.c1 = p.c1; q.c2 = p.c2; q.temp = temp;
-    q.res_valid = p.R; q.str_valid = p.Cn; q.res_pad = p.Mp; q.str_pad = p.Np;
-    q.n_res_strips = p.Mp / BM; q.n_str_tiles = (p.Cn + BN - 1) / BN;
-    q.res_op = w.A;
-    q.atten = scratch;
-    if (mode == 4) return cg == 2 ? launch_ts_pass<kNoop, 2>(tm, q, st) : launch_ts_pass<kNoop, 0>(tm, q, st);
-    if (mode == 5) return cg == 2 ? launch_ts_pass<kLoadOnly, 2>(tm, q, st) : launch_ts_pass<kLoadOnly, 0>(tm, q, st);
-    return cg == 2 ? launch_ts_pass<kWsum, 2>(tm, q, st) : launch_ts_pass<kWsum, 0>(tm, q, st);
+    if (prep)
+        tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm,
+                                                                     B, C, 1, 1, w.bg_a, w.bg_b, w.s00);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
+    if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
+    p.dev = flags;
+    p.rowpart = p.rowmaxpart = p.rowpart4 = w.rowpart;
+    p.colpart = w.colpart;
+    p.lrs = w.lrs;
+    p.lcs = w.lcs;
+    p.G = w.G;
+    return mode == 3 ? launch_pass<kWsum>(tmA, tmB, p, st)
+                     : mode == 2 ? launch_pass<kLabel>(tmA, tmB, p, st) : launch_pass<kStats>(tmA, tmB, p, st);
 }

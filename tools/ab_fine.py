@@ -1,4 +1,4 @@
-"""A/B the SS-mode and TS-mode fused fine kernels: parity vs the oracle + timing."""
+"""Fused fine kernel: parity vs the oracle + timing, for several row-steps-per-task settings (0 = automatic)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,10 +17,10 @@ f1d, f2d = f1.to(dev), f2.to(dev)
 big = {k: v.to(dev) for k, v in pkg.synth.replicate_batch(pkg.synth.make_batch(list(range(4))), 4).items()}
 bgb = big["bg"][:, None, :]
 F1, F2 = torch.cat([bgb, big["dense_fm"]], 1).contiguous(), torch.cat([bgb, big["dense_fo"]], 1).contiguous()
-for variant in (0, 1, 3):
-    L.pem_dev_set_fine_variant(variant)
+for variant in (0, 8, 4, 2, 1):
+    L.pem_dev_set_fine_steps_per_task(variant)
     got = mu.compute_feature_similarity(f1d, f2d, "cosine", 0.1, True, backend="tc").cpu()
-    print("variant", variant, "similarity max err", (got - atten).abs().max().item())
+    print("steps/task", variant, "similarity max err", (got - atten).abs().max().item())
     R, t, s, st = mu.compute_fine_Rt_fused(f1d, f2d, gd["dense_pm"], gd["dense_po"], gd["model"], 0.1, 0.15, return_stages=True)
     print("   w1 mismatch", (st["w1"].cpu() != ost["w1"]).float().mean().item(), "w2", (st["w2"].cpu() != ost["w2"]).float().mean().item(),
           "row err", (st["row"].cpu() - ost["row"]).abs().max().item(), "pred err", (st["pred"].cpu() - ost["pred"]).abs().max().item())
@@ -34,4 +34,4 @@ for variant in (0, 1, 3):
         mu.compute_fine_Rt_fused(F1, F2, big["dense_pm"], big["dense_po"], big["model"], 0.1, 0.15)
     e1.record(); torch.cuda.synchronize()
     print("   fused fine B=16: %.1f us" % (e0.elapsed_time(e1) / 10 * 1e3))
-L.pem_dev_set_fine_variant(0)
+L.pem_dev_set_fine_steps_per_task(0)

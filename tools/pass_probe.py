@@ -1,3 +1,5 @@
+"""Timing experiments on one fine GEMM pass: which role bounds it?
+flags: 1 no MMAs, 2 no streamed TMA loads, 4 no epilogue math.  mode: 1 stats, 2 label, 3 wsum."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,22 +8,35 @@ pkg = g.load_package()
 dev = torch.device("cuda:0")
 L = ctypes.CDLL(pkg._lib.LIB_PATH)
 L.pem_dev_fine_pass.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-L.pem_fine_fused_workspace_bytes.restype = ctypes.c_size_t
-B, N, C = 16, 2048, 256
-f1 = torch.randn(B, N + 1, C, device=dev); f2 = torch.randn(B, N + 1, C, device=dev)
-nb = L.pem_fine_fused_workspace_bytes(B, N, N, C)
-ws = torch.empty(nb, dtype=torch.uint8, device=dev); scratch = torch.zeros(1024, device=dev)
+                                ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+B = int(os.environ.get("B", 16))
+base = pkg.synth.make_batch(list(range(4)))
+b = {k: v.to(dev) for k, v in pkg.synth.replicate_batch(base, B // 4).items()}
+bg = b["bg"][:, None, :]
+f1, f2 = torch.cat([bg, b["dense_fm"]], 1).contiguous(), torch.cat([bg, b["dense_fo"]], 1).contiguous()
+N, C = f1.shape[1] - 1, f1.shape[2]
+nb = pkg._lib.lib().pem_fine_fused_workspace_bytes(B, N, N, C)
+ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+R = torch.empty(B, 9, device=dev); t = torch.empty(B, 3, device=dev); sc = torch.empty(B, device=dev)
 st = torch.cuda.current_stream().cuda_stream
-for cg in (0, 2):
-    for mode in (4, 5):
-        def run():
-            rc = L.pem_dev_fine_pass(f1.data_ptr(), f2.data_ptr(), B, N, N, C, 0.1, mode, cg, scratch.data_ptr(), ws.data_ptr(), nb, st)
-            assert rc == 0, rc
-        for _ in range(3): run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10): run()
-        e1.record(); torch.cuda.synchronize()
-        print("cg", cg, "mode", {4: "no epilogue", 5: "TMEM loads only"}[mode], "prep+pass: %.1f us" % (e0.elapsed_time(e1) / 10 * 1e3))
+lib = pkg._lib.lib()
+rc = lib.pem_fine_fused(f1.data_ptr(), f2.data_ptr(), b["dense_pm"].data_ptr(), b["dense_po"].data_ptr(), b["model"].data_ptr(),
+                        B, N, N, C, b["model"].shape[1], 0.1, 0.15, R.data_ptr(), t.data_ptr(), sc.data_ptr(),
+                        None, None, None, None, ws.data_ptr(), nb, st)
+assert rc == 0, rc
+torch.cuda.synchronize()
+for spt in (0,):
+    L.pem_dev_set_fine_steps_per_task(spt)
+    for mode in (1, 2, 3):
+        for flags in (0, 4, 2, 6, 7):
+            def run(prep=0):
+                rc = L.pem_dev_fine_pass(f1.data_ptr(), f2.data_ptr(), B, N, N, C, 0.1, flags, mode, prep, ws.data_ptr(), nb, st)
+                assert rc == 0, rc
+            for _ in range(3): run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): run()
+            e1.record(); torch.cuda.synchronize()
+            names = [n for bit, n in ((1, "noMMA"), (2, "noLoad"), (4, "noEpi")) if flags & bit]
+            print(f"steps/task {spt} mode {mode} {'+'.join(names) or 'full'}: pass {e0.elapsed_time(e1) / 10 * 1e3:.1f} us", flush=True)

@@ -232,6 +232,15 @@ int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const fl
                    pem_stream_t stream);
 
 /*
+ * Profiling hook (no reference counterpart): re-run ONE of the three reducing GEMM passes of
+ * pem_fine_fused (pass 1 softmax statistics, 2 foreground labels, 3 weighted sums) on the
+ * operands and constants a previous pem_fine_fused call with the same shapes left in
+ * `workspace`.  Outputs go to workspace scratch only.  bench.py times the dominant kernel with it.
+ */
+int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
+                        int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream);
+
+/*
  * Weighted Procrustes (MU:343-436) for B' problems of n points each, one CTA per
  * problem: src, ref (B',n,3), weights (B',n) or NULL (ones) -> R (B',9), t (B',3).
  * ref ~ R src + t.

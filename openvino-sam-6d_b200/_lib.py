@@ -46,6 +46,7 @@ SIGNATURES = {
     "pem_feature_similarity_tc": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "pem_fine_fused": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p,
                              c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "pem_fine_fused_pass": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_sz, c_p]),
     "pem_pack_records": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
     "pem_weighted_procrustes": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
 }

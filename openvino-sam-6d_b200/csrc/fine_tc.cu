@@ -1022,3 +1022,15 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     return mode == 3 ? launch_pass<kWsum>(tmA, tmB, p, st)
                      : mode == 2 ? launch_pass<kLabel>(tmA, tmB, p, st) : launch_pass<kStats>(tmA, tmB, p, st);
 }
+
+// One reducing GEMM pass on its own (profiling hook, see pem_b200.h)
+extern "C" int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
+                                   int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(f1);
+    PEM_REQUIRE_PTR(f2);
+    PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0, PEM_E_SHAPE);
+    PEM_REQUIRE(pass >= 1 && pass <= 3, PEM_E_UNSUPPORTED);
+    PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
+                PEM_E_WORKSPACE);
+    return pem_dev_fine_pass(f1, f2, B, N1, N2, C, temp, 0, pass, 0, workspace, workspace_bytes, stream);
+}

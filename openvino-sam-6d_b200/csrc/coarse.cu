@@ -577,9 +577,20 @@ __device__ __forceinline__ void score_items(const float4 *__restrict__ s_model, 
             q2[u] = qx[u] * qx[u] + qy[u] * qy[u] + qz[u] * qz[u];
         }
     }
-#pragma unroll 4
-    for (int m = 0; m < Nm; ++m) {
-        const float4 a = s_model[m];  // (-2mx, -2my, -2mz, |m|^2), broadcast
+    // two model points per trip: 6 FFMA + ONE 3-input minimum (FMNMX3) per query
+    int m = 0;
+#pragma unroll 2
+    for (; m + 1 < Nm; m += 2) {
+        const float4 a = s_model[m], c = s_model[m + 1];  // (-2mx, -2my, -2mz, |m|^2), broadcast
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            const float d0 = fmaf(qx[u], a.x, fmaf(qy[u], a.y, fmaf(qz[u], a.z, a.w)));
+            const float d1 = fmaf(qx[u], c.x, fmaf(qy[u], c.y, fmaf(qz[u], c.z, c.w)));
+            best[u] = fminf(fminf(best[u], d0), d1);
+        }
+    }
+    if (m < Nm) {
+        const float4 a = s_model[m];
 #pragma unroll
         for (int u = 0; u < Q; ++u)
             best[u] = fminf(best[u], fmaf(qx[u], a.x, fmaf(qy[u], a.y, fmaf(qz[u], a.z, a.w))));
@@ -768,6 +779,14 @@ extern "C" int pem_select_smallest(const float *resid, int B, int P1, int P2, in
     return pem_launch_status();
 }
 
+namespace pem {
+int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
+                    const float *pts1, const float *w1, int N1, const float *model, int Nm,
+                    float *scores, cudaStream_t st);  // score_tc.cu
+}
+static int g_score_simt = 0;  // development knob: 1 = always the SIMT kernel
+extern "C" void pem_dev_set_score_simt(int v) { g_score_simt = v; }
+
 extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_t *sel, int B, int P,
                                     int H, const float *pts1, const float *w1, int N1,
                                     const float *model, int Nm, float *scores,
@@ -781,6 +800,10 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     PEM_REQUIRE(B > 0 && P > 0 && H > 0 && N1 > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(sel != nullptr || H <= P, PEM_E_SHAPE);
     PEM_REQUIRE(N1 <= 256, PEM_E_UNSUPPORTED);  // hyps*N1 <= kScQMax*threads in both shapes
+    if (!g_score_simt) {  // tensor-core kernel (score_tc.cu) for every shape it takes
+        const int rc = score_tc_launch(R, t, sel, B, P, H, pts1, w1, N1, model, Nm, scores, pem_cu_stream(stream));
+        if (rc != PEM_E_UNSUPPORTED) return rc;
+    }
     // 8 hypotheses per CTA amortise the model-point staging best; small problems use 4 so the
     // grid still covers every SM several times
     const bool big = (long long)B * ((H + 7) / 8) >= 4LL * PEM_NUM_SMS * 4;

@@ -1,0 +1,291 @@
+// Hypothesis scoring (MU:267-271) on the tensor cores.
+//
+//   score_h = nfg / (sum_i min_m || (p_i - t_h) R_h - m || + 1e-8)      i over the foreground points
+//
+// is a nearest-neighbour search of ~150 transformed points against ~1024 model points for each of
+// B x 300 hypotheses: 7.5e8 point pairs per step.  The squared distance expands to
+// |q|^2 + (|m|^2 - 2 q.m), and the bracket is one row of a GEMM with K = 3 (+1 for |m|^2):
+//
+//   D[row, m] = sum_k A[row, k] * Bm[m, k]        row = (hypothesis, foreground point)
+//
+// computed with tcgen05.mma kind::tf32.  fp32-class accuracy comes from splitting every coordinate
+// into two TF32 values (hi + lo, 22 significant bits) and giving each of the four cross products its
+// own K slots -- 14 of the 16 K values of two K = 8 instructions:
+//
+//   A  row: qh.x qh.y qh.z | qh.x qh.y qh.z | ql.x ql.y ql.z | ql.x ql.y ql.z | 1    1    0 0
+//   Bm row: -2mh.x ..      | -2ml.x ..      | -2mh.x ..      | -2ml.x ..      | s_hi s_lo 0 0     s = |m|^2
+//
+// One persistent CTA per (instance, slice of its hypotheses):
+//   * the model operand (1024 rows x 64 used bytes, SWIZZLE_128B K-major rows) is built once in
+//     shared memory; rows of all hypotheses of the slice are packed back to back into 128-row
+//     tiles, so no tensor work is wasted on padding 151 points to 256;
+//   * warps 2-9 ("row threads", two per TMEM lane = tile row, one per half of the columns)
+//     transform their point, write their half of the A row (generic stores + proxy fence), and
+//     later reduce their lane of the accumulator with 3-input minima straight out of TMEM;
+//   * warp 1 issues M128 x N256 x K8 MMAs: 2 per 256-model-point chunk, accumulator chunks double
+//     buffered in the 512 TMEM columns; A tiles double buffered so tile t+1 is built while tile t
+//     is reduced;
+//   * distances land in shared memory, and each hypothesis is summed in a fixed order.
+// The SIMT kernel (coarse.cu) remains for shapes this one does not take (more than 1024 model points).
+#include "tc_ptx.cuh"
+
+namespace pem {
+namespace tc {
+
+constexpr int kSRows = 128;          // rows per tile = TMEM lanes
+constexpr int kSChunk = 256;         // model points per accumulator buffer
+constexpr int kSMaxNm = 1024;        // model points held in shared memory (128 B per row)
+constexpr int kSMaxN1 = 256;         // query points per instance
+constexpr int kSBatchHyps = 40;      // hypotheses whose distances fit in shared memory at once
+constexpr int kSRowThreads = 256;
+constexpr int kSThreads = 64 + kSRowThreads;
+constexpr uint32_t kSIdesc = make_idesc_tf32(kSRows, kSChunk);
+
+struct ScoreSmem {
+    uint8_t b[kSMaxNm * 128];        // model operand
+    uint8_t a[2][kSRows * 128];      // query tiles
+    float dis[kSBatchHyps * kSMaxN1];
+    float comb[2][kSRows];           // best of column half 1, handed to the half-0 thread of the row
+    float px[kSMaxN1], py[kSMaxN1], pz[kSMaxN1];  // compacted foreground points
+    float Rt[kSBatchHyps][12];       // R (row-major) | t of the hypotheses of the batch
+    int nfg;
+    uint64_t a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void row_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kSRowThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kSThreads, 1)
+score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const int32_t *__restrict__ sel,
+                int P, int H, const float *__restrict__ pts1, const float *__restrict__ w1, int N1,
+                const float *__restrict__ model, int Nm, int cpi, float *__restrict__ scores) {
+    extern __shared__ uint8_t smem_raw[];
+    ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = warp_id(), lane = lane_id(), tid = threadIdx.x;
+    const int b = blockIdx.x / cpi, slice = blockIdx.x - b * cpi;
+    const int hpc = (H + cpi - 1) / cpi;                       // hypotheses per CTA
+    const int h_begin = slice * hpc, h_end = min(H, h_begin + hpc);
+    const int n_chunks = (Nm + kSChunk - 1) / kSChunk;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&sm.a_full[i]), kSRowThreads);
+            mbar_init(smem_u32(&sm.a_empty[i]), 1);
+            mbar_init(smem_u32(&sm.tmem_full[i]), 1);
+            mbar_init(smem_u32(&sm.tmem_empty[i]), kSRowThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&sm.tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- per-CTA setup: foreground points (ordered compaction) and the model operand
+    if (warp == 0) {
+        const float *wb = w1 + (size_t)b * N1, *pb = pts1 + (size_t)b * N1 * 3;
+        int n = 0;
+        for (int base = 0; base < N1; base += 32) {
+            const int i = base + lane;
+            const bool fg = i < N1 && __ldg(wb + i) != 0.f;
+            const unsigned bal = __ballot_sync(kFull, fg);
+            if (fg) {
+                const int o = n + __popc(bal & ((1u << lane) - 1u));
+                sm.px[o] = __ldg(pb + 3 * i);
+                sm.py[o] = __ldg(pb + 3 * i + 1);
+                sm.pz[o] = __ldg(pb + 3 * i + 2);
+            }
+            n += __popc(bal);
+        }
+        if (lane == 0) sm.nfg = n;
+    }
+    {
+        const float *mb = model + (size_t)b * Nm * 3;
+        for (int m = tid; m < n_chunks * kSChunk; m += kSThreads) {
+            float4 c0, c1, c2, c3;
+            if (m < Nm) {
+                const float x = __ldg(mb + 3 * m), y = __ldg(mb + 3 * m + 1), z = __ldg(mb + 3 * m + 2);
+                const float xh = to_tf32(x), yh = to_tf32(y), zh = to_tf32(z);
+                const float xl = to_tf32(x - xh), yl = to_tf32(y - yh), zl = to_tf32(z - zh);
+                const float s = x * x + y * y + z * z, sh = to_tf32(s), sl = to_tf32(s - sh);
+                c0 = make_float4(-2.f * xh, -2.f * yh, -2.f * zh, -2.f * xl);
+                c1 = make_float4(-2.f * yl, -2.f * zl, -2.f * xh, -2.f * yh);
+                c2 = make_float4(-2.f * zh, -2.f * xl, -2.f * yl, -2.f * zl);
+                c3 = make_float4(sh, sl, 0.f, 0.f);
+            } else {  // padding up to a whole chunk: a point that never wins the minimum
+                c0 = c1 = c2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                c3 = make_float4(1e30f, 0.f, 0.f, 0.f);
+            }
+            *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 0)) = c0;
+            *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 1)) = c1;
+            *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 2)) = c2;
+            *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 3)) = c3;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+    const int nfg = sm.nfg;
+
+    // pipeline state shared by the roles (every role walks the same batch / tile sequence)
+    if (nfg > 0 && h_begin < h_end) {
+        if (warp == 1) {
+            // ================================ MMA issuer ==================================
+            const uint64_t b0 = umma_desc_sw128(smem_u32(sm.b));
+            uint32_t tile_seq = 0, chunk_seq = 0;
+            for (int hb = h_begin; hb < h_end; hb += kSBatchHyps) {
+                const int rows = (min(h_end, hb + kSBatchHyps) - hb) * nfg;
+                for (int r0 = 0; r0 < rows; r0 += kSRows, ++tile_seq) {
+                    const int buf = tile_seq & 1;
+                    mbar_wait(smem_u32(&sm.a_full[buf]), (tile_seq >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sm.a[buf]));
+                    for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                        const int cb = chunk_seq & 1;
+                        mbar_wait(smem_u32(&sm.tmem_empty[cb]), ((chunk_seq >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t d = tmem_base + (uint32_t)(cb * kSChunk);
+                            const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
+                            tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
+                            tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
+                            tc_commit(smem_u32(&sm.tmem_full[cb]));
+                            if (c == n_chunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        } else if (warp >= 2) {
+            // ================================ row threads =================================
+            const int quad = warp & 3, half = (warp - 2) >> 2;
+            const int et = quad * 32 + lane;  // tile row = TMEM lane
+            uint32_t tile_seq = 0, chunk_seq = 0;
+            float q2_next = 0.f;
+
+            // transform the point of tile row `et` and write this thread's half of the A row
+            auto build = [&](int rows, int r0, uint32_t seq) {
+                const int buf = seq & 1;
+                mbar_wait(smem_u32(&sm.a_empty[buf]), ((seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
+                const int row = r0 + et;
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                float q2 = 0.f;
+                if (row < rows) {
+                    const int hh = row / nfg, i = row - hh * nfg;
+                    const float *Rm = sm.Rt[hh];
+                    const float v0 = sm.px[i] - Rm[9], v1 = sm.py[i] - Rm[10], v2 = sm.pz[i] - Rm[11];
+                    // (p1 - t) @ R : row vector times R (MU:267)
+                    const float qx = v0 * Rm[0] + v1 * Rm[3] + v2 * Rm[6];
+                    const float qy = v0 * Rm[1] + v1 * Rm[4] + v2 * Rm[7];
+                    const float qz = v0 * Rm[2] + v1 * Rm[5] + v2 * Rm[8];
+                    q2 = qx * qx + qy * qy + qz * qz;
+                    const float xh = to_tf32(qx), yh = to_tf32(qy), zh = to_tf32(qz);
+                    const float xl = to_tf32(qx - xh), yl = to_tf32(qy - yh), zl = to_tf32(qz - zh);
+                    if (half == 0) {
+                        c0 = make_float4(xh, yh, zh, xh);
+                        c1 = make_float4(yh, zh, xl, yl);
+                    } else {
+                        c0 = make_float4(zl, xl, yl, zl);
+                        c1 = make_float4(1.f, 1.f, 0.f, 0.f);
+                    }
+                }
+                *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half)) = c0;
+                *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half + 1)) = c1;
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(&sm.a_full[buf]));
+                return q2;
+            };
+
+            for (int hb = h_begin; hb < h_end; hb += kSBatchHyps) {
+                const int nb = min(h_end, hb + kSBatchHyps) - hb, rows = nb * nfg;
+                for (int k = tid - 64; k < nb * 12; k += kSRowThreads) {  // stage R | t of the batch
+                    const int hh = k / 12, e = k - hh * 12, h = hb + hh;
+                    const size_t src = (size_t)b * P + (sel ? __ldg(sel + (size_t)b * H + h) : h);
+                    sm.Rt[hh][e] = e < 9 ? __ldg(R + src * 9 + e) : __ldg(t + src * 3 + (e - 9));
+                }
+                row_barrier();
+                q2_next = build(rows, 0, tile_seq);
+                for (int r0 = 0; r0 < rows; r0 += kSRows, ++tile_seq) {
+                    const float q2 = q2_next;
+                    if (r0 + kSRows < rows) q2_next = build(rows, r0 + kSRows, tile_seq + 1);
+                    // reduce this thread's lane over its half of every chunk
+                    float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+                    for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                        const int cb = chunk_seq & 1;
+                        mbar_wait(smem_u32(&sm.tmem_full[cb]), (chunk_seq >> 1) & 1);
+                        tc_fence_after();
+                        {
+                            float v[kSChunk / 2];
+                            tmem_ld128(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                           (uint32_t)(cb * kSChunk + half * (kSChunk / 2)), v);
+#pragma unroll
+                            for (int q = 0; q < kSChunk / 2; q += 8) {
+                                m0 = fminf(fminf(m0, v[q]), v[q + 1]);
+                                m1 = fminf(fminf(m1, v[q + 2]), v[q + 3]);
+                                m2 = fminf(fminf(m2, v[q + 4]), v[q + 5]);
+                                m3 = fminf(fminf(m3, v[q + 6]), v[q + 7]);
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[cb]));
+                    }
+                    const float best = fminf(fminf(m0, m1), fminf(m2, m3));
+                    const int par = tile_seq & 1;
+                    if (half == 1) sm.comb[par][et] = best;
+                    row_barrier();
+                    if (half == 0 && r0 + et < rows)
+                        sm.dis[r0 + et] = sqrtf(fmaxf(q2 + fminf(best, sm.comb[par][et]), 0.f));  // clamp, then sqrt
+                }
+                // deterministic per-hypothesis sums: one warp per hypothesis, fixed order
+                row_barrier();
+                for (int hh = warp - 2; hh < nb; hh += kSRowThreads / 32) {
+                    float s = 0.f;
+                    for (int i = lane; i < nfg; i += 32) s += sm.dis[hh * nfg + i];
+                    s = warp_sum(s);
+                    if (lane == 0) scores[(size_t)b * H + hb + hh] = __fdiv_rn((float)nfg, s + 1e-8f);  // MU:271
+                }
+                row_barrier();  // dis is rewritten by the next batch
+            }
+        }
+    } else if (warp >= 2) {
+        // no foreground point: sum = 0 -> score = 0 / 1e-8 = 0 (MU:271)
+        for (int h = h_begin + (tid - 64); h < h_end; h += kSRowThreads) scores[(size_t)b * H + h] = 0.f;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                     : "memory");
+    }
+}
+
+}  // namespace tc
+
+// returns PEM_E_UNSUPPORTED for shapes the tensor-core kernel does not take (the caller falls back
+// to the SIMT kernel)
+int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
+                    const float *pts1, const float *w1, int N1, const float *model, int Nm,
+                    float *scores, cudaStream_t st) {
+    using namespace tc;
+    if (Nm > kSMaxNm || N1 > kSMaxN1) return PEM_E_UNSUPPORTED;
+    int dev = 0, sms = PEM_NUM_SMS;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int cpi = max(1, min(sms / B, (H + 7) / 8));  // CTAs per instance
+    const size_t smem = sizeof(ScoreSmem) + 1024;
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(score_tc_kernel, smem, &cached)) return rc;
+    score_tc_kernel<<<B * cpi, kSThreads, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
+    return pem_launch_status();
+}
+
+}  // namespace pem

@@ -125,6 +125,40 @@ def test_score_hypotheses_S4(pkg, oracle, dev):
     assert ((got2 - want2).abs() / want2.abs().clamp_min(1e-6)).max().item() < 1e-4
 
 
+@pytest.mark.parametrize("Nm,H,n1,nfg", [(1024, 300, 196, 150), (1000, 37, 196, 196), (300, 5, 50, 1),
+                                           (1024, 1, 200, 0), (513, 410, 256, 131), (2048, 64, 196, 100)])
+def test_score_hypotheses_tensor_core_vs_simt_and_oracle(pkg, oracle, dev, Nm, H, n1, nfg):
+    """The tcgen05 (split-tf32) scoring kernel against the SIMT kernel and the oracle: ragged model
+    sizes, hypothesis counts that do not divide over the CTAs, several batches per CTA, no / one /
+    all foreground points.  (Nm = 2048 is outside the tensor-core kernel: both calls take the SIMT path.)"""
+    import ctypes
+    g = torch.Generator().manual_seed(Nm + H)
+    Bn = 3
+    q, _ = torch.linalg.qr(torch.randn(Bn, H, 3, 3, generator=g))
+    R = q.contiguous()
+    t = (0.1 * torch.randn(Bn, H, 3, generator=g)).contiguous()
+    pts = (0.4 * torch.randn(Bn, n1, 3, generator=g)).contiguous()
+    model = (0.4 * torch.randn(Bn, Nm, 3, generator=g)).contiguous()
+    w1 = torch.zeros(Bn, n1)
+    for b in range(Bn):
+        w1[b, torch.randperm(n1, generator=g)[:nfg]] = 1.0
+    want = oracle.score_hypotheses(R, t, pts, w1, model)
+    L = ctypes.CDLL(pkg._lib.LIB_PATH)
+    args = (R.to(dev), t.to(dev), pts.to(dev), w1.to(dev), model.to(dev))
+    L.pem_dev_set_score_simt(1)
+    simt = pkg.model_utils.score_hypotheses(*args).cpu()
+    L.pem_dev_set_score_simt(0)
+    tc = pkg.model_utils.score_hypotheses(*args).cpu()
+    if nfg == 0:
+        assert (tc == 0).all() and (simt == 0).all()
+        return
+    rel = lambda a, b: ((a - b).abs() / b.abs().clamp_min(1e-6)).max().item()
+    assert rel(simt, want) < 1e-4
+    assert rel(tc, want) < 1e-4
+    assert rel(tc, simt) < 2e-5
+    assert torch.equal(tc.argmax(1), simt.argmax(1)) or rel(tc.max(1)[0], simt.max(1)[0]) < 1e-6
+
+
 def test_coarse_end_to_end_S5(pkg, oracle, dev):
     """From atten to the coarse pose.
 

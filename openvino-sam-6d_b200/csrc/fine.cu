@@ -232,9 +232,11 @@ fine_wsum_kernel(const float *__restrict__ atten, int R, int Cn, const float *__
 __global__ void __launch_bounds__(256)
 weighted_procrustes_kernel(const float *__restrict__ src, const float *__restrict__ ref,
                            const float *__restrict__ weights, int n, float thresh, float eps,
-                           float *__restrict__ Rout, float *__restrict__ tout) {
+                           float *__restrict__ Rout, float *__restrict__ tout,
+                           int *__restrict__ zero3 /* (B,3) scratch to clear, or null */) {
     __shared__ double s_red[32];
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (zero3 && tid < 3) zero3[3 * b + tid] = 0;
     const float *S = src + (size_t)b * n * 3, *Rf = ref + (size_t)b * n * 3;
     const float *W = weights ? weights + (size_t)b * n : nullptr;
     auto wt = [&](int i) {
@@ -383,9 +385,8 @@ static FineWs fine_carve(void *base, int B, int N1, int N2) {
 int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA, const float *w1,
                      const float *model, int B, int N1, int Nm, float dis_thres, int *counters,
                      float *R, float *t, float *score, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)B * 3 * sizeof(int), st);
-    if (e != cudaSuccess) return (int)e;
-    weighted_procrustes_kernel<<<B, 256, 0, st>>>(pred, pts1, rowsumA, N1, 0.0f, 1e-5f, R, t);
+    // (the Procrustes kernel also zeroes the pose-score counters of its instance)
+    weighted_procrustes_kernel<<<B, 256, 0, st>>>(pred, pts1, rowsumA, N1, 0.0f, 1e-5f, R, t, counters);
     const size_t smem = (size_t)Nm * sizeof(float4);
     static size_t cached = 40 * 1024;
     if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
@@ -412,7 +413,7 @@ extern "C" int pem_weighted_procrustes(const float *src, const float *ref, const
     PEM_REQUIRE_PTR(t);
     PEM_REQUIRE(Bp > 0 && n > 0, PEM_E_SHAPE);
     weighted_procrustes_kernel<<<Bp, 256, 0, pem_cu_stream(stream)>>>(src, ref, weights, n,
-                                                                      weight_thresh, eps, R, t);
+                                                                      weight_thresh, eps, R, t, nullptr);
     return pem_launch_status();
 }
 

@@ -394,19 +394,22 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------- prep / finish
-// One warp per padded row of the GEMM operands: x / max(|x|,1e-12) split into bf16 hi and lo.
-// The first `skip` rows of every instance (the background token) stay out of the operands; with
-// skip = 1 the warp also leaves the fp32 cosine of its row with the OTHER set's background
+// One warp per PAIR of padded rows of the GEMM operands: x / max(|x|,1e-12) split into bf16 hi and
+// lo.  The first `skip` rows of every instance (the background token) stay out of the operands; with
+// skip = 1 the warp also leaves the fp32 cosine of its rows with the OTHER set's background
 // token, i.e. the background column (bg_a) / row (bg_b) of the similarity matrix, and their
-// corner s00.  C <= 256 and C % 64 == 0: a lane holds C/32 values of the row in registers
-// (float2 loads, bf16x2 stores: every access of the warp is one contiguous 256 / 128 byte run).
-__global__ void __launch_bounds__(256)
+// corner s00.  C <= 256 and C % 64 == 0: a lane holds C/32 values of each row in registers
+// (float2 loads, bf16x2 stores: every access of the warp is one contiguous 256 / 128 byte run;
+// both rows' loads are in flight together).  rows_pa and rows_pb are even.
+constexpr int kPrepRows = 2;
+template <int NIT>  // C / 64: float2 per lane and row
+__global__ void __launch_bounds__(256, 4)
 tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloat16 *__restrict__ outa,
                const float *__restrict__ fb, int rows_b, int rows_pb, __nv_bfloat16 *__restrict__ outb,
                int B, int C, int normalize, int skip, float *__restrict__ bg_a /* (B,rows_pa) */,
                float *__restrict__ bg_b /* (B,rows_pb) */, float *__restrict__ s00 /* (B) */) {
-    // both operands in one launch: warps [0, B*rows_pa) prepare A', the rest prepare B'
-    int gr = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    // both operands in one launch: warps [0, B*rows_pa/2) prepare A', the rest prepare B'
+    int gr = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * kPrepRows;
     const bool second = gr >= B * rows_pa;
     if (second) gr -= B * rows_pa;
     const float *f = second ? fb : fa, *fo = second ? fa : fb;
@@ -414,58 +417,70 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
     const int rows_o = second ? rows_a : rows_b;
     __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
     if (gr >= B * rows_p) return;
-    const int b = gr / rows_p, i = gr - b * rows_p, lane = lane_id();
-    const int nit = C >> 6;  // float2 per lane
-    __nv_bfloat162 *hi = reinterpret_cast<__nv_bfloat162 *>(out + (size_t)gr * C),
-                   *lo = reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)B * rows_p + gr) * C);
+    const int b = gr / rows_p, i0 = gr - b * rows_p, lane = lane_id();  // rows i0, i0+1 of instance b
+    constexpr int nit = NIT;
     float *bg = second ? bg_b : bg_a;
-    if (i >= rows) {
-        for (int it = 0; it < nit; ++it) {
-            hi[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
-            lo[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
-        }
-        if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
-        return;
-    }
-    // a row as kMaxKC float2 per lane, and 1 / max(|row|, 1e-12) (1 when not normalising)
-    auto load_row = [&](const float *row, float2 (&x)[kMaxKC]) {
+    // a row as kMaxKC float2 per lane; sum of squares (unreduced)
+    auto load_row = [&](const float *row, float2 (&x)[NIT]) {
         float s = 0.f;
 #pragma unroll
-        for (int it = 0; it < kMaxKC; ++it) {
-            x[it] = it < nit ? __ldg(reinterpret_cast<const float2 *>(row) + it * 32 + lane) : make_float2(0.f, 0.f);
+        for (int it = 0; it < NIT; ++it) {
+            x[it] = __ldg(reinterpret_cast<const float2 *>(row) + it * 32 + lane);
             s = fmaf(x[it].x, x[it].x, s);
             s = fmaf(x[it].y, x[it].y, s);
         }
-        return normalize ? fmaxf(sqrtf(warp_sum(s)), 1e-12f) : 1.f;
+        return s;
     };
-    float2 x[kMaxKC], tk[kMaxKC];
-    const float inv = load_row(f + ((size_t)b * (rows + skip) + skip + i) * C, x);
-    float dot = 0.f;
+    auto inv_of = [&](float ss) { return normalize ? fmaxf(sqrtf(warp_sum(ss)), 1e-12f) : 1.f; };
+    float2 x[kPrepRows][NIT], tk[NIT];
+    float ss[kPrepRows];
+#pragma unroll
+    for (int r = 0; r < kPrepRows; ++r) {
+        ss[r] = 0.f;
+        if (i0 + r < rows) ss[r] = load_row(f + ((size_t)b * (rows + skip) + skip + i0 + r) * C, x[r]);
+    }
     const float *tok = fo + (size_t)b * (rows_o + skip) * C;  // the other set's background token
     float inv_tok = 1.f;
-    if (skip) inv_tok = load_row(tok, tk);
+    if (skip) inv_tok = inv_of(load_row(tok, tk));
 #pragma unroll
-    for (int it = 0; it < kMaxKC; ++it) {
-        if (it >= nit) break;
-        float2 v = x[it];
-        if (normalize) { v.x = __fdiv_rn(v.x, inv); v.y = __fdiv_rn(v.y, inv); }
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-        const float2 hf = __bfloat1622float2(h);
-        hi[it * 32 + lane] = h;
-        lo[it * 32 + lane] = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
-        if (skip) { dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot); }
-    }
-    if (!skip) return;
-    dot = __fdiv_rn(warp_sum(dot), inv_tok);
-    if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
-    if (!second && i == 0) {  // the corner: background token x background token
-        float2 own[kMaxKC];
-        const float inv_own = load_row(f + (size_t)b * (rows + skip) * C, own);
-        float d0 = 0.f;
+    for (int r = 0; r < kPrepRows; ++r) {
+        const int i = i0 + r;
+        __nv_bfloat162 *hi = reinterpret_cast<__nv_bfloat162 *>(out + (size_t)(gr + r) * C),
+                       *lo = reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)B * rows_p + gr + r) * C);
+        if (i >= rows) {  // padding rows
+            for (int it = 0; it < nit; ++it) {
+                hi[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
+                lo[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
+            }
+            if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
+            continue;
+        }
+        // x * (1/norm) instead of the reference's x / norm: at most 1 ulp apart, far below the
+        // 2^-17 of the hi/lo split that follows, and 8 IEEE divisions per lane cheaper
+        const float rinv = 1.0f / inv_of(ss[r]);
+        float dot = 0.f;
 #pragma unroll
-        for (int it = 0; it < kMaxKC; ++it) { d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0); }
-        d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
-        if (lane == 0) s00[b] = d0;
+        for (int it = 0; it < NIT; ++it) {
+            float2 v = x[r][it];
+            if (normalize) { v.x *= rinv; v.y *= rinv; }
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+            const float2 hf = __bfloat1622float2(h);
+            hi[it * 32 + lane] = h;
+            lo[it * 32 + lane] = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+            if (skip) { dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot); }
+        }
+        if (!skip) continue;
+        dot = __fdiv_rn(warp_sum(dot), inv_tok);
+        if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
+        if (!second && i == 0) {  // the corner: background token x background token
+            float2 own[NIT];
+            const float inv_own = inv_of(load_row(f + (size_t)b * (rows + skip) * C, own));
+            float d0 = 0.f;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) { d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0); }
+            d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
+            if (lane == 0) s00[b] = d0;
+        }
     }
 }
 
@@ -689,6 +704,22 @@ static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp
     return PEM_OK;
 }
 
+// normalise + split both operands (and the background dots when skip = 1)
+static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const float *f1, __nv_bfloat16 *A,
+                        const float *f2, __nv_bfloat16 *Bm, int normalize, int skip, float *bg_a, float *bg_b,
+                        float *s00) {
+    const int grid = (B * (p.Mp + p.Np) / kPrepRows + 7) / 8;
+    auto go = [&](auto kern) {
+        kern<<<grid, 256, 0, st>>>(f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip, bg_a, bg_b, s00);
+    };
+    switch (C >> 6) {
+        case 1: go(tc_prep_kernel<1>); break;
+        case 2: go(tc_prep_kernel<2>); break;
+        case 3: go(tc_prep_kernel<3>); break;
+        default: go(tc_prep_kernel<4>); break;
+    }
+}
+
 template <int MODE>
 static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
     static_assert(kEpiThreads == TN, "one epilogue thread per strip column");
@@ -737,8 +768,7 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
                 PEM_E_WORKSPACE);
     cudaStream_t st = pem_cu_stream(stream);
     Ws w = carve(workspace, B, N1p, N2p, C);
-    tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
-                                                                 C, normalize, 0, nullptr, nullptr, nullptr);
+    launch_prep(p, B, C, st, f1, w.A, f2, w.Bm, normalize, 0, nullptr, nullptr, nullptr);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
@@ -772,8 +802,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     float *rsA = rowsum_out ? rowsum_out : w.rowsumA;
     float *pred = pred_out ? pred_out : w.pred;
 
-    tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm, B,
-                                                                 C, 1, 1, w.bg_a, w.bg_b, w.s00);
+    launch_prep(p, B, C, st, f1, w.A, f2, w.Bm, 1, 1, w.bg_a, w.bg_b, w.s00);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
@@ -817,8 +846,7 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     Ws w = carve(workspace, B, N1, N2, C);
     if (workspace_bytes < w.bytes) return PEM_E_WORKSPACE;
     if (prep)
-        tc_prep_kernel<<<(B * (p.Mp + p.Np) + 7) / 8, 256, 0, st>>>(f1, p.R, p.Mp, w.A, f2, p.Cn, p.Np, w.Bm,
-                                                                     B, C, 1, 1, w.bg_a, w.bg_b, w.s00);
+        launch_prep(p, B, C, st, f1, w.A, f2, w.Bm, 1, 1, w.bg_a, w.bg_b, w.s00);
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;

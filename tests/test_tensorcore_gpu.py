@@ -34,3 +34,36 @@ def test_fine_fused(pkg, oracle, dev, ids, n_dense, feat_dim):
     assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1   # north_star: <= 0.1 deg
     assert (t.cpu() - ot).abs().max().item() < 1e-4                    # <= 0.1 mm at 1 m radius
     assert (s.cpu() - os_).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("B,N1,N2,C,spt", [(2, 700, 300, 128, 0), (1, 1300, 1537, 64, 0), (3, 256, 257, 256, 1),
+                                           (1, 1300, 600, 192, 4), (2, 1, 5, 64, 0)])
+def test_fine_fused_ragged_shapes_and_task_splits(pkg, oracle, dev, B, N1, N2, C, spt):
+    """N1 != N2, sizes that are not multiples of the 256-wide tiles, every row-steps-per-task
+    setting (0 = the host's choice): correlated random features so that the assignment is not flat."""
+    import ctypes
+    g = torch.Generator().manual_seed(N1 * 7 + N2)
+    base = torch.randn(B, max(N1, N2) + 1, C, generator=g)
+    f1 = (base[:, : N1 + 1] + 0.3 * torch.randn(B, N1 + 1, C, generator=g)).contiguous()
+    f2 = (base[:, : N2 + 1] + 0.3 * torch.randn(B, N2 + 1, C, generator=g)).contiguous()
+    p1 = (0.3 * torch.randn(B, N1, 3, generator=g)).contiguous()
+    p2 = (0.3 * torch.randn(B, N2, 3, generator=g)).contiguous()
+    model = (0.3 * torch.randn(B, 500, 3, generator=g)).contiguous()
+    atten = oracle.feature_similarity(f1, f2, 0.1)
+    oR, ot, os_, ost = oracle.fine_Rt(atten, p1, p2, model)
+    L = ctypes.CDLL(pkg._lib.LIB_PATH)
+    L.pem_dev_set_fine_steps_per_task(spt)
+    try:
+        R, t, s, st = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), p1.to(dev), p2.to(dev),
+                                                            model.to(dev), 0.1, 0.15, return_stages=True)
+    finally:
+        L.pem_dev_set_fine_steps_per_task(0)
+    for k in ("w1", "w2"):
+        bad = (st[k].cpu() != ost[k]).float().sum().item()
+        assert bad <= max(1.0, 2e-3 * ost[k].numel()), (k, bad)
+    assert (st["row"].cpu() - ost["row"]).abs().max().item() < 1e-4
+    if min(N1, N2) >= 256:  # a well-conditioned Procrustes problem
+        assert (st["pred"].cpu() - ost["pred"]).abs().max().item() < 1e-3
+        assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1
+        assert (t.cpu() - ot).abs().max().item() < 1e-4
+        assert (s.cpu() - os_).abs().max().item() < 2e-3

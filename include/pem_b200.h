@@ -125,6 +125,33 @@ int pem_query_and_group(const float *xyz, const float *new_xyz, const float *fea
 int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, float radius1, int nsample1,
                   float *out1, float radius2, int nsample2, float *out2, pem_stream_t stream);
 
+/*
+ * Tensor-core pre-filter for pem_pe_group2.  The exact ball query pays ~13 instructions for each
+ * of the N^2 (centre, point) pairs although only a few per cent lie near the ball, and for the
+ * cloud that fine_point_matching.py:113-137 groups AFTER applying the coarse pose that scan sits on
+ * the critical path behind the whole coarse stage.
+ *   pem_pe_masks          one bit per pair (B,N,ceil(N/32)) uint32: set when the point MAY lie within
+ *                         `radius` of the centre -- a split-TF32 tcgen05 GEMM of |p|^2 - 2 c.p with a
+ *                         slack that covers its own rounding plus rel_margin * radius^2.  Ball
+ *                         membership survives a rigid motion up to rounding, so the masks can be
+ *                         computed on the cloud BEFORE it is moved (any time, e.g. a side stream).
+ *   pem_pe_group2_masked  pem_pe_group2 on the (moved) cloud visiting only the set bits, each with
+ *                         the reference's exact arithmetic (ball_query.cpp:44-61): bit-identical to
+ *                         pem_pe_group2 provided the masks were made with radius >= max(radius1,
+ *                         radius2) and the motion changes no squared distance by more than
+ *                         rel_margin * radius^2 (1e-3 leaves two orders of magnitude over the fp32
+ *                         rounding of an orthonormal R).
+ * max_ctas > 0 caps the filter's grid (it takes a whole SM per CTA) so that it can share the GPU
+ * with a concurrent latency-critical kernel instead of queueing behind it; 0 = one CTA per SM.
+ * N <= 4096.
+ */
+size_t pem_pe_masks_bytes(int B, int N);
+int pem_pe_masks(const float *xyz, int B, int N, float centre_eps, float radius, float rel_margin,
+                 int max_ctas, void *masks, size_t masks_bytes, pem_stream_t stream);
+int pem_pe_group2_masked(const float *xyz, int B, int N, float centre_eps, float radius1,
+                         int nsample1, float *out1, float radius2, int nsample2, float *out2,
+                         const void *masks, size_t masks_bytes, pem_stream_t stream);
+
 /* ---------------------------------------------------------------- similarity */
 
 /*

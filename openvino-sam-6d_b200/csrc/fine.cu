@@ -294,7 +294,11 @@ weighted_procrustes_kernel(const float *__restrict__ src, const float *__restric
 }
 
 // pose score (MU:334-339) ---------------------------------------------------------------
-constexpr int kPsThreads = 128;
+// CTA = 256 points x 4 quarters of the model, 512 threads: thread (lane point pair, quarter) scans
+// its quarter for two points (one LDS.128 per 8 FP ops), the four partial minima meet in shared
+// memory.  2048 points x 16 instances = 128 CTAs: one per SM, 4 warps per scheduler.
+constexpr int kPsLanes = 128, kPsQ = 2, kPsPoints = kPsLanes * kPsQ, kPsParts = 4;
+constexpr int kPsThreads = kPsLanes * kPsParts;
 
 __global__ void __launch_bounds__(kPsThreads)
 fine_pose_score_kernel(const float *__restrict__ pts1, const float *__restrict__ w1,
@@ -303,35 +307,60 @@ fine_pose_score_kernel(const float *__restrict__ pts1, const float *__restrict__
                        int *__restrict__ counters /* (B,3): hits, fg, ticket */,
                        float *__restrict__ score) {
     extern __shared__ float4 s_model[];
-    __shared__ int s_h[4], s_f[4];
-    const int b = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * kPsThreads + tid;
+    __shared__ float s_best[kPsParts][kPsPoints];
+    __shared__ int s_h[kPsLanes / 32], s_f[kPsLanes / 32];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int pt = tid & (kPsLanes - 1), part = tid / kPsLanes;  // part is warp-uniform
     const float *mb = model + (size_t)b * Nm * 3;
     for (int m = tid; m < Nm; m += kPsThreads) {
         const float x = __ldg(mb + 3 * m), y = __ldg(mb + 3 * m + 1), z = __ldg(mb + 3 * m + 2);
         s_model[m] = make_float4(-2.f * x, -2.f * y, -2.f * z, x * x + y * y + z * z);
     }
-    __syncthreads();
-    int hit = 0, fg = 0;
-    if (i < N1) {
-        fg = w1[(size_t)b * N1 + i] != 0.f;
-        const float *R9 = Rm + (size_t)b * 9, *t3 = tv + (size_t)b * 3;
-        const float *p = pts1 + ((size_t)b * N1 + i) * 3;
-        const float v0 = __ldg(p) - t3[0], v1 = __ldg(p + 1) - t3[1], v2 = __ldg(p + 2) - t3[2];
-        const float qx = v0 * R9[0] + v1 * R9[3] + v2 * R9[6];
-        const float qy = v0 * R9[1] + v1 * R9[4] + v2 * R9[7];
-        const float qz = v0 * R9[2] + v1 * R9[5] + v2 * R9[8];
-        const float q2 = qx * qx + qy * qy + qz * qz;
-        float best = INFINITY;
-#pragma unroll 4
-        for (int m = 0; m < Nm; ++m) {
-            const float4 a = s_model[m];
-            best = fminf(best, fmaf(qx, a.x, fmaf(qy, a.y, fmaf(qz, a.z, a.w))));
+    float qx[kPsQ], qy[kPsQ], qz[kPsQ], q2[kPsQ], best[kPsQ];
+    const float *R9 = Rm + (size_t)b * 9, *t3 = tv + (size_t)b * 3;
+#pragma unroll
+    for (int u = 0; u < kPsQ; ++u) {
+        const int i = blockIdx.x * kPsPoints + u * kPsLanes + pt;
+        qx[u] = qy[u] = qz[u] = q2[u] = 0.f;
+        best[u] = INFINITY;
+        if (i < N1) {
+            const float *p = pts1 + ((size_t)b * N1 + i) * 3;
+            const float v0 = __ldg(p) - t3[0], v1 = __ldg(p + 1) - t3[1], v2 = __ldg(p + 2) - t3[2];
+            qx[u] = v0 * R9[0] + v1 * R9[3] + v2 * R9[6];
+            qy[u] = v0 * R9[1] + v1 * R9[4] + v2 * R9[7];
+            qz[u] = v0 * R9[2] + v1 * R9[5] + v2 * R9[8];
+            q2[u] = qx[u] * qx[u] + qy[u] * qy[u] + qz[u] * qz[u];
         }
-        const float dis = sqrtf(fmaxf(q2 + best, 0.f));
-        hit = fg && (dis < dis_thres);
     }
-    const unsigned hb = __ballot_sync(kFull, hit), fb = __ballot_sync(kFull, fg);
-    if (lane_id() == 0) { s_h[warp_id()] = __popc(hb); s_f[warp_id()] = __popc(fb); }
+    __syncthreads();
+    const int per = (Nm + kPsParts - 1) / kPsParts, m0 = part * per, m1 = min(Nm, m0 + per);
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m) {
+        const float4 a = s_model[m];
+#pragma unroll
+        for (int u = 0; u < kPsQ; ++u)
+            best[u] = fminf(best[u], fmaf(qx[u], a.x, fmaf(qy[u], a.y, fmaf(qz[u], a.z, a.w))));
+    }
+#pragma unroll
+    for (int u = 0; u < kPsQ; ++u) s_best[part][u * kPsLanes + pt] = best[u];
+    __syncthreads();
+    if (part == 0) {  // warps 0..3
+        int hits = 0, fgs = 0;
+#pragma unroll
+        for (int u = 0; u < kPsQ; ++u) {
+            const int l = u * kPsLanes + pt, i = blockIdx.x * kPsPoints + l;
+            int hit = 0, fg = 0;
+            if (i < N1) {
+                const float bm = fminf(fminf(s_best[0][l], s_best[1][l]), fminf(s_best[2][l], s_best[3][l]));
+                fg = w1[(size_t)b * N1 + i] != 0.f;
+                const float dis = sqrtf(fmaxf(q2[u] + bm, 0.f));
+                hit = fg && (dis < dis_thres);
+            }
+            hits += __popc(__ballot_sync(kFull, hit));
+            fgs += __popc(__ballot_sync(kFull, fg));
+        }
+        if (lane_id() == 0) { s_h[warp_id()] = hits; s_f[warp_id()] = fgs; }
+    }
     __syncthreads();
     if (tid == 0) {
         int *c = counters + 3 * b;
@@ -390,7 +419,7 @@ int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA,
     const size_t smem = (size_t)Nm * sizeof(float4);
     static size_t cached = 40 * 1024;
     if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
-    fine_pose_score_kernel<<<dim3((N1 + kPsThreads - 1) / kPsThreads, B), kPsThreads, smem, st>>>(
+    fine_pose_score_kernel<<<dim3((N1 + kPsPoints - 1) / kPsPoints, B), kPsThreads, smem, st>>>(
         pts1, w1, R, t, model, N1, Nm, dis_thres, counters, score);
     return pem_launch_status();
 }

@@ -501,10 +501,21 @@ tc_store_bg_kernel(const float *__restrict__ bg_a, const float *__restrict__ bg_
 __global__ void __launch_bounds__(256)
 tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restrict__ colpart,
                        const float *__restrict__ bg_a, const float *__restrict__ bg_b, int R, int Cn,
-                       int Mp, int Np, int n_part, int planes, float c1, float c2,
-                       float *__restrict__ inv_rowsum, float *__restrict__ lrs,
-                       float *__restrict__ inv_colsum, float *__restrict__ lcs) {
+                       const float *__restrict__ s00, int Mp, int Np, int n_part, int planes, float c1,
+                       float c2, float *__restrict__ inv_rowsum, float *__restrict__ lrs,
+                       float *__restrict__ inv_colsum, float *__restrict__ lcs,
+                       float *__restrict__ lbg /* (B,2): log2 of the background row / column sums */) {
+    __shared__ float red[32];
     const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == gridDim.x - 1) {  // one block per instance: sums of the background row and column
+        float sr = 0.f, sc = 0.f;
+        for (int j = threadIdx.x; j < Cn; j += blockDim.x) sr += ex2(fmaf(bg_b[(size_t)b * Np + j], c1, -c2));
+        for (int i = threadIdx.x; i < R; i += blockDim.x) sc += ex2(fmaf(bg_a[(size_t)b * Mp + i], c1, -c2));
+        const float e00 = ex2(fmaf(s00[b], c1, -c2));
+        sr = block_sum(sr, red);
+        sc = block_sum(sc, red);
+        if (threadIdx.x == 0) { lbg[2 * b] = log2f(sr + e00); lbg[2 * b + 1] = log2f(sc + e00); }
+    }
     if (k < Mp) {
         float s = 0.f;
         if (k < R) {
@@ -529,22 +540,16 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
 
 // after pass 2: w1_i, w2_j and the per-column constants of pass 3.  A point is foreground when its
 // best match beats the background entry (MU:321-322); the background row / column sums are reduced
-// here from the 2 x 2049 exact cosines of the prep kernel.
+// by tc_finish_stats_kernel from the 2 x 2049 exact cosines of the prep kernel.
 __global__ void __launch_bounds__(256)
 tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__restrict__ colpart,
                        const float *__restrict__ bg_a, const float *__restrict__ bg_b,
-                       const float *__restrict__ s00, const float *__restrict__ inv_colsum,
+                       const float *__restrict__ lbg, const float *__restrict__ inv_colsum,
                        const float *__restrict__ pts2, int R, int Cn, int Mp, int Np, int n_part,
                        int planes, float c1, float c2, float *__restrict__ w1 /* (B,R) */,
                        float *__restrict__ w2_out /* (B,Cn) or null */, float4 *__restrict__ G) {
-    __shared__ float red[32];
     const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
-    float sr = 0.f, sc = 0.f;  // background row sum (over columns), background column sum (over rows)
-    for (int j = threadIdx.x; j < Cn; j += blockDim.x) sr += ex2(fmaf(bg_b[(size_t)b * Np + j], c1, -c2));
-    for (int i = threadIdx.x; i < R; i += blockDim.x) sc += ex2(fmaf(bg_a[(size_t)b * Mp + i], c1, -c2));
-    const float e00 = ex2(fmaf(s00[b], c1, -c2));
-    const float lrs0 = log2f(block_sum(sr, red) + e00), lcs0 = log2f(block_sum(sc, red) + e00);
-    const float c2x = 2.0f * c1;
+    const float lrs0 = lbg[2 * b], lcs0 = lbg[2 * b + 1], c2x = 2.0f * c1;
     if (k < R) {
         float m = -INFINITY;
         for (int t = 0; t < n_part; ++t) m = fmaxf(m, rowmaxpart[((size_t)b * n_part + t) * Mp + k]);
@@ -625,6 +630,7 @@ struct Ws {
     float *rowpart;  // (B, 2*n_strips, 4, Mp): the largest of the per-pass row partial layouts
     float *colpart;  // (2*n_msteps, B, Np): column partial planes (sums, then maxima)
     float *bg_a, *bg_b, *s00;  // background column / row of the cosine matrix and their corner
+    float *lbg;                // (B,2) log2 of the background row / column sums
     float *inv_rowsum, *lrs, *inv_colsum, *lcs, *w1, *w2, *rowsumA, *pred;
     float4 *G;
     int *counters;
@@ -650,6 +656,7 @@ static Ws carve(void *base, int B, int rows1, int rows2, int C) {
     w.bg_a = (float *)take(B * Mp * 4);
     w.bg_b = (float *)take(B * Np * 4);
     w.s00 = (float *)take(B * 4);
+    w.lbg = (float *)take(B * 8);
     w.inv_rowsum = (float *)take(B * Mp * 4);
     w.lrs = (float *)take(B * Mp * 4);
     w.inv_colsum = (float *)take(B * Np * 4);
@@ -814,15 +821,15 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     p.colpart = w.colpart;
     if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
     tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-        w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
-        w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs);
+        w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, w.s00, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
+        w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs, w.lbg);
     // pass 2: foreground labels
     p.lrs = w.lrs;
     p.lcs = w.lcs;
     p.rowmaxpart = w.rowpart;
     if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
     tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-        w.rowpart, w.colpart, w.bg_a, w.bg_b, w.s00, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
+        w.rowpart, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
         planes, p.c1, p.c2, w1, w2_out, w.G);
     // pass 3: weighted row sums -> correspondences
     p.G = w.G;

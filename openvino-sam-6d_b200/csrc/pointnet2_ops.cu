@@ -542,10 +542,17 @@ constexpr int kPeSegWords = kPeTile / 32 / kPeSeg;  // mask words per thread per
 // CLOUD_IN_SMEM (N <= 4096): the whole cloud, padded to a multiple of kPeTile, is staged once as
 // float4 and serves both the scan and the final gather: a random 16-byte shared-memory read per
 // neighbour instead of three fully divergent global loads (32 L1 wavefronts each).
-template <bool CLOUD_IN_SMEM>
+//
+// MASKED: instead of testing every point, the scan visits only the set bits of a per-centre
+// candidate mask (B,N,ceil(N/32)) produced by the tensor-core filter (pe_mask_tc.cu) for the LARGER
+// radius -- possibly on the cloud as it was BEFORE a rigid motion, since ball membership survives
+// one up to rounding and the filter is generous by more than that.  Every candidate still goes
+// through the exact test below on THIS cloud, so the outputs do not change.
+template <bool CLOUD_IN_SMEM, bool MASKED>
 __global__ void __launch_bounds__(kPeThreads)
 pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int ns1,
-                 float *__restrict__ out1, float r2b, int ns2, float *__restrict__ out2) {
+                 float *__restrict__ out1, float r2b, int ns2, float *__restrict__ out2,
+                 const uint32_t *__restrict__ cmask, int W) {
     extern __shared__ float4 s_dyn[];
     const int n_pts_smem = CLOUD_IN_SMEM ? (N + kPeTile - 1) / kPeTile * kPeTile : kPeTile;
     float4 *s_pts = s_dyn;                                                   // n_pts_smem
@@ -593,16 +600,48 @@ pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int
         const float4 *tile = CLOUD_IN_SMEM ? s_pts + base : s_pts;
         unsigned m1[kPeSegWords], m2[kPeSegWords];
         int h1 = 0, h2 = 0;
+        unsigned cw[kPeSegWords];  // candidate words of this thread's quarter of the tile
+        if (MASKED) {
+            const int wi0 = (base >> 5) + seg * kPeSegWords;
+            const uint32_t *mrow = cmask + ((size_t)b * N + (active ? j : 0)) * W;
+#pragma unroll
+            for (int w = 0; w < kPeSegWords; ++w) cw[w] = 0u;
+            if (active) {
+                if ((W & 3) == 0 && wi0 + kPeSegWords <= W) {
+#pragma unroll
+                    for (int w = 0; w < kPeSegWords; w += 4) {
+                        const uint4 q4 = __ldg(reinterpret_cast<const uint4 *>(mrow + wi0 + w));
+                        cw[w] = q4.x; cw[w + 1] = q4.y; cw[w + 2] = q4.z; cw[w + 3] = q4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < kPeSegWords; ++w)
+                        if (wi0 + w < W) cw[w] = __ldg(mrow + wi0 + w);
+                }
+            }
+        }
 #pragma unroll
         for (int w = 0; w < kPeSegWords; ++w) {
             const float4 *pp = tile + (seg * kPeSegWords + w) * 32;
             unsigned a1 = 0u, a2 = 0u;
+            if (MASKED) {
+                unsigned cm = cw[w];
+                while (cm != 0u) {
+                    const int u = __ffs(cm) - 1;
+                    cm &= cm - 1u;
+                    const float4 p = pp[u];
+                    const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
+                    if (d2 < r2a) a1 |= 1u << u;
+                    if (d2 < r2b) a2 |= 1u << u;
+                }
+            } else {
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-                const float4 p = pp[u];
-                const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
-                if (d2 < r2a) a1 |= 1u << u;
-                if (d2 < r2b) a2 |= 1u << u;
+                for (int u = 0; u < 32; ++u) {
+                    const float4 p = pp[u];
+                    const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
+                    if (d2 < r2a) a1 |= 1u << u;
+                    if (d2 < r2b) a2 |= 1u << u;
+                }
             }
             m1[w] = a1; m2[w] = a2;
             h1 += __popc(a1); h2 += __popc(a2);
@@ -834,15 +873,60 @@ extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, f
     const dim3 grid((N + kPeCentres - 1) / kPeCentres, B);
     if (in_smem) {
         static size_t cached = 0;
-        if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true>, smem, &cached)) return rc;
-        pe_group2_kernel<true><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
-            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2);
+        if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true, false>, smem, &cached)) return rc;
+        pe_group2_kernel<true, false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
+            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
+            nullptr, 0);
     } else {
         static size_t cached = 0;
-        if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<false>, smem, &cached)) return rc;
-        pe_group2_kernel<false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
-            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2);
+        if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<false, false>, smem, &cached)) return rc;
+        pe_group2_kernel<false, false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
+            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
+            nullptr, 0);
     }
+    return pem_launch_status();
+}
+
+namespace pem {
+int pe_mask_tc_launch(const float *xyz, int B, int N, float eps, float thr, float rel_slack, int max_ctas,
+                      uint32_t *masks, cudaStream_t st);  // pe_mask_tc.cu
+}
+
+extern "C" size_t pem_pe_masks_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 0;
+    return (size_t)B * N * ((N + 31) / 32) * sizeof(uint32_t);
+}
+
+extern "C" int pem_pe_masks(const float *xyz, int B, int N, float centre_eps, float radius, float rel_margin,
+                            int max_ctas, void *masks, size_t masks_bytes, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(masks);
+    PEM_REQUIRE(B > 0 && N > 0 && radius > 0.f && rel_margin >= 0.f && rel_margin <= 0.5f, PEM_E_SHAPE);
+    PEM_REQUIRE(N <= 4096, PEM_E_UNSUPPORTED);
+    PEM_REQUIRE(masks_bytes >= pem_pe_masks_bytes(B, N), PEM_E_WORKSPACE);
+    return pe_mask_tc_launch(xyz, B, N, centre_eps, radius * radius, rel_margin, max_ctas, (uint32_t *)masks,
+                             pem_cu_stream(stream));
+}
+
+extern "C" int pem_pe_group2_masked(const float *xyz, int B, int N, float centre_eps, float radius1,
+                                    int nsample1, float *out1, float radius2, int nsample2, float *out2,
+                                    const void *masks, size_t masks_bytes, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(out1);
+    PEM_REQUIRE_PTR(out2);
+    PEM_REQUIRE_PTR(masks);
+    PEM_REQUIRE(B > 0 && N > 0 && nsample1 > 0 && nsample2 > 0 && B <= 65535, PEM_E_SHAPE);
+    PEM_REQUIRE(nsample1 <= 128 && nsample2 <= 128 && N <= 4096, PEM_E_UNSUPPORTED);  // cloud in smem
+    PEM_REQUIRE(masks_bytes >= pem_pe_masks_bytes(B, N), PEM_E_WORKSPACE);
+    const size_t n_pts = (size_t)(N + kPeTile - 1) / kPeTile * kPeTile;
+    const size_t smem = n_pts * sizeof(float4) +
+                        (size_t)kPeCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
+    static size_t cached = 0;
+    if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true, true>, smem, &cached)) return rc;
+    pe_group2_kernel<true, true><<<dim3((N + kPeCentres - 1) / kPeCentres, B), kPeThreads, smem,
+                                  pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,
+                                                           radius2 * radius2, nsample2, out2,
+                                                           (const uint32_t *)masks, (N + 31) / 32);
     return pem_launch_status();
 }
 

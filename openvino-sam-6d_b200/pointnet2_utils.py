@@ -94,6 +94,36 @@ def pe_group2(xyz, radius1=0.1, nsample1=32, radius2=0.2, nsample2=64, centre_ep
     return out1, out2
 
 
+def pe_masks(xyz, radius=0.2, centre_eps=1e-8, rel_margin=1e-3, max_ctas=0):
+    """Tensor-core candidate filter for pe_group2_masked: one bit per (centre, point) pair, set when
+    the point may lie within `radius` of the centre.  May be computed on the cloud BEFORE a rigid
+    motion (ball membership is invariant; rel_margin covers the rounding of the motion)."""
+    _ext._check(xyz, "xyz", torch.float32, "a float")
+    B, N, _ = xyz.shape
+    L = _lib.lib()
+    nbytes = L.pem_pe_masks_bytes(B, N)
+    masks = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(L.pem_pe_masks(xyz.data_ptr(), B, N, float(centre_eps), float(radius), float(rel_margin),
+                                  int(max_ctas), masks.data_ptr(), nbytes, _ext._stream()), "pem_pe_masks")
+    return masks
+
+
+def pe_group2_masked(xyz, masks, radius1=0.1, nsample1=32, radius2=0.2, nsample2=64, centre_eps=1e-8):
+    """pe_group2(xyz) visiting only the candidates of `masks` (made with radius >= both radii, on this
+    cloud or on it before a rigid motion): bit-identical outputs."""
+    _ext._check(xyz, "xyz", torch.float32, "a float")
+    B, N, _ = xyz.shape
+    out1 = torch.empty((B, 6, N, nsample1), dtype=torch.float32, device=xyz.device)
+    out2 = torch.empty((B, 6, N, nsample2), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.lib().pem_pe_group2_masked(xyz.data_ptr(), B, N, float(centre_eps), float(radius1),
+                                                   int(nsample1), out1.data_ptr(), float(radius2),
+                                                   int(nsample2), out2.data_ptr(), masks.data_ptr(),
+                                                   masks.numel(), _ext._stream()), "pem_pe_group2_masked")
+    return out1, out2
+
+
 class QueryAndGroup(nn.Module):
     """pointnet2_utils.py:303-403.  Only the configuration PEM uses is accelerated
     (use_xyz=True, no uniform re-sampling); other flags raise."""

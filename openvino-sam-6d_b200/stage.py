@@ -38,6 +38,7 @@ class GeometricStage:
         self.P1, self.P2, self.temp, self.dis_thres = n_proposal1, n_proposal2, temp, dis_thres
         self.dev = torch.device(device)
         self.L = _lib.lib()
+        self.n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.fine_mode = fine_mode
         B, N, M, C, Nm, P1, P2 = batch, n_dense, n_sparse, feat_dim, n_model, n_proposal1, n_proposal2
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -66,6 +67,8 @@ class GeometricStage:
         # step 3
         self.pe_xyz = e((1, B, N, 3), **f32)      # p1_ = (p1 - init_t) @ init_R
         self.pe_out = [e((2 * B, 6, N, ns), **f32) for _, ns in PE_SCALES]
+        self.pe_mask_bytes = self.L.pem_pe_masks_bytes(2 * B, N)
+        self.pe_masks = e((self.pe_mask_bytes,), dtype=torch.uint8, device=self.dev)  # ball-query candidates
         self.sparse_fine = [e((2, B, M, C), **f32) for _ in range(3)]
         # step 4
         self.atten_f = e((B, N + 1, N + 1), **f32) if fine_mode == "materialised" else None
@@ -76,8 +79,10 @@ class GeometricStage:
                  self.L.pem_fine_fused_workspace_bytes(B, N, N, C), 256)
         self.ws = torch.empty(nb, dtype=torch.uint8, device=self.dev)
         self.ws_bytes = nb
-        self.stream = torch.cuda.Stream(device=self.dev)
-        self.side = torch.cuda.Stream(device=self.dev)  # template-only work, forked inside a step
+        # the critical chain runs at high priority: when SM resources free up its CTAs go first, so the
+        # side stream's bulk kernels only soak up what the latency-bound coarse chain leaves idle
+        self.stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.side = torch.cuda.Stream(device=self.dev, priority=0)  # pose-independent work, forked inside a step
         self.graph = None
         self.use_graph = use_graph
         self.kernels_per_step = 0
@@ -106,12 +111,23 @@ class GeometricStage:
         ck = _lib.check
         p = lambda t: t.data_ptr()
         n = 0
-        # fork: the PE grouping of the template cloud depends on nothing but the template, so it
-        # runs on a side stream concurrently with the (latency-bound, few-CTA) coarse chain
+        # fork: pose-independent work runs on a side stream, concurrently with the (latency-bound,
+        # few-CTA) FPS at the head of the coarse chain:
+        #  * tensor-core candidate masks of the ball query for BOTH clouds in one launch.  One cloud is
+        #    grouped only after the coarse pose has moved it -- but rigidly, and ball membership
+        #    survives a rigid motion, so its N^2 filter also runs here, ahead of the pose, and step 3
+        #    only re-tests the candidates exactly on the moved points;
+        #  * the PE grouping of the cloud that is not moved.
         (r1, ns1), (r2, ns2) = PE_SCALES
+        half = self.pe_mask_bytes // 2
         self.side.wait_stream(self.stream)
-        ck(L.pem_pe_group2(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
-                           p(self.pe_out[1][B:]), self.side.cuda_stream), "pe_group2 template"); n += 1
+        # (grid capped so that the filter's CTAs -- one whole SM each -- are resident TOGETHER with the
+        # 2B CTAs of the FPS kernel instead of waiting for them in a second round)
+        ck(L.pem_pe_masks(p(self.pts), 2 * B, N, 1e-8, max(r1, r2), 1e-3, max(1, self.n_sms - 2 * B),
+                          p(self.pe_masks), self.pe_mask_bytes, self.side.cuda_stream), "pe_masks"); n += 1
+        ck(L.pem_pe_group2_masked(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
+                                  p(self.pe_out[1][B:]), p(self.pe_masks) + half, half,
+                                  self.side.cuda_stream), "pe_group2 unmoved cloud"); n += 1
         # 1. FPS on both clouds in one launch (2B clouds), then row gathers
         ck(L.pem_fps(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), None, 0, st), "fps"); n += 1
         ck(L.pem_gather_rows(p(self.pts), p(self.fps_idx), 2 * B, N, 3, M, N * 3, 3,
@@ -138,9 +154,12 @@ class GeometricStage:
         # 3. fine front end: p1_ = (p1 - t) @ R ; PE grouping of p1_ and of the template
         ck(L.pem_transform_points(p(self.pts[0]), p(self.init_R), p(self.init_t), B, N, 0.0,
                                   p(self.pe_xyz[0]), st), "transform"); n += 1
-        # both PE scales of the observed cloud in a single kernel (distance computed once per pair)
-        ck(L.pem_pe_group2(p(self.pe_xyz[0]), B, N, 1e-8, r1, ns1, p(self.pe_out[0]), r2, ns2,
-                           p(self.pe_out[1]), st), "pe_group2 observed"); n += 1
+        # both PE scales of the moved cloud: exact test of the candidates only (bit-identical to
+        # pem_pe_group2 on the moved cloud); needs the side stream's masks
+        self.stream.wait_stream(self.side)
+        ck(L.pem_pe_group2_masked(p(self.pe_xyz[0]), B, N, 1e-8, r1, ns1, p(self.pe_out[0]), r2, ns2,
+                                  p(self.pe_out[1]), p(self.pe_masks), half, st),
+           "pe_group2 moved cloud"); n += 1
         # 3 transformer blocks x (observed, template): gather 196 rows of the bg-prepended
         # (B,2049,C) features with the FPS indices (reference quirk kept: index 0 fetches the
         # background row, transformer.py:667-671)

@@ -172,3 +172,34 @@ def test_pe_group2_fused_bit_exact(pkg, oracle, dev):
     w2, _ = oracle.query_and_group(xyz.numpy(), (xyz + 1e-8).numpy(), feat.numpy(), 0.2, 64)
     np.testing.assert_array_equal(o1.cpu().numpy(), w1)
     np.testing.assert_array_equal(o2.cpu().numpy(), w2)
+
+
+@pytest.mark.parametrize("N,scale,moved", [(2048, 0.3, True), (777, 0.2, True), (2048, 0.05, True), (4096, 0.3, True),
+                                           (2048, 0.3, False), (1500, 3.0, False), (33, 0.1, True)])
+def test_pe_group2_masked_bit_exact(pkg, oracle, dev, N, scale, moved):
+    """Tensor-core candidate masks (from the UNMOVED cloud when `moved`) + exact re-test of the
+    candidates == QueryAndGroup on the final cloud, bit for bit: random rigid motions, a dense cloud
+    where every neighbour list fills up at once, a sparse one with mostly empty balls, points
+    planted exactly on both ball surfaces, sizes that are not multiples of the tiles."""
+    g = torch.Generator().manual_seed(N)
+    B = 3
+    xyz = (torch.randn(B, N, 3, generator=g) * scale + torch.tensor([0.7, -0.2, 1.3])).contiguous()
+    xyz[:, 1] = xyz[:, 0] + torch.tensor([0.1, 0.0, 0.0])   # |d| == r1 up to rounding
+    xyz[:, 2] = xyz[:, 0] + torch.tensor([0.0, 0.2, 0.0])   # |d| == r2 up to rounding
+    final = xyz
+    if moved:
+        q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+        t = 0.3 * torch.randn(B, 1, 3, generator=g)
+        final = ((xyz - t) @ q).contiguous()                  # MU:267 form of the rigid motion
+    masks = pkg.pointnet2_utils.pe_masks(xyz.to(dev))
+    o1, o2 = pkg.pointnet2_utils.pe_group2_masked(final.to(dev), masks)
+    feat = final.transpose(1, 2).contiguous()
+    w1, _ = oracle.query_and_group(final.numpy(), (final + 1e-8).numpy(), feat.numpy(), 0.1, 32)
+    w2, _ = oracle.query_and_group(final.numpy(), (final + 1e-8).numpy(), feat.numpy(), 0.2, 64)
+    np.testing.assert_array_equal(o1.cpu().numpy(), w1)
+    np.testing.assert_array_equal(o2.cpu().numpy(), w2)
+    # the filter is a filter: a few per cent of the pairs, never fewer than the true neighbours
+    bits = masks.view(torch.int32).view(B, N, -1)
+    frac = sum(bin(int(x) & 0xFFFFFFFF).count("1") for x in bits[0].flatten().tolist()) / float(N * N)
+    true_frac = float((torch.cdist(final[0], final[0]) < 0.2).float().mean())
+    assert true_frac <= frac <= true_frac * 1.05 + 1e-3, (frac, true_frac)

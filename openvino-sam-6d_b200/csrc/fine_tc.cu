@@ -507,7 +507,7 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
                        float *__restrict__ lbg /* (B,2): log2 of the background row / column sums */) {
     __shared__ float red[32];
     const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == gridDim.x - 1) {  // one block per instance: sums of the background row and column
+    if (blockIdx.x == gridDim.x - 1) {  // one EXTRA block per instance: sums of the background row and column
         float sr = 0.f, sc = 0.f;
         for (int j = threadIdx.x; j < Cn; j += blockDim.x) sr += ex2(fmaf(bg_b[(size_t)b * Np + j], c1, -c2));
         for (int i = threadIdx.x; i < R; i += blockDim.x) sc += ex2(fmaf(bg_a[(size_t)b * Mp + i], c1, -c2));
@@ -515,6 +515,7 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
         sr = block_sum(sr, red);
         sc = block_sum(sc, red);
         if (threadIdx.x == 0) { lbg[2 * b] = log2f(sr + e00); lbg[2 * b + 1] = log2f(sc + e00); }
+        return;
     }
     if (k < Mp) {
         float s = 0.f;
@@ -820,7 +821,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     p.rowpart = w.rowpart;
     p.colpart = w.colpart;
     if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
-    tc_finish_stats_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+    tc_finish_stats_kernel<<<dim3((mx + 255) / 256 + 1, B), 256, 0, st>>>(
         w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, w.s00, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
         w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs, w.lbg);
     // pass 2: foreground labels

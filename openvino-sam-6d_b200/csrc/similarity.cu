@@ -10,12 +10,14 @@
 
 namespace pem {
 
-// 1 / max(||row||_2, 1e-12): one warp per row (F.normalize, eps = 1e-12).
+// 1 / max(||row||_2, 1e-12): one warp per row (F.normalize, eps = 1e-12); both feature sets in one
+// launch (rows [0, rows1) of f1, then rows2 rows of f2; inv holds them back to back).
 __global__ void __launch_bounds__(256)
-row_inv_norm_kernel(const float *__restrict__ f, int rows, int C, float *__restrict__ inv) {
+row_inv_norm_kernel(const float *__restrict__ f1, int rows1, const float *__restrict__ f2, int rows2, int C,
+                    float *__restrict__ inv) {
     const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (row >= rows) return;
-    const float *p = f + (size_t)row * C;
+    if (row >= rows1 + rows2) return;
+    const float *p = row < rows1 ? f1 + (size_t)row * C : f2 + (size_t)(row - rows1) * C;
     float s = 0.f;
     for (int c = lane_id(); c < C; c += 32) {
         const float v = __ldg(p + c);
@@ -170,8 +172,7 @@ extern "C" int pem_feature_similarity(const float *f1, const float *f2, int B, i
                     PEM_E_WORKSPACE);
         inv1 = (float *)workspace;
         inv2 = inv1 + (size_t)B * N1;
-        row_inv_norm_kernel<<<(B * N1 + 7) / 8, 256, 0, st>>>(f1, B * N1, C, inv1);
-        row_inv_norm_kernel<<<(B * N2 + 7) / 8, 256, 0, st>>>(f2, B * N2, C, inv2);
+        row_inv_norm_kernel<<<(B * (N1 + N2) + 7) / 8, 256, 0, st>>>(f1, B * N1, f2, B * N2, C, inv1);
     }
     if (N1 <= 512 && N2 <= 512) {
         dim3 grid((N2 + 63) / 64, (N1 + 63) / 64, B);

@@ -138,7 +138,7 @@ class GeometricStage:
         # 2. coarse
         ck(L.pem_feature_similarity(p(self.sparse_feats[0]), p(self.sparse_feats[1]), B, M + 1, M + 1,
                                     C, self.temp, 1, p(self.atten_c), p(self.ws), self.ws_bytes, st),
-           "coarse similarity"); n += 3
+           "coarse similarity"); n += 2
         ck(L.pem_coarse_assign(p(self.atten_c), B, M, M, p(self.w1c), p(self.w2c), p(self.cdf), st),
            "coarse_assign"); n += 1
         ck(L.pem_coarse_hypotheses(p(self.cdf), p(self.rand), p(self.sparse_pts[0]),

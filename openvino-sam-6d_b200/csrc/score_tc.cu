@@ -26,7 +26,9 @@
 //     buffered in the 512 TMEM columns; A tiles double buffered so tile t+1 is built while tile t
 //     is reduced;
 //   * distances land in shared memory, and each hypothesis is summed in a fixed order.
-// The SIMT kernel (coarse.cu) remains for shapes this one does not take (more than 1024 model points).
+// More than 1024 model points are taken in blocks of 1024: the tiles of a batch of hypotheses run
+// once per block and the running minima wait in shared memory.  The SIMT kernel (coarse.cu) remains
+// for shapes this one does not take (more than 4096 model points or 256 query points).
 #include "tc_ptx.cuh"
 
 namespace pem {
@@ -67,7 +69,6 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
     const int b = blockIdx.x / cpi, slice = blockIdx.x - b * cpi;
     const int hpc = (H + cpi - 1) / cpi;                       // hypotheses per CTA
     const int h_begin = slice * hpc, h_end = min(H, h_begin + hpc);
-    const int n_chunks = (Nm + kSChunk - 1) / kSChunk;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -85,7 +86,7 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ---- per-CTA setup: foreground points (ordered compaction) and the model operand
+    // ---- per-CTA setup: foreground points (ordered compaction)
     if (warp == 0) {
         const float *wb = w1 + (size_t)b * N1, *pb = pts1 + (size_t)b * N1 * 3;
         int n = 0;
@@ -103,12 +104,23 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
         }
         if (lane == 0) sm.nfg = n;
     }
-    {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+    const int nfg = sm.nfg;
+    const int n_blocks = (Nm + kSMaxNm - 1) / kSMaxNm;  // model blocks of <= 1024 points
+
+    // the model operand: block `mblk` of the model points as B rows
+    auto build_model = [&](int mblk) {
         const float *mb = model + (size_t)b * Nm * 3;
-        for (int m = tid; m < n_chunks * kSChunk; m += kSThreads) {
+        const int m_lo = mblk * kSMaxNm, cnt = min(kSMaxNm, Nm - m_lo);
+        const int padded = (cnt + kSChunk - 1) / kSChunk * kSChunk;
+        for (int m = tid; m < padded; m += kSThreads) {
             float4 c0, c1, c2, c3;
-            if (m < Nm) {
-                const float x = __ldg(mb + 3 * m), y = __ldg(mb + 3 * m + 1), z = __ldg(mb + 3 * m + 2);
+            if (m < cnt) {
+                const float *p = mb + 3 * (size_t)(m_lo + m);
+                const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
                 const float xh = to_tf32(x), yh = to_tf32(y), zh = to_tf32(z);
                 const float xl = to_tf32(x - xh), yl = to_tf32(y - yh), zl = to_tf32(z - zh);
                 const float s = x * x + y * y + z * z, sh = to_tf32(s), sl = to_tf32(s - sh);
@@ -125,134 +137,148 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
             *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 2)) = c2;
             *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 3)) = c3;
         }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = sm.tmem_base;
-    const int nfg = sm.nfg;
+        fence_proxy_async_smem();
+        return padded / kSChunk;
+    };
 
-    // pipeline state shared by the roles (every role walks the same batch / tile sequence)
     if (nfg > 0 && h_begin < h_end) {
-        if (warp == 1) {
-            // ================================ MMA issuer ==================================
-            const uint64_t b0 = umma_desc_sw128(smem_u32(sm.b));
-            uint32_t tile_seq = 0, chunk_seq = 0;
-            for (int hb = h_begin; hb < h_end; hb += kSBatchHyps) {
-                const int rows = (min(h_end, hb + kSBatchHyps) - hb) * nfg;
-                for (int r0 = 0; r0 < rows; r0 += kSRows, ++tile_seq) {
-                    const int buf = tile_seq & 1;
-                    mbar_wait(smem_u32(&sm.a_full[buf]), (tile_seq >> 1) & 1);
-                    tc_fence_after();
-                    const uint64_t ad = umma_desc_sw128(smem_u32(sm.a[buf]));
-                    for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
-                        const int cb = chunk_seq & 1;
-                        mbar_wait(smem_u32(&sm.tmem_empty[cb]), ((chunk_seq >> 1) & 1) ^ 1);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t d = tmem_base + (uint32_t)(cb * kSChunk);
-                            const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
-                            tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
-                            tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
-                            tc_commit(smem_u32(&sm.tmem_full[cb]));
-                            if (c == n_chunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-        } else if (warp >= 2) {
-            // ================================ row threads =================================
-            const int quad = warp & 3, half = (warp - 2) >> 2;
-            const int et = quad * 32 + lane;  // tile row = TMEM lane
-            uint32_t tile_seq = 0, chunk_seq = 0;
-            float q2_next = 0.f;
-
-            // transform the point of tile row `et` and write this thread's half of the A row
-            auto build = [&](int rows, int r0, uint32_t seq) {
-                const int buf = seq & 1;
-                mbar_wait(smem_u32(&sm.a_empty[buf]), ((seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
-                const int row = r0 + et;
-                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-                float q2 = 0.f;
-                if (row < rows) {
-                    const int hh = row / nfg, i = row - hh * nfg;
-                    const float *Rm = sm.Rt[hh];
-                    const float v0 = sm.px[i] - Rm[9], v1 = sm.py[i] - Rm[10], v2 = sm.pz[i] - Rm[11];
-                    // (p1 - t) @ R : row vector times R (MU:267)
-                    const float qx = v0 * Rm[0] + v1 * Rm[3] + v2 * Rm[6];
-                    const float qy = v0 * Rm[1] + v1 * Rm[4] + v2 * Rm[7];
-                    const float qz = v0 * Rm[2] + v1 * Rm[5] + v2 * Rm[8];
-                    q2 = qx * qx + qy * qy + qz * qz;
-                    const float xh = to_tf32(qx), yh = to_tf32(qy), zh = to_tf32(qz);
-                    const float xl = to_tf32(qx - xh), yl = to_tf32(qy - yh), zl = to_tf32(qz - zh);
-                    if (half == 0) {
-                        c0 = make_float4(xh, yh, zh, xh);
-                        c1 = make_float4(yh, zh, xl, yl);
-                    } else {
-                        c0 = make_float4(zl, xl, yl, zl);
-                        c1 = make_float4(1.f, 1.f, 0.f, 0.f);
-                    }
-                }
-                *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half)) = c0;
-                *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half + 1)) = c1;
-                fence_proxy_async_smem();
-                mbar_arrive(smem_u32(&sm.a_full[buf]));
-                return q2;
-            };
-
-            for (int hb = h_begin; hb < h_end; hb += kSBatchHyps) {
-                const int nb = min(h_end, hb + kSBatchHyps) - hb, rows = nb * nfg;
+        // Every warp walks the same (batch of hypotheses, model block) sequence; with more than 1024
+        // model points the tiles of a batch are run once per model block and the running minimum of
+        // each row waits in `dis` in between.  Barrier phases (tile_seq, chunk_seq) run on throughout.
+        uint32_t tile_seq = 0, chunk_seq = 0;
+        int loaded = -1;  // model block currently in shared memory
+        for (int hb = h_begin; hb < h_end; hb += kSBatchHyps) {
+            const int nb = min(h_end, hb + kSBatchHyps) - hb, rows = nb * nfg;
+            const int n_tiles = (rows + kSRows - 1) / kSRows;
+            if (warp >= 2)
                 for (int k = tid - 64; k < nb * 12; k += kSRowThreads) {  // stage R | t of the batch
                     const int hh = k / 12, e = k - hh * 12, h = hb + hh;
                     const size_t src = (size_t)b * P + (sel ? __ldg(sel + (size_t)b * H + h) : h);
                     sm.Rt[hh][e] = e < 9 ? __ldg(R + src * 9 + e) : __ldg(t + src * 3 + (e - 9));
                 }
-                row_barrier();
-                q2_next = build(rows, 0, tile_seq);
-                for (int r0 = 0; r0 < rows; r0 += kSRows, ++tile_seq) {
-                    const float q2 = q2_next;
-                    if (r0 + kSRows < rows) q2_next = build(rows, r0 + kSRows, tile_seq + 1);
-                    // reduce this thread's lane over its half of every chunk
-                    float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
-                    for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
-                        const int cb = chunk_seq & 1;
-                        mbar_wait(smem_u32(&sm.tmem_full[cb]), (chunk_seq >> 1) & 1);
+            for (int mblk = 0; mblk < n_blocks; ++mblk) {
+                int n_chunks = (min(kSMaxNm, Nm - mblk * kSMaxNm) + kSChunk - 1) / kSChunk;
+                if (loaded != mblk) {  // (every MMA that read the previous block has retired: its
+                    __syncthreads();   //  accumulators were all consumed before this barrier)
+                    n_chunks = build_model(mblk);
+                    loaded = mblk;
+                }
+                __syncthreads();
+                const bool first = mblk == 0, last = mblk == n_blocks - 1;
+
+                if (warp == 1) {
+                    // ================================ MMA issuer ==================================
+                    const uint64_t b0 = umma_desc_sw128(smem_u32(sm.b));
+                    for (int tl = 0; tl < n_tiles; ++tl, ++tile_seq) {
+                        const int buf = tile_seq & 1;
+                        mbar_wait(smem_u32(&sm.a_full[buf]), (tile_seq >> 1) & 1);
                         tc_fence_after();
-                        {
-                            float v[kSChunk / 2];
-                            tmem_ld128(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                           (uint32_t)(cb * kSChunk + half * (kSChunk / 2)), v);
-#pragma unroll
-                            for (int q = 0; q < kSChunk / 2; q += 8) {
-                                m0 = fminf(fminf(m0, v[q]), v[q + 1]);
-                                m1 = fminf(fminf(m1, v[q + 2]), v[q + 3]);
-                                m2 = fminf(fminf(m2, v[q + 4]), v[q + 5]);
-                                m3 = fminf(fminf(m3, v[q + 6]), v[q + 7]);
+                        const uint64_t ad = umma_desc_sw128(smem_u32(sm.a[buf]));
+                        for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                            const int cb = chunk_seq & 1;
+                            mbar_wait(smem_u32(&sm.tmem_empty[cb]), ((chunk_seq >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t d = tmem_base + (uint32_t)(cb * kSChunk);
+                                const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
+                                tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
+                                tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
+                                tc_commit(smem_u32(&sm.tmem_full[cb]));
+                                if (c == n_chunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                            }
+                            __syncwarp();
+                        }
+                    }
+                } else if (warp >= 2) {
+                    // ================================ row threads =================================
+                    const int quad = warp & 3, half = (warp - 2) >> 2;
+                    const int et = quad * 32 + lane;  // tile row = TMEM lane
+
+                    // transform the point of tile row `et` and write this thread's half of the A row
+                    auto build = [&](int r0, uint32_t seq) {
+                        const int buf = seq & 1;
+                        mbar_wait(smem_u32(&sm.a_empty[buf]), ((seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
+                        const int row = r0 + et;
+                        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                        float q2 = 0.f;
+                        if (row < rows) {
+                            const int hh = row / nfg, i = row - hh * nfg;
+                            const float *Rm = sm.Rt[hh];
+                            const float v0 = sm.px[i] - Rm[9], v1 = sm.py[i] - Rm[10], v2 = sm.pz[i] - Rm[11];
+                            // (p1 - t) @ R : row vector times R (MU:267)
+                            const float qx = v0 * Rm[0] + v1 * Rm[3] + v2 * Rm[6];
+                            const float qy = v0 * Rm[1] + v1 * Rm[4] + v2 * Rm[7];
+                            const float qz = v0 * Rm[2] + v1 * Rm[5] + v2 * Rm[8];
+                            q2 = qx * qx + qy * qy + qz * qz;
+                            const float xh = to_tf32(qx), yh = to_tf32(qy), zh = to_tf32(qz);
+                            const float xl = to_tf32(qx - xh), yl = to_tf32(qy - yh), zl = to_tf32(qz - zh);
+                            if (half == 0) {
+                                c0 = make_float4(xh, yh, zh, xh);
+                                c1 = make_float4(yh, zh, xl, yl);
+                            } else {
+                                c0 = make_float4(zl, xl, yl, zl);
+                                c1 = make_float4(1.f, 1.f, 0.f, 0.f);
                             }
                         }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[cb]));
+                        *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half)) = c0;
+                        *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half + 1)) = c1;
+                        fence_proxy_async_smem();
+                        mbar_arrive(smem_u32(&sm.a_full[buf]));
+                        return q2;
+                    };
+
+                    float q2_next = build(0, tile_seq);
+                    for (int tl = 0; tl < n_tiles; ++tl, ++tile_seq) {
+                        const int r0 = tl * kSRows;
+                        const float q2 = q2_next;
+                        if (tl + 1 < n_tiles) q2_next = build(r0 + kSRows, tile_seq + 1);
+                        // reduce this thread's lane over its half of every chunk
+                        float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+                        for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                            const int cb = chunk_seq & 1;
+                            mbar_wait(smem_u32(&sm.tmem_full[cb]), (chunk_seq >> 1) & 1);
+                            tc_fence_after();
+                            {
+                                float v[kSChunk / 2];
+                                tmem_ld128(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                               (uint32_t)(cb * kSChunk + half * (kSChunk / 2)), v);
+#pragma unroll
+                                for (int q = 0; q < kSChunk / 2; q += 8) {
+                                    m0 = fminf(fminf(m0, v[q]), v[q + 1]);
+                                    m1 = fminf(fminf(m1, v[q + 2]), v[q + 3]);
+                                    m2 = fminf(fminf(m2, v[q + 4]), v[q + 5]);
+                                    m3 = fminf(fminf(m3, v[q + 6]), v[q + 7]);
+                                }
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[cb]));
+                        }
+                        const float best = fminf(fminf(m0, m1), fminf(m2, m3));
+                        const int par = tile_seq & 1;
+                        if (half == 1) sm.comb[par][et] = best;
+                        row_barrier();
+                        if (half == 0 && r0 + et < rows) {
+                            float d = fminf(best, sm.comb[par][et]);
+                            if (!first) d = fminf(d, sm.dis[r0 + et]);  // minimum over the earlier model blocks
+                            sm.dis[r0 + et] = last ? sqrtf(fmaxf(q2 + d, 0.f)) : d;  // clamp, then sqrt
+                        }
                     }
-                    const float best = fminf(fminf(m0, m1), fminf(m2, m3));
-                    const int par = tile_seq & 1;
-                    if (half == 1) sm.comb[par][et] = best;
-                    row_barrier();
-                    if (half == 0 && r0 + et < rows)
-                        sm.dis[r0 + et] = sqrtf(fmaxf(q2 + fminf(best, sm.comb[par][et]), 0.f));  // clamp, then sqrt
+                } else {  // warp 0 keeps the sequence numbers in step
+                    tile_seq += (uint32_t)n_tiles;
+                    chunk_seq += (uint32_t)(n_tiles * n_chunks);
                 }
-                // deterministic per-hypothesis sums: one warp per hypothesis, fixed order
-                row_barrier();
+            }
+            // deterministic per-hypothesis sums: one warp per hypothesis, fixed order
+            __syncthreads();
+            if (warp >= 2)
                 for (int hh = warp - 2; hh < nb; hh += kSRowThreads / 32) {
                     float s = 0.f;
                     for (int i = lane; i < nfg; i += 32) s += sm.dis[hh * nfg + i];
                     s = warp_sum(s);
                     if (lane == 0) scores[(size_t)b * H + hb + hh] = __fdiv_rn((float)nfg, s + 1e-8f);  // MU:271
                 }
-                row_barrier();  // dis is rewritten by the next batch
-            }
+            __syncthreads();  // dis and Rt are rewritten by the next batch
         }
     } else if (warp >= 2) {
         // no foreground point: sum = 0 -> score = 0 / 1e-8 = 0 (MU:271)
@@ -276,7 +302,7 @@ int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, i
                     const float *pts1, const float *w1, int N1, const float *model, int Nm,
                     float *scores, cudaStream_t st) {
     using namespace tc;
-    if (Nm > kSMaxNm || N1 > kSMaxN1) return PEM_E_UNSUPPORTED;
+    if (Nm > 4 * kSMaxNm || N1 > kSMaxN1) return PEM_E_UNSUPPORTED;
     int dev = 0, sms = PEM_NUM_SMS;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

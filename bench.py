@@ -137,13 +137,14 @@ def run_b200(args, rank, world, local_rank):
     stage = pkg.stage.GeometricStage(B, dev)
     stage.instance_ids.copy_(torch.tensor(ids, dtype=torch.float32))
     stage.load(host)
-    gathered = [stage.records]
+    gathered = torch.empty((world * B, 16), dtype=torch.float32, device=dev)  # every rank's records
 
     def step_collective():
-        # the only multi-GPU traffic: one all-gather of the 64-byte pose records (NCCL over NVLink)
+        # the only multi-GPU traffic: one all-gather of the 64-byte pose records (NCCL over NVLink),
+        # straight from the stage's record buffer into a preallocated table
         if world > 1:
             with torch.cuda.stream(stage.stream):
-                gathered[0] = pkg.parallel.gather_records(stage.records, world * B, world)
+                pkg.parallel.gather_records(stage.records, world * B, world, out=gathered)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 

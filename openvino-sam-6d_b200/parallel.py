@@ -35,17 +35,23 @@ def unpack_records(rec):
             rec[:, 14].to(torch.int64))
 
 
-def gather_records(rec, n_instances, world):
-    """All ranks end up with the (n_instances,16) record table ordered by rank slice.  Uneven
-    slices are padded to the largest slice for the collective and trimmed afterwards."""
+def gather_records(rec, n_instances, world, out=None):
+    """All ranks end up with the (n_instances,16) record table ordered by rank slice.  Even slices
+    (the usual case) are ONE collective straight into `out` (preallocated by the caller, or fresh);
+    uneven slices are padded to the largest slice for the collective and trimmed afterwards."""
     import torch.distributed as dist
     if world == 1:
         return rec
     shards = shard_instances(n_instances, world)
     width = max(hi - lo for lo, hi in shards)
+    if all(hi - lo == width for lo, hi in shards) and rec.shape[0] == width and rec.is_contiguous():
+        if out is None:
+            out = torch.empty((world * width, RECORD_FLOATS), dtype=torch.float32, device=rec.device)
+        dist.all_gather_into_tensor(out, rec)
+        return out
     padded = torch.zeros((width, RECORD_FLOATS), dtype=torch.float32, device=rec.device)
     padded[: rec.shape[0]] = rec
-    out = torch.empty((world * width, RECORD_FLOATS), dtype=torch.float32, device=rec.device)
-    dist.all_gather_into_tensor(out, padded)
-    parts = [out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(shards)]
+    full = torch.empty((world * width, RECORD_FLOATS), dtype=torch.float32, device=rec.device)
+    dist.all_gather_into_tensor(full, padded)
+    parts = [full[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(shards)]
     return torch.cat(parts, 0)

@@ -46,6 +46,16 @@ assert pid.tolist() == [100 + i for i in range(10)]
 assert torch.allclose(s, torch.arange(10).float() / 10)
 assert t[:5].eq(0).all() and t[5:].eq(1).all()
 assert R[7, 0, 0] == 2.0
+# the same into a caller-owned table (what bench.py does every step)
+table = torch.full((10, 16), -1.0)
+assert pkg.parallel.gather_records(rec, 10, world, out=table) is table and torch.equal(table, allrec)
+# uneven slices (4 + 3): padded collective, trimmed result
+lo, hi = pkg.parallel.shard_instances(7, world)[rank]
+rec7 = pkg.parallel.pack_records(torch.eye(3).repeat(hi - lo, 1, 1), torch.zeros(hi - lo, 3),
+                                 torch.arange(lo, hi).float(), torch.arange(lo, hi, dtype=torch.int32),
+                                 torch.arange(lo, hi))
+all7 = pkg.parallel.gather_records(rec7, 7, world)
+assert all7.shape == (7, 16) and pkg.parallel.unpack_records(all7)[4].tolist() == list(range(7))
 if rank == 0:
     print("GATHER_OK")
 dist.destroy_process_group()

@@ -248,7 +248,9 @@ int pem_feature_similarity_tc(const float *f1, const float *f2, int B, int N1p, 
 /*
  * Fused fine stage: compute_feature_similarity (MU:131-153, cosine, normalised) followed by
  * compute_fine_Rt (MU:308-341) straight from the features; the (B,N1+1,N2+1) attention
- * matrix is never written to memory (three tcgen05 GEMM passes with reducing epilogues).
+ * matrix is never written to memory.  Two full tcgen05 GEMM passes with reducing epilogues
+ * (softmax statistics; foreground labels + weighted sums over every column) and a short ragged
+ * pass that takes the background columns' share out again.
  * f1 (B,N1+1,C), f2 (B,N2+1,C) with the background token in row 0; other arguments and
  * outputs as pem_fine_Rt.  Same constraints as pem_feature_similarity_tc.
  */
@@ -259,10 +261,11 @@ int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const fl
                    pem_stream_t stream);
 
 /*
- * Profiling hook (no reference counterpart): re-run ONE of the three reducing GEMM passes of
- * pem_fine_fused (pass 1 softmax statistics, 2 foreground labels, 3 weighted sums) on the
- * operands and constants a previous pem_fine_fused call with the same shapes left in
- * `workspace`.  Outputs go to workspace scratch only.  bench.py times the dominant kernel with it.
+ * Profiling hook (no reference counterpart): re-run ONE reducing GEMM pass of pem_fine_fused on the
+ * operands and constants a previous pem_fine_fused call with the same shapes left in `workspace`:
+ * pass 1 softmax statistics, 4 foreground labels + weighted sums over all columns (the two full
+ * passes of the default path), 2 labels only, 3 weighted sums only (the original three-pass
+ * path).  Outputs go to workspace scratch only.  bench.py times the dominant kernel with it.
  */
 int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
                         int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream);

@@ -8,17 +8,20 @@
 //             background token (row 0 of both feature sets) stays OUT of the GEMM: its row and
 //             column of the similarity matrix are 2 x 2049 exact fp32 dot products computed
 //             here, so the GEMM is exactly 2048 x 2048 per instance (no 2049 -> 2304 padding).
-//   GEMM x3   S = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (split-bf16: ~2^-17 relative, i.e.
+//   GEMM      S = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (split-bf16: ~2^-17 relative, i.e.
 //             fp32-class logits; plain bf16 would move the pose by up to 0.05 deg) with the
-//             accumulator in TMEM, recomputed in three passes whose epilogues reduce
-//             straight out of TMEM:
+//             accumulator in TMEM, recomputed in passes whose epilogues reduce straight out of TMEM:
 //               pass 1  e = exp(s/temp - 1/temp);  row sums, column sums      (softmax stats)
 //               pass 2  foreground labels (MU:321-322), compared in the log2 domain:
 //                       row max of (2 s/temp - log colsum_j) vs the background column,
-//                       column max of (2 s/temp - log rowsum_i) vs the background row
-//               pass 3  per row: sum_j P_ij w2_j  and  sum_j P_ij w2_j pts2_j  (MU:324-330)
-//             Because features are unit vectors, |s/temp| <= 1/temp, so a fixed shift
-//             replaces the running max of a streaming softmax.
+//                       column max of (2 s/temp - log rowsum_i) vs the background row;
+//                       AND, per row, sum_j P_ij and sum_j P_ij pts2_j over EVERY column j
+//               pass 3  (ragged: one 256-column strip per instance) the same sums over the columns
+//                       that pass 2 found to be background, compacted into a spare operand, to be
+//                       subtracted: MU:324-330 sums over foreground columns only, ~96 % of them
+//             (The original form -- labels in pass 2, sums over the foreground columns in a full
+//             pass 3 -- remains selectable.)  Because features are unit vectors, |s/temp| <= 1/temp,
+//             so a fixed shift replaces the running max of a streaming softmax.
 //   then the weighted Procrustes + pose score kernels of fine.cu.
 //
 // Kernel anatomy (persistent, one CTA per SM, 320 threads, CTAs grouped in PAIRS = clusters of 2
@@ -63,7 +66,7 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 2 * TN;      // double-buffered 128 x 256 accumulator: all of TMEM
 
-enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3 };
+enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3, kLabelW = 4 };  // kLabelW = kLabel + kWsum in one pass
 
 struct Params {
     int B, R, Cn;          // instances, valid rows and columns of the GEMM
@@ -86,6 +89,9 @@ struct Params {
     // kWsum
     const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for padding
     float *rowpart4;       // (B, 2*n_strips, 4, Mp)
+    // ragged passes (the background-column correction): strips >= strip_count[b] are skipped
+    const int *strip_count;
+    int strip_major;       // task order: strips outermost
     int dev;               // timing experiments: 1 no MMAs, 2 no streamed loads, 4 no epilogue math
 };
 
@@ -111,8 +117,13 @@ struct Task {
 __device__ __forceinline__ Task decode_task(const Params &p, int task) {
     Task t;
     const int split = task % p.n_splits, bn = task / p.n_splits;
-    t.b = bn / p.n_strips;
-    t.n = bn - t.b * p.n_strips;
+    if (p.strip_major) {  // strips outermost: the few live tasks of a ragged pass come first
+        t.n = bn / p.B;
+        t.b = bn - t.n * p.B;
+    } else {
+        t.b = bn / p.n_strips;
+        t.n = bn - t.b * p.n_strips;
+    }
     t.m0 = split * p.spt;
     t.m1 = min(p.n_msteps, t.m0 + p.spt);
     return t;
@@ -171,6 +182,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t phase = 0, b_phase = 0;
         for (int task = task0; task < n_tasks; task += task_step) {
             const Task t = decode_task(p, task);
+            if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;  // ragged pass: nothing there
             const int rowB = t.b * p.Np + t.n * TN + crank * BN;
             for (int m = t.m0; m < t.m1; ++m) {
                 const int rowA = t.b * p.Mp + m * TM + crank * BM;
@@ -216,6 +228,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
             for (int task = task0; task < n_tasks; task += task_step) {
                 const Task t = decode_task(p, task);
+                if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;
                 for (int m = t.m0; m < t.m1; ++m) {
                     mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
                     tc_fence_after();
@@ -268,32 +281,44 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int et = quad * 32 + lane;           // row of this CTA's 128 rows owned by this thread
         const int ep_tid = (warp - 2) * 32 + lane; // 0..255
         const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
+        constexpr bool LAB = (MODE == kLabel || MODE == kLabelW);  // label maxima
+        constexpr bool WS = (MODE == kWsum || MODE == kLabelW);    // weighted row sums
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int task = task0; task < n_tasks; task += task_step) {
             const Task t = decode_task(p, task);
+            if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;
             const int b = t.b, n = t.n;
             const int j0 = n * TN + half * WC;     // first column of this warp
             const int ncols = min(WC, p.Cn - j0);  // valid columns (<= 0: none)
-            float colacc[WC];
+            // Column reductions.  kStats / kLabel keep one accumulator per column in registers across the
+            // steps of the task (cheapest in instructions).  kLabelW has no registers to spare for that:
+            // it folds each 32-column chunk across the warp's 32 rows at once (31-shuffle transpose
+            // reduce) and keeps only lane L's column of every chunk.
+            constexpr bool COLREG = MODE == kStats || MODE == kLabel;
+            float colacc[COLREG ? WC : 1];
+            float cmx[WC / 32];
 #pragma unroll
-            for (int q = 0; q < WC; ++q) colacc[q] = (MODE == kLabel) ? -INFINITY : 0.f;
+            for (int q = 0; q < (COLREG ? WC : 1); ++q) colacc[q] = LAB ? -INFINITY : 0.f;
+#pragma unroll
+            for (int q = 0; q < WC / 32; ++q) cmx[q] = -INFINITY;
             // per-column constants of the task (+inf keeps padded columns out of the row max)
-            if (MODE == kLabel) sm.colc[ep_tid] = p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
-            if (MODE == kWsum) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * TN + ep_tid];
-            if (MODE == kLabel || MODE == kWsum) epi_barrier();
+            if (LAB) sm.colc[ep_tid] = p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
+            if (WS) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * TN + ep_tid];
+            if (LAB || WS) epi_barrier();
 
             for (int m = t.m0; m < t.m1; ++m) {
                 const int gi = m * TM + crank * BM + et;
                 const bool row_ok = gi < p.R;
                 float rowc = 0.f;  // per-row constant of this tile
                 if (MODE == kStats) rowc = row_ok ? kc2 : INFINITY;  // e = 0 for padded rows
-                if (MODE == kLabel) rowc = p.lrs[(size_t)b * p.Mp + gi];  // +inf for padded rows
-                float r0 = (MODE == kLabel) ? -INFINITY : 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+                if (LAB) rowc = p.lrs[(size_t)b * p.Mp + gi];  // +inf for padded rows
+                float rm = -INFINITY;                           // label: row maximum
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;   // statistics / weighted sums
                 mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
                 tc_fence_after();
                 // columns per TMEM load: 16 where 128 column accumulators already fill the registers
-                constexpr int CW = (MODE == kStats || MODE == kLabel) ? 16 : 32;
+                constexpr int CW = COLREG ? 16 : 32;
 #pragma unroll
                 for (int c = 0; c < WC / CW; ++c) {
                     if (p.dev & 4) break;
@@ -324,18 +349,22 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 colacc[c * CW + q] += e;
                             }
                         }
-                    } else if (MODE == kLabel) {
+                    }
+                    if (LAB) {
 #pragma unroll
                         for (int q = 0; q < CW; q += 4) {
                             const float4 cc = lds_f4(&sm.colc[half * WC + c * CW + q]);
                             // 2 s/temp - log colsum_j (row side), 2 s/temp - log rowsum_i (column side)
-                            r0 = fmaxf(fmaxf(r0, fmaf(v[q], kc2x, -cc.x)), fmaf(v[q + 1], kc2x, -cc.y));
-                            r0 = fmaxf(fmaxf(r0, fmaf(v[q + 2], kc2x, -cc.z)), fmaf(v[q + 3], kc2x, -cc.w));
+                            rm = fmaxf(fmaxf(rm, fmaf(v[q], kc2x, -cc.x)), fmaf(v[q + 1], kc2x, -cc.y));
+                            rm = fmaxf(fmaxf(rm, fmaf(v[q + 2], kc2x, -cc.z)), fmaf(v[q + 3], kc2x, -cc.w));
+                            if (COLREG) {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                colacc[c * CW + q + u] = fmaxf(colacc[c * CW + q + u], fmaf(v[q + u], kc2x, -rowc));
+                                for (int u = 0; u < 4; ++u)
+                                    colacc[c * CW + q + u] = fmaxf(colacc[c * CW + q + u], fmaf(v[q + u], kc2x, -rowc));
+                            }
                         }
-                    } else {  // kWsum
+                    }
+                    if (WS) {
 #pragma unroll
                         for (int q = 0; q < CW; ++q) {
                             const float u = ex2(fmaf(v[q], kc2x, -2.0f * kc2));  // e^2
@@ -346,6 +375,11 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             r3 = fmaf(u, g.z, r3);
                         }
                     }
+                    if constexpr (LAB && !COLREG) {  // column side of the labels for this chunk (v is dead after this)
+#pragma unroll
+                        for (int q = 0; q < CW; ++q) v[q] = fmaf(v[q], kc2x, -rowc);
+                        cmx[c] = fmaxf(cmx[c], warp_transpose_reduce<true>(v));
+                    }
                 }
                 // accumulator fully read: hand the TMEM buffer back to the MMA warp of the leader
                 tc_fence_before();
@@ -355,27 +389,31 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // per-(row, half-strip) partials: consecutive lanes = consecutive rows
                 const size_t pr = ((size_t)b * 2 * p.n_strips + 2 * n + half);
                 if (MODE == kStats) p.rowpart[pr * p.Mp + gi] = r0;
-                if (MODE == kLabel) p.rowmaxpart[pr * p.Mp + gi] = r0;
-                if (MODE == kWsum) {
+                if (LAB) p.rowmaxpart[pr * p.Mp + gi] = rm;
+                if (WS) {
                     float *dst = p.rowpart4 + pr * 4 * p.Mp + gi;
                     dst[0] = r0; dst[p.Mp] = r1; dst[2 * p.Mp] = r2; dst[3 * p.Mp] = r3;
                 }
             }
             // fold the column accumulators across the 32 lanes, then across the 4 quadrants;
             // every (row split, CTA of the pair) leaves its own plane
-            if (MODE == kStats || MODE == kLabel) {
+            if (MODE == kStats || LAB) {
 #pragma unroll
                 for (int c = 0; c < WC / 32; ++c) {
-                    float v[32];
+                    if (COLREG) {
+                        float v[32];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = colacc[c * 32 + q];
-                    sm.colred[quad][half * WC + c * 32 + lane] = warp_transpose_reduce<MODE == kLabel>(v);
+                        for (int q = 0; q < 32; ++q) v[q] = colacc[c * 32 + q];
+                        sm.colred[quad][half * WC + c * 32 + lane] = warp_transpose_reduce<LAB>(v);
+                    } else {
+                        sm.colred[quad][half * WC + c * 32 + lane] = cmx[c];
+                    }
                 }
                 epi_barrier();
                 float s = sm.colred[0][ep_tid];
 #pragma unroll
                 for (int w = 1; w < 4; ++w)
-                    s = (MODE == kLabel) ? fmaxf(s, sm.colred[w][ep_tid]) : s + sm.colred[w][ep_tid];
+                    s = LAB ? fmaxf(s, sm.colred[w][ep_tid]) : s + sm.colred[w][ep_tid];
                 const int plane = 2 * (t.m0 / p.spt) + crank;
                 p.colpart[((size_t)plane * p.B + b) * p.Np + n * TN + ep_tid] = s;
             }
@@ -504,7 +542,9 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
                        const float *__restrict__ s00, int Mp, int Np, int n_part, int planes, float c1,
                        float c2, float *__restrict__ inv_rowsum, float *__restrict__ lrs,
                        float *__restrict__ inv_colsum, float *__restrict__ lcs,
-                       float *__restrict__ lbg /* (B,2): log2 of the background row / column sums */) {
+                       float *__restrict__ lbg /* (B,2): log2 of the background row / column sums */,
+                       const float *__restrict__ pts2 /* (B,Cn,3) or null */,
+                       float4 *__restrict__ Gall /* (B,Np) or null: 1/colsum_j * (x_j, y_j, z_j, 1), EVERY column */) {
     __shared__ float red[32];
     const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == gridDim.x - 1) {  // one EXTRA block per instance: sums of the background row and column
@@ -534,8 +574,17 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
             s += ex2(fmaf(bg_b[(size_t)b * Np + k], c1, -c2));
         }
         const bool ok = k < Cn && s > 0.f;
-        inv_colsum[(size_t)b * Np + k] = ok ? 1.0f / s : 0.f;
+        const float ic = ok ? 1.0f / s : 0.f;
+        inv_colsum[(size_t)b * Np + k] = ic;
         lcs[(size_t)b * Np + k] = ok ? log2f(s) : INFINITY;
+        if (Gall) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < Cn) {
+                const float *q = pts2 + ((size_t)b * Cn + k) * 3;
+                g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+            }
+            Gall[(size_t)b * Np + k] = g;
+        }
     }
 }
 
@@ -548,7 +597,8 @@ tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__rest
                        const float *__restrict__ lbg, const float *__restrict__ inv_colsum,
                        const float *__restrict__ pts2, int R, int Cn, int Mp, int Np, int n_part,
                        int planes, float c1, float c2, float *__restrict__ w1 /* (B,R) */,
-                       float *__restrict__ w2_out /* (B,Cn) or null */, float4 *__restrict__ G) {
+                       float *__restrict__ w2_out /* (B,Cn) or null */, float4 *__restrict__ G /* or null */,
+                       float *__restrict__ fgcol /* (B,Np) or null: 1 = foreground or padding, 0 = background */) {
     const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     const float lrs0 = lbg[2 * b], lcs0 = lbg[2 * b + 1], c2x = 2.0f * c1;
     if (k < R) {
@@ -558,10 +608,12 @@ tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__rest
     }
     if (k < Np) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool isbg = false;
         if (k < Cn) {
             float cm = -INFINITY;
             for (int q = 0; q < planes; ++q) cm = fmaxf(cm, colpart[((size_t)q * B + b) * Np + k]);
             const bool fg = cm > fmaf(bg_b[(size_t)b * Np + k], c2x, -lrs0);  // label2 > 0
+            isbg = !fg;
             if (w2_out) w2_out[(size_t)b * Cn + k] = fg ? 1.f : 0.f;
             if (fg) {
                 const float ic = inv_colsum[(size_t)b * Np + k];
@@ -569,21 +621,94 @@ tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__rest
                 g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
             }
         }
-        G[(size_t)b * Np + k] = g;
+        if (G) G[(size_t)b * Np + k] = g;
+        if (fgcol) fgcol[(size_t)b * Np + k] = isbg ? 0.f : 1.f;
     }
+}
+
+// Two-pass path: pass 2 summed e^2 * G over EVERY column; the columns that turned out to be
+// background (a few per cent) are collected here, in index order, into a compact operand so that a
+// short ragged pass can take their share out again.  gridDim.y blocks per instance: each repeats the
+// (cheap) ordered compaction and copies its share of the rows.
+__global__ void __launch_bounds__(1024)
+tc_bg_gather_kernel(const float *__restrict__ fgcol, int Cn, int Np, int C, int B,
+                    const __nv_bfloat16 *__restrict__ Bm /* (2, B*Np, C) */, const float4 *__restrict__ Gall,
+                    __nv_bfloat16 *__restrict__ Bc /* (2, B*Np, C) */, float4 *__restrict__ Gc,
+                    int *__restrict__ strip_count /* (B) */) {
+    __shared__ int s_list[4096];
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int b = blockIdx.x, tid = threadIdx.x, per = (Np + 1023) / 1024;  // Np <= 4096
+    const int part_id = blockIdx.y, n_parts = gridDim.y;
+    int flags = 0, cnt = 0;
+    for (int u = 0; u < per; ++u) {
+        const int j = tid * per + u;
+        const int isbg = j < Cn && fgcol[(size_t)b * Np + j] == 0.f;
+        flags |= isbg << u;
+        cnt += isbg;
+    }
+    // block-wide exclusive scan of cnt
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane_id() >= o) incl += v;
+    }
+    if (lane_id() == 31) s_warp[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+        int w = s_warp[lane_id()];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, w, o);
+            if (lane_id() >= o) w += v;
+        }
+        s_warp[lane_id()] = w;
+        if (lane_id() == 31) s_total = w;
+    }
+    __syncthreads();
+    int pos = incl - cnt + (warp_id() ? s_warp[warp_id() - 1] : 0);
+    for (int u = 0; u < per; ++u)
+        if (flags >> u & 1) s_list[pos++] = tid * per + u;
+    __syncthreads();
+    const int nbg = s_total, padded = (nbg + TN - 1) / TN * TN;
+    if (tid == 0 && part_id == 0) strip_count[b] = padded / TN;
+    // gather the rows (hi and lo halves, 16 bytes per thread and trip), zero the padding
+    const int v4 = C / 8;  // uint4 per row half
+    const size_t half_rows = (size_t)B * Np;
+    for (int e = part_id * 1024 + tid; e < padded * 2 * v4; e += 1024 * n_parts) {
+        const int q = e / (2 * v4), r = e - q * 2 * v4, part = r / v4, x = r - part * v4;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (q < nbg)
+            val = __ldg(reinterpret_cast<const uint4 *>(Bm + (part * half_rows + (size_t)b * Np + s_list[q]) * C) + x);
+        reinterpret_cast<uint4 *>(Bc + (part * half_rows + (size_t)b * Np + q) * C)[x] = val;
+    }
+    for (int q = part_id * 1024 + tid; q < padded; q += 1024 * n_parts)
+        Gc[(size_t)b * Np + q] = q < nbg ? Gall[(size_t)b * Np + s_list[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // after pass 3: assignment_score and the soft correspondences (MU:324-330)
 __global__ void __launch_bounds__(256)
 tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restrict__ inv_rowsum,
                       const float *__restrict__ w1, int R, int Mp, int n_part,
-                      float *__restrict__ rowsumA, float *__restrict__ pred) {
+                      float *__restrict__ rowsumA, float *__restrict__ pred,
+                      const float *__restrict__ corr4 /* (B,n_part,4,Mp) or null */,
+                      const int *__restrict__ strip_count /* (B): live strips of corr4 */) {
     const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     float a[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = 0; t < n_part; ++t)
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] += rowpart4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
+    if (corr4) {  // take the background columns' share out again (two partials per live strip)
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const int live = 2 * strip_count[b];
+        for (int t = 0; t < live; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] += corr4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] -= c[k];
+    }
     const size_t ri = (size_t)b * R + i;
     const float f = w1[ri] * inv_rowsum[(size_t)b * Mp + i];
     const float sA = a[0] * f;
@@ -632,6 +757,11 @@ struct Ws {
     float *colpart;  // (2*n_msteps, B, Np): column partial planes (sums, then maxima)
     float *bg_a, *bg_b, *s00;  // background column / row of the cosine matrix and their corner
     float *lbg;                // (B,2) log2 of the background row / column sums
+    // two-pass path: row maxima next to the weighted sums, background-column correction
+    float *rowmax, *rowpart_c, *fgcol;
+    float4 *Gall, *Gc;
+    __nv_bfloat16 *Bc;
+    int *strip_count;
     float *inv_rowsum, *lrs, *inv_colsum, *lcs, *w1, *w2, *rowsumA, *pred;
     float4 *G;
     int *counters;
@@ -658,6 +788,13 @@ static Ws carve(void *base, int B, int rows1, int rows2, int C) {
     w.bg_b = (float *)take(B * Np * 4);
     w.s00 = (float *)take(B * 4);
     w.lbg = (float *)take(B * 8);
+    w.rowmax = (float *)take(B * 2 * ns * Mp * 4);
+    w.rowpart_c = (float *)take(B * 2 * ns * 4 * Mp * 4);
+    w.fgcol = (float *)take(B * Np * 4);
+    w.Gall = (float4 *)take(B * Np * 16);
+    w.Gc = (float4 *)take(B * Np * 16);
+    w.Bc = (__nv_bfloat16 *)take(2 * B * Np * C * 2);
+    w.strip_count = (int *)take(B * 4);
     w.inv_rowsum = (float *)take(B * Mp * 4);
     w.lrs = (float *)take(B * Mp * 4);
     w.inv_colsum = (float *)take(B * Np * 4);
@@ -684,6 +821,7 @@ static int num_sms() {
 }
 
 static int g_steps_per_task = 0;  // development knob: 0 = choose automatically
+static int g_fine_passes = 2;     // development knob: 3 = the original three full GEMM passes
 
 // rows1 x rows2 GEMM per instance
 static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp) {
@@ -747,6 +885,7 @@ using namespace pem;
 using namespace pem::tc;
 
 extern "C" void pem_dev_set_fine_steps_per_task(int v) { g_steps_per_task = v; }
+extern "C" void pem_dev_set_fine_passes(int v) { g_fine_passes = v == 3 ? 3 : 2; }
 
 // fine.cu
 namespace pem {
@@ -817,27 +956,53 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
 
     const int mx = max(p.Mp, p.Np);
     const int n_part = 2 * p.n_strips, planes = 2 * p.n_splits;
+    const bool two_pass = g_fine_passes == 2 && p.Np <= 4096;
     // pass 1: softmax statistics
     p.rowpart = w.rowpart;
     p.colpart = w.colpart;
     if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
     tc_finish_stats_kernel<<<dim3((mx + 255) / 256 + 1, B), 256, 0, st>>>(
         w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, w.s00, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
-        w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs, w.lbg);
-    // pass 2: foreground labels
+        w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs, w.lbg, pts2, two_pass ? w.Gall : nullptr);
     p.lrs = w.lrs;
     p.lcs = w.lcs;
-    p.rowmaxpart = w.rowpart;
-    if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
-    tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-        w.rowpart, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
-        planes, p.c1, p.c2, w1, w2_out, w.G);
-    // pass 3: weighted row sums -> correspondences
-    p.G = w.G;
-    p.rowpart4 = w.rowpart;
-    if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
-    tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(w.rowpart, w.inv_rowsum, w1, p.R,
-                                                                     p.Mp, n_part, rsA, pred);
+    if (two_pass) {
+        // pass 2: foreground labels AND the weighted row sums over EVERY column (the column labels
+        // are not known yet; ~96 % of the columns turn out foreground)
+        p.rowmaxpart = w.rowmax;
+        p.G = w.Gall;
+        p.rowpart4 = w.rowpart;
+        if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
+        tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+            w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
+            planes, p.c1, p.c2, w1, w2_out, nullptr, w.fgcol);
+        // the background columns, compacted, and a short ragged pass that takes their share out again
+        tc_bg_gather_kernel<<<dim3(B, 8), 1024, 0, st>>>(w.fgcol, p.Cn, p.Np, C, B, w.Bm, w.Gall, w.Bc, w.Gc,
+                                                w.strip_count);
+        CUtensorMap tmC;
+        if (int rc = make_operand_map(&tmC, w.Bc, (size_t)2 * B * p.Np, C)) return rc;
+        Params pc = p;
+        pc.G = w.Gc;
+        pc.rowpart4 = w.rowpart_c;
+        pc.strip_count = w.strip_count;
+        pc.strip_major = 1;
+        if (int rc = launch_pass<kWsum>(tmA, tmC, pc, st)) return rc;
+        tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
+            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, w.rowpart_c, w.strip_count);
+    } else {
+        // pass 2: foreground labels
+        p.rowmaxpart = w.rowpart;
+        if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
+        tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+            w.rowpart, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
+            planes, p.c1, p.c2, w1, w2_out, w.G, nullptr);
+        // pass 3: weighted row sums -> correspondences
+        p.G = w.G;
+        p.rowpart4 = w.rowpart;
+        if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
+        tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
+            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, nullptr);
+    }
     // weighted Procrustes + pose score (fine.cu)
     return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
                             score, st);
@@ -864,6 +1029,11 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     p.lrs = w.lrs;
     p.lcs = w.lcs;
     p.G = w.G;
+    if (mode == 4) {  // the merged pass of the two-pass path
+        p.rowmaxpart = w.rowmax;
+        p.G = w.Gall;
+        return launch_pass<kLabelW>(tmA, tmB, p, st);
+    }
     return mode == 3 ? launch_pass<kWsum>(tmA, tmB, p, st)
                      : mode == 2 ? launch_pass<kLabel>(tmA, tmB, p, st) : launch_pass<kStats>(tmA, tmB, p, st);
 }
@@ -874,7 +1044,7 @@ extern "C" int pem_fine_fused_pass(const float *f1, const float *f2, int B, int 
     PEM_REQUIRE_PTR(f1);
     PEM_REQUIRE_PTR(f2);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0, PEM_E_SHAPE);
-    PEM_REQUIRE(pass >= 1 && pass <= 3, PEM_E_UNSUPPORTED);
+    PEM_REQUIRE(pass >= 1 && pass <= 4, PEM_E_UNSUPPORTED);
     PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
     return pem_dev_fine_pass(f1, f2, B, N1, N2, C, temp, 0, pass, 0, workspace, workspace_bytes, stream);

@@ -67,3 +67,46 @@ def test_fine_fused_ragged_shapes_and_task_splits(pkg, oracle, dev, B, N1, N2, C
         assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1
         assert (t.cpu() - ot).abs().max().item() < 1e-4
         assert (s.cpu() - os_).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("n_unrelated", [0, 40, 700, 2048])
+def test_fine_fused_two_pass_equals_three_pass(pkg, oracle, dev, n_unrelated):
+    """The default path merges the label pass with the weighted sums over ALL columns and takes the
+    background columns out again with a short ragged pass; the original three full passes stay
+    selectable.  Both must agree with each other and with the oracle for any number of background
+    columns: none, fewer than one 256-wide strip, several strips, (nearly) all of them."""
+    import ctypes
+    g = torch.Generator().manual_seed(n_unrelated + 5)
+    B, N, C = 2, 2048, 128
+    base = torch.randn(B, N + 1, C, generator=g)
+    f1 = (base + 0.3 * torch.randn(B, N + 1, C, generator=g)).contiguous()
+    f2 = (base + 0.3 * torch.randn(B, N + 1, C, generator=g)).contiguous()
+    if n_unrelated:  # observation points whose best match is the background token: they end up background
+        idx = 1 + torch.randperm(N, generator=g)[:n_unrelated]
+        f2[:, idx] = f1[:, 0:1] + 0.2 * torch.randn(B, n_unrelated, C, generator=g)
+    p1 = (0.3 * torch.randn(B, N, 3, generator=g)).contiguous()
+    p2 = (0.3 * torch.randn(B, N, 3, generator=g)).contiguous()
+    model = (0.3 * torch.randn(B, 500, 3, generator=g)).contiguous()
+    L = ctypes.CDLL(pkg._lib.LIB_PATH)
+    out = {}
+    try:
+        for passes in (3, 2):
+            L.pem_dev_set_fine_passes(passes)
+            out[passes] = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), p1.to(dev), p2.to(dev),
+                                                                model.to(dev), 0.1, 0.15, return_stages=True)
+    finally:
+        L.pem_dev_set_fine_passes(2)
+    (R3, t3, s3, st3), (R2, t2, s2, st2) = out[3], out[2]
+    assert torch.equal(st3["w1"], st2["w1"]) and torch.equal(st3["w2"], st2["w2"])
+    n_bg = int((st2["w2"] == 0).sum(1).max().item())
+    assert n_bg >= min(n_unrelated, N) * 0.9, n_bg            # the case exercises what it claims
+    assert (st3["row"] - st2["row"]).abs().max().item() < 2e-6
+    live = st3["row"] > 1e-3                                   # rows that carry weight in the Procrustes
+    assert ((st3["pred"] - st2["pred"]).abs().max(-1)[0] * live).max().item() < 1e-4
+    if n_unrelated < N:
+        assert oracle.rotation_angle_deg(R2.cpu(), R3.cpu()).max().item() < 1e-3
+        atten = oracle.feature_similarity(f1, f2, 0.1)
+        oR, ot, os_, ost = oracle.fine_Rt(atten, p1, p2, model)
+        assert (st2["row"].cpu() - ost["row"]).abs().max().item() < 1e-4
+        assert oracle.rotation_angle_deg(R2.cpu(), oR).max().item() < 0.1
+        assert (t2.cpu() - ot).abs().max().item() < 1e-4

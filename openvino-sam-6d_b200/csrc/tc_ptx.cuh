@@ -182,11 +182,14 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
         "h"((uint16_t)3)
         : "memory");
 }
-// arrive on the barrier at the same shared-memory offset in cluster rank `rank`
+// Arrive on the barrier at the same shared-memory offset in cluster rank `rank`.  RELAXED: it only
+// hands a TMEM accumulator back (its reads were completed by tcgen05.wait::ld and ordered by
+// tcgen05.fence::before_thread_sync); a release at cluster scope would first wait for every global
+// store the thread still has in flight (ERRBAR + MEMBAR: 17 % of the GEMM kernel's stall samples).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     uint32_t raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared address (cute::Sm100MmaPeerBitMask)
 

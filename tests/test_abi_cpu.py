@@ -50,6 +50,17 @@ def test_argument_validation_without_gpu(pkg):
     assert lib.pem_coarse_assign(p, 1, 500, 500, p, p, p, None) == -3   # matrix exceeds the cluster capacity
     assert lib.pem_select_smallest(p, 1, 10, 11, p, None) == -2         # P2 > P1
     assert lib.pem_fine_Rt(p, p, p, p, 1, 8, 8, 8, 0.15, p, p, p, None, None, None, None, None, 0, None) == -4
+    # the tensor-core entry points
+    assert lib.pem_pe_masks_bytes(2, 2048) == 2 * 2048 * 64 * 4
+    assert lib.pem_pe_masks(None, 1, 64, 1e-8, 0.2, 1e-3, 0, p, 64, None) == -1
+    assert lib.pem_pe_masks(p, 1, 8192, 1e-8, 0.2, 1e-3, 0, p, 1 << 30, None) == -3     # cloud does not fit in shared memory
+    assert lib.pem_pe_masks(p, 1, 64, 1e-8, 0.2, 1e-3, 0, p, 8, None) == -4             # mask buffer too small
+    assert lib.pem_pe_group2_masked(p, 1, 64, 1e-8, 0.1, 32, p, 0.2, 64, p, p, 8, None) == -4
+    assert lib.pem_fine_fused(p, p, p, p, p, 1, 8, 8, 100, 8, 0.1, 0.15, p, p, p, None, None, None, None, p, 1 << 30,
+                              None) == -3                                                # C must be a multiple of 64
+    assert lib.pem_fine_fused(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, p, p, p, None, None, None, None, p, 16,
+                              None) == -4
+    assert lib.pem_fine_fused_pass(p, p, 1, 8, 8, 64, 0.1, 7, p, 1 << 30, None) == -3
     assert lib.pem_fps_workspace_bytes(4, 2048) == 0
     assert lib.pem_fps_workspace_bytes(2, 210000) == 0 and lib.pem_fps_workspace_bytes(2, 300000) == 2 * 300000 * 4
     assert lib.pem_fine_workspace_bytes(16, 2048, 2048) > 16 * 2049 * 4 * 6

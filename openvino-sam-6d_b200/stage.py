@@ -171,7 +171,7 @@ class GeometricStage:
             ck(L.pem_fine_fused(p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]),
                                 p(self.model), B, N, N, C, Nm, self.temp, self.dis_thres, p(self.R),
                                 p(self.t), p(self.score), None, None, None, None, p(self.ws),
-                                self.ws_bytes, st), "fine_fused"); n += 9
+                                self.ws_bytes, st), "fine_fused"); n += 10
         else:
             self._enqueue_fine_materialised(); n += 12
         self.stream.wait_stream(self.side)  # join

@@ -436,11 +436,11 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // lo.  The first `skip` rows of every instance (the background token) stay out of the operands; with
 // skip = 1 the warp also leaves the fp32 cosine of its rows with the OTHER set's background
 // token, i.e. the background column (bg_a) / row (bg_b) of the similarity matrix, and their
-// corner s00.  C <= 256 and C % 64 == 0: a lane holds C/32 values of each row in registers
-// (float2 loads, bf16x2 stores: every access of the warp is one contiguous 256 / 128 byte run;
-// both rows' loads are in flight together).  rows_pa and rows_pb are even.
+// corner s00.  C <= 256 and C % 64 == 0: a lane holds up to NQ float4 of each row in registers
+// (16-byte loads, 8-byte bf16x4 stores, every access of the warp one contiguous run; both rows'
+// loads are in flight together).  rows_pa and rows_pb are even.
 constexpr int kPrepRows = 2;
-template <int NIT>  // C / 64: float2 per lane and row
+template <int NQ>  // ceil(C / 128): float4 per lane and row
 __global__ void __launch_bounds__(256, 4)
 tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloat16 *__restrict__ outa,
                const float *__restrict__ fb, int rows_b, int rows_pb, __nv_bfloat16 *__restrict__ outb,
@@ -456,21 +456,32 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
     __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
     if (gr >= B * rows_p) return;
     const int b = gr / rows_p, i0 = gr - b * rows_p, lane = lane_id();  // rows i0, i0+1 of instance b
-    constexpr int nit = NIT;
+    const int nq = C >> 2;  // float4 per row
     float *bg = second ? bg_b : bg_a;
-    // a row as kMaxKC float2 per lane; sum of squares (unreduced)
-    auto load_row = [&](const float *row, float2 (&x)[NIT]) {
+    // a row as NQ float4 per lane (zero beyond the row); sum of squares (unreduced)
+    auto load_row = [&](const float *row, float4 (&x)[NQ]) {
         float s = 0.f;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            x[it] = __ldg(reinterpret_cast<const float2 *>(row) + it * 32 + lane);
+        for (int it = 0; it < NQ; ++it) {
+            const int q = it * 32 + lane;
+            x[it] = q < nq ? __ldg(reinterpret_cast<const float4 *>(row) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             s = fmaf(x[it].x, x[it].x, s);
             s = fmaf(x[it].y, x[it].y, s);
+            s = fmaf(x[it].z, x[it].z, s);
+            s = fmaf(x[it].w, x[it].w, s);
         }
         return s;
     };
     auto inv_of = [&](float ss) { return normalize ? fmaxf(sqrtf(warp_sum(ss)), 1e-12f) : 1.f; };
-    float2 x[kPrepRows][NIT], tk[NIT];
+    auto split_store = [&](float4 v, uint2 *hi, uint2 *lo, int q) {  // 4 values -> bf16 hi / lo, 8 bytes each
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y),
+                             l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+        hi[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+        lo[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+    };
+    float4 x[kPrepRows][NQ], tk[NQ];
     float ss[kPrepRows];
 #pragma unroll
     for (int r = 0; r < kPrepRows; ++r) {
@@ -483,12 +494,13 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
 #pragma unroll
     for (int r = 0; r < kPrepRows; ++r) {
         const int i = i0 + r;
-        __nv_bfloat162 *hi = reinterpret_cast<__nv_bfloat162 *>(out + (size_t)(gr + r) * C),
-                       *lo = reinterpret_cast<__nv_bfloat162 *>(out + ((size_t)B * rows_p + gr + r) * C);
+        uint2 *hi = reinterpret_cast<uint2 *>(out + (size_t)(gr + r) * C),
+              *lo = reinterpret_cast<uint2 *>(out + ((size_t)B * rows_p + gr + r) * C);
         if (i >= rows) {  // padding rows
-            for (int it = 0; it < nit; ++it) {
-                hi[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
-                lo[it * 32 + lane] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < NQ; ++it) {
+                const int q = it * 32 + lane;
+                if (q < nq) { hi[q] = make_uint2(0u, 0u); lo[q] = make_uint2(0u, 0u); }
             }
             if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
             continue;
@@ -498,24 +510,29 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
         const float rinv = 1.0f / inv_of(ss[r]);
         float dot = 0.f;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            float2 v = x[r][it];
-            if (normalize) { v.x *= rinv; v.y *= rinv; }
-            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-            const float2 hf = __bfloat1622float2(h);
-            hi[it * 32 + lane] = h;
-            lo[it * 32 + lane] = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
-            if (skip) { dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot); }
+        for (int it = 0; it < NQ; ++it) {
+            const int q = it * 32 + lane;
+            if (q >= nq) continue;
+            float4 v = x[r][it];
+            if (normalize) { v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv; }
+            split_store(v, hi, lo, q);
+            if (skip) {
+                dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot);
+                dot = fmaf(v.z, tk[it].z, dot); dot = fmaf(v.w, tk[it].w, dot);
+            }
         }
         if (!skip) continue;
         dot = __fdiv_rn(warp_sum(dot), inv_tok);
         if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
         if (!second && i == 0) {  // the corner: background token x background token
-            float2 own[NIT];
+            float4 own[NQ];
             const float inv_own = inv_of(load_row(f + (size_t)b * (rows + skip) * C, own));
             float d0 = 0.f;
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) { d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0); }
+            for (int it = 0; it < NQ; ++it) {
+                d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0);
+                d0 = fmaf(own[it].z, tk[it].z, d0); d0 = fmaf(own[it].w, tk[it].w, d0);
+            }
             d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
             if (lane == 0) s00[b] = d0;
         }
@@ -858,12 +875,8 @@ static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const fl
     auto go = [&](auto kern) {
         kern<<<grid, 256, 0, st>>>(f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip, bg_a, bg_b, s00);
     };
-    switch (C >> 6) {
-        case 1: go(tc_prep_kernel<1>); break;
-        case 2: go(tc_prep_kernel<2>); break;
-        case 3: go(tc_prep_kernel<3>); break;
-        default: go(tc_prep_kernel<4>); break;
-    }
+    if (C <= 128) go(tc_prep_kernel<1>);
+    else go(tc_prep_kernel<2>);
 }
 
 template <int MODE>
@@ -908,6 +921,7 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
     PEM_REQUIRE_PTR(f2);
     PEM_REQUIRE_PTR(atten);
     PEM_REQUIRE(B > 0 && N1p > 0 && N2p > 0 && C > 0, PEM_E_SHAPE);
+    PEM_REQUIRE((uintptr_t)f1 % 16 == 0 && (uintptr_t)f2 % 16 == 0, PEM_E_UNSUPPORTED);  // 16-byte row loads
     Params p{};
     if (int rc = fill_common(p, B, N1p, N2p, C, temp)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
@@ -938,6 +952,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     PEM_REQUIRE_PTR(t);
     PEM_REQUIRE_PTR(score);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
+    PEM_REQUIRE((uintptr_t)f1 % 16 == 0 && (uintptr_t)f2 % 16 == 0, PEM_E_UNSUPPORTED);  // 16-byte row loads
     Params p{};
     if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;  // the background token stays out of the GEMM
     PEM_REQUIRE(workspace != nullptr &&

@@ -57,13 +57,9 @@ namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 64;  // per-CTA operand tile; BK bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int TM = 2 * BM, TN = 2 * BN;     // rows per step / columns per strip of a CTA pair
-constexpr int WC = TN / 2;                  // accumulator columns per epilogue warp
 constexpr int kChunkBytes = BM * BK * 2;    // 16 KB
 constexpr int kStages = 5;
 constexpr int kMaxKC = 4;                   // C <= 256
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 2 * TN;      // double-buffered 128 x 256 accumulator: all of TMEM
 
 enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3, kLabelW = 4 };  // kLabelW = kLabel + kWsum in one pass
@@ -80,7 +76,7 @@ struct Params {
     float *atten;
     int off;
     // kStats
-    float *rowpart;        // (B, 2*n_strips, Mp): row sums per column half-strip
+    float *rowpart;        // (B, parts*n_strips, Mp): row sums per column part of a strip (parts = 2, or 4 in kLabelW)
     float *colpart;        // (2*n_splits, B, Np): column sums (kStats) / maxima (kLabel) per plane
     // kLabel (log2 domain)
     const float *lrs;      // (B,Mp)  log2(rowsum_i); +inf for padded rows
@@ -107,9 +103,16 @@ struct Smem {
     uint32_t tmem_base;
 };
 
+template <int THREADS>
 __device__ __forceinline__ void epi_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 }
+
+// Epilogue warps per CTA: two per TMEM lane quadrant (128 accumulator columns each).  (Four per
+// quadrant were tried for the merged label + weighted-sum pass, whose epilogue does two jobs per
+// element and holds the tensor pipe at 76 %: 71 us instead of 69 us -- the extra barrier traffic
+// costs more than the latency hiding gains.  The kernel is written for either.)
+__host__ __device__ constexpr int epi_warps(int /*mode*/) { return 8; }
 
 struct Task {
     int b, n, m0, m1;  // instance, column strip, row steps [m0, m1)
@@ -130,10 +133,13 @@ __device__ __forceinline__ Task decode_task(const Params &p, int task) {
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * epi_warps(MODE), 1)
 fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const Params p) {
     constexpr uint32_t kIdesc = make_idesc(TM, TN);
+    constexpr int EPW = epi_warps(MODE), EPT = 32 * EPW;  // epilogue warps / threads
+    constexpr int NPW = EPW / 4;                          // column parts of a strip (one per warp of a quadrant)
+    constexpr int WC = TN / NPW;                          // accumulator columns per epilogue warp
 
     extern __shared__ uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -153,7 +159,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&sm.tmem_full[a]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[a]), 2 * kEpiWarps);  // one arrival per epilogue warp of the pair
+            mbar_init(smem_u32(&sm.tmem_empty[a]), 2 * EPW);  // one arrival per epilogue warp of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -277,9 +283,9 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ================================ epilogue ====================================
         const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
-        const int half = (warp - 2) >> 2;          // columns [WC*half, WC*half+WC) of the tile
+        const int half = (warp - 2) >> 2;          // column part: columns [WC*half, WC*half+WC) of the tile
         const int et = quad * 32 + lane;           // row of this CTA's 128 rows owned by this thread
-        const int ep_tid = (warp - 2) * 32 + lane; // 0..255
+        const int ep_tid = (warp - 2) * 32 + lane; // 0..EPT-1
         const float kc1 = p.c1, kc2 = p.c2, kc2x = 2.0f * p.c1, ktemp = p.temp;
         constexpr bool LAB = (MODE == kLabel || MODE == kLabelW);  // label maxima
         constexpr bool WS = (MODE == kWsum || MODE == kLabelW);    // weighted row sums
@@ -303,9 +309,9 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int q = 0; q < WC / 32; ++q) cmx[q] = -INFINITY;
             // per-column constants of the task (+inf keeps padded columns out of the row max)
-            if (LAB) sm.colc[ep_tid] = p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
-            if (WS) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * TN + ep_tid];
-            if (LAB || WS) epi_barrier();
+            if (LAB && ep_tid < TN) sm.colc[ep_tid] = p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
+            if (WS && ep_tid < TN) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * TN + ep_tid];
+            if (LAB || WS) epi_barrier<EPT>();
 
             for (int m = t.m0; m < t.m1; ++m) {
                 const int gi = m * TM + crank * BM + et;
@@ -387,7 +393,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive_remote(smem_u32(&sm.tmem_empty[acc]), 0);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // per-(row, half-strip) partials: consecutive lanes = consecutive rows
-                const size_t pr = ((size_t)b * 2 * p.n_strips + 2 * n + half);
+                const size_t pr = ((size_t)b * NPW * p.n_strips + NPW * n + half);
                 if (MODE == kStats) p.rowpart[pr * p.Mp + gi] = r0;
                 if (LAB) p.rowmaxpart[pr * p.Mp + gi] = rm;
                 if (WS) {
@@ -409,15 +415,17 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         sm.colred[quad][half * WC + c * 32 + lane] = cmx[c];
                     }
                 }
-                epi_barrier();
-                float s = sm.colred[0][ep_tid];
+                epi_barrier<EPT>();
+                if (ep_tid < TN) {
+                    float s = sm.colred[0][ep_tid];
 #pragma unroll
-                for (int w = 1; w < 4; ++w)
-                    s = LAB ? fmaxf(s, sm.colred[w][ep_tid]) : s + sm.colred[w][ep_tid];
-                const int plane = 2 * (t.m0 / p.spt) + crank;
-                p.colpart[((size_t)plane * p.B + b) * p.Np + n * TN + ep_tid] = s;
+                    for (int w = 1; w < 4; ++w)
+                        s = LAB ? fmaxf(s, sm.colred[w][ep_tid]) : s + sm.colred[w][ep_tid];
+                    const int plane = 2 * (t.m0 / p.spt) + crank;
+                    p.colpart[((size_t)plane * p.B + b) * p.Np + n * TN + ep_tid] = s;
+                }
             }
-            epi_barrier();  // shared per-task constants / colred are reused by the next task
+            epi_barrier<EPT>();  // shared per-task constants / colred are reused by the next task
         }
     }
 
@@ -709,7 +717,7 @@ __global__ void __launch_bounds__(256)
 tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restrict__ inv_rowsum,
                       const float *__restrict__ w1, int R, int Mp, int n_part,
                       float *__restrict__ rowsumA, float *__restrict__ pred,
-                      const float *__restrict__ corr4 /* (B,n_part,4,Mp) or null */,
+                      const float *__restrict__ corr4 /* (B,n_part_c,4,Mp) or null */, int n_part_c,
                       const int *__restrict__ strip_count /* (B): live strips of corr4 */) {
     const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
@@ -722,7 +730,7 @@ tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restric
         const int live = 2 * strip_count[b];
         for (int t = 0; t < live; ++t)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] += corr4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
+            for (int k = 0; k < 4; ++k) c[k] += corr4[(((size_t)b * n_part_c + t) * 4 + k) * Mp + i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] -= c[k];
     }
@@ -770,7 +778,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, size_t rows, int
 
 struct Ws {
     __nv_bfloat16 *A, *Bm;
-    float *rowpart;  // (B, 2*n_strips, 4, Mp): the largest of the per-pass row partial layouts
+    float *rowpart;  // (B, 4*n_strips, 4, Mp): the largest of the per-pass row partial layouts
     float *colpart;  // (2*n_msteps, B, Np): column partial planes (sums, then maxima)
     float *bg_a, *bg_b, *s00;  // background column / row of the cosine matrix and their corner
     float *lbg;                // (B,2) log2 of the background row / column sums
@@ -799,13 +807,13 @@ static Ws carve(void *base, int B, int rows1, int rows2, int C) {
     Ws w;
     w.A = (__nv_bfloat16 *)take(2 * B * Mp * C * 2);
     w.Bm = (__nv_bfloat16 *)take(2 * B * Np * C * 2);
-    w.rowpart = (float *)take(B * 2 * ns * 4 * Mp * 4);
+    w.rowpart = (float *)take(B * 4 * ns * 4 * Mp * 4);  // up to 4 column parts per strip
     w.colpart = (float *)take(2 * nm * B * Np * 4);
     w.bg_a = (float *)take(B * Mp * 4);
     w.bg_b = (float *)take(B * Np * 4);
     w.s00 = (float *)take(B * 4);
     w.lbg = (float *)take(B * 8);
-    w.rowmax = (float *)take(B * 2 * ns * Mp * 4);
+    w.rowmax = (float *)take(B * 4 * ns * Mp * 4);
     w.rowpart_c = (float *)take(B * 2 * ns * 4 * Mp * 4);
     w.fgcol = (float *)take(B * Np * 4);
     w.Gall = (float4 *)take(B * Np * 16);
@@ -881,7 +889,7 @@ static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const fl
 
 template <int MODE>
 static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
-    static_assert(kEpiThreads == TN, "one epilogue thread per strip column");
+    constexpr int kThreads = 64 + 32 * epi_warps(MODE);
     const size_t smem = sizeof(Smem) + 1024;
     static size_t cached = 0;
     if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE>, smem, &cached)) return rc;
@@ -988,8 +996,9 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         p.G = w.Gall;
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
+        const int n_part_m = (epi_warps(kLabelW) / 4) * p.n_strips;  // row partials of the merged pass
         tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
-            w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
+            w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part_m,
             planes, p.c1, p.c2, w1, w2_out, nullptr, w.fgcol);
         // the background columns, compacted, and a short ragged pass that takes their share out again
         tc_bg_gather_kernel<<<dim3(B, 8), 1024, 0, st>>>(w.fgcol, p.Cn, p.Np, C, B, w.Bm, w.Gall, w.Bc, w.Gc,
@@ -1003,7 +1012,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         pc.strip_major = 1;
         if (int rc = launch_pass<kWsum>(tmA, tmC, pc, st)) return rc;
         tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
-            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, w.rowpart_c, w.strip_count);
+            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part_m, rsA, pred, w.rowpart_c, n_part, w.strip_count);
     } else {
         // pass 2: foreground labels
         p.rowmaxpart = w.rowpart;
@@ -1016,7 +1025,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
         tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
-            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, nullptr);
+            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, 0, nullptr);
     }
     // weighted Procrustes + pose score (fine.cu)
     return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,

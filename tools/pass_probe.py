@@ -1,5 +1,5 @@
 """Timing experiments on one fine GEMM pass: which role bounds it?
-flags: 1 no MMAs, 2 no streamed TMA loads, 4 no epilogue math.  mode: 1 stats, 2 label, 3 wsum."""
+flags: 1 no MMAs, 2 no streamed TMA loads, 4 no epilogue math.  mode: 1 stats, 4 label + wsum (the merged pass), 2 label, 3 wsum."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,7 +27,7 @@ assert rc == 0, rc
 torch.cuda.synchronize()
 for spt in (0,):
     L.pem_dev_set_fine_steps_per_task(spt)
-    for mode in (1, 2, 3):
+    for mode in (1, 4, 2, 3):  # statistics, labels + weighted sums (merged), labels, weighted sums
         for flags in (0, 4, 2, 6, 7):
             def run(prep=0):
                 rc = L.pem_dev_fine_pass(f1.data_ptr(), f2.data_ptr(), B, N, N, C, 0.1, flags, mode, prep, ws.data_ptr(), nb, st)

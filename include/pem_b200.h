@@ -280,6 +280,19 @@ int pem_weighted_procrustes(const float *src, const float *ref, const float *wei
                             pem_stream_t stream);
 
 /*
+ * GeometricStructureEmbedding.get_embedding_indices (model/transformer.py:304-341):
+ * indices of the pair-wise distance embedding and of the triplet-wise angular embedding of the coarse
+ * transformer, straight from the sparse points:
+ *   d_indices (B,N,N)   = sqrt(pairwise_distance(points, points)) / sigma_d           (:321-322)
+ *   a_indices (B,N,N,k) = atan2(|r x a|, r.a) * 180 / (sigma_a * pi) with r = knn_l(i) - p_i, a = p_j - p_i,
+ *                         knn = entries 1..k of the k+1 smallest distances of row i, sin clamped at 1e-8
+ *                         and the dot product to [-1,1] as the reference does (:325-343)
+ * Ties between equal distances go to the lower index.  angle_k <= 8, N <= 8192.
+ */
+int pem_geo_embedding_indices(const float *points, int B, int N, int angle_k, float sigma_d,
+                              float sigma_a, float *d_indices, float *a_indices, pem_stream_t stream);
+
+/*
  * Pack the per-instance result into the 64-byte record the multi-GPU gather moves
  * (no reference counterpart): records (B,16) fp32 = R (9) | t (3) | pose_score |
  * proposal id | instance id | 0.  proposal_id and instance_id may be NULL.

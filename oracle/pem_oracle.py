@@ -306,6 +306,33 @@ def fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15):
 # --------------------------------------------------------------------------
 # comparison helpers shared by tests, smoke() and bench
 # --------------------------------------------------------------------------
+def geo_embedding_indices(points, sigma_d=0.2, sigma_a=15.0, angle_k=3):
+    """GeometricStructureEmbedding.get_embedding_indices (model/transformer.py:304-341): indices of
+    the pair-wise distance embedding and of the triplet-wise angular embedding.
+
+    points (B,N,3) -> d_indices (B,N,N) = dist / sigma_d, a_indices (B,N,N,k) = angle * 180/(sigma_a*pi),
+    angle between (knn_l(i) - p_i) and (p_j - p_i); the k nearest neighbours are entries 1..k of the
+    (k+1) smallest distances of row i (:324), sin clamped at 1e-8 and the raw dot product clamped to
+    (-1+1e-8, 1-1e-8), i.e. [-1, 1] in fp32 (:338-340).
+    """
+    points = _t(points).float()
+    B, N, _ = points.shape
+    dist = torch.sqrt(sq_pairwise(points, points))                                   # :321
+    d_indices = dist / sigma_d                                                       # :322
+    k = angle_k
+    knn = dist.topk(k=k + 1, dim=2, largest=False)[1][:, :, 1:]                      # :325 (B,N,k)
+    knn_points = torch.gather(points.unsqueeze(1).expand(B, N, N, 3), 2, knn.unsqueeze(3).expand(B, N, k, 3))
+    ref = (knn_points - points.unsqueeze(2)).unsqueeze(2).expand(B, N, N, k, 3)      # :329,331
+    anc = (points.unsqueeze(1) - points.unsqueeze(2)).unsqueeze(3).expand(B, N, N, k, 3)  # :330,332
+    sin_v = torch.linalg.norm(torch.cross(ref, anc, dim=-1), dim=-1)                 # :333
+    cos_v = torch.sum(ref * anc, dim=-1)                                             # :334
+    eps = 1e-8
+    sin_v = torch.clamp(sin_v, min=eps)                                              # :339
+    cos_v = torch.clamp(cos_v, min=-1.0 + eps, max=1.0 - eps)                        # :340
+    a_indices = torch.atan2(sin_v, cos_v) * (180.0 / (sigma_a * np.pi))              # :342-343
+    return d_indices, a_indices, knn
+
+
 def rotation_angle_deg(Ra, Rb):
     """Geodesic angle via the chord formula 2*asin(||Ra-Rb||_F / (2*sqrt(2))) in fp64
     (fp32 acos((tr-1)/2) bottoms out near 0.03 deg)."""

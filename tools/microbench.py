@@ -106,6 +106,30 @@ byts = 2 * B * 6 * 2048 * 96 * 4
 row("pe_group2 32 clouds (both PE scales)", ms, gflops=flop / ms / 1e6, frac_fp32_lane_peak=flop / ms / 1e9 / FP32_OPS,
     out_gbs=byts / ms / 1e6)
 
+masks = pu.pe_masks(both)
+ms_f = timeit(lambda: pu.pe_masks(both))
+ms_g = timeit(lambda: pu.pe_group2_masked(both, masks))
+row("pe_masks 32 clouds (tensor-core candidate filter)", ms_f, pairs_per_sec=2 * B * 2048 * 2048 / ms_f * 1e3)
+row("pe_group2_masked 32 clouds (exact re-test + output)", ms_g, out_gbs=byts / ms_g / 1e6)
+
+# ------------------------------------------------------------------ SURVEY 8f "next" rows
+# rank 2: template-side FPS at object load, 1 x 210000 -> 2048 (feature_extraction.py:152-158)
+big = ellipsoid_clouds(1, 210000, 5).to(dev)
+ms = timeit(lambda: ext.furthest_point_sampling(big, 2048), iters=3, warm=1)
+flop = 2047 * 210000 * 10
+row("fps 1x210000->2048 (object load, 16-CTA cluster)", ms, gflops=flop / ms / 1e6,
+    frac_fp32_lane_peak=flop / ms / 1e9 / FP32_OPS)
+# rank 3: GeometricStructureEmbedding.get_embedding_indices on the sparse points (transformer.py:304-341)
+sp32 = torch.randn(2 * B, 197, 3, device=dev) * 0.4
+ms = timeit(lambda: pkg.transformer.get_embedding_indices(sp32))
+row("geo_embedding_indices 32x197 (d (N,N) + a (N,N,3))", ms, out_gbs=2 * B * 197 * 197 * 16 / ms / 1e6)
+import time as _time
+cpu_pts = sp32[:4].cpu()
+t0 = _time.perf_counter()
+O.geo_embedding_indices(cpu_pts)
+row("geo_embedding_indices reference arithmetic on CPU, 4x197 (torch, all host threads)",
+    (_time.perf_counter() - t0) * 1e3)
+
 # ------------------------------------------------------------------ configs[3]: scoring sweep
 sp, sf, _ = mu.sample_pts_feats(pm, b["dense_fm"], 196, True)
 tp, tf, _ = mu.sample_pts_feats(po, b["dense_fo"], 196, True)

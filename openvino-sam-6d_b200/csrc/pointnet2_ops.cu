@@ -552,7 +552,8 @@ template <bool CLOUD_IN_SMEM, bool MASKED>
 __global__ void __launch_bounds__(kPeThreads)
 pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int ns1,
                  float *__restrict__ out1, float r2b, int ns2, float *__restrict__ out2,
-                 const uint32_t *__restrict__ cmask, int W) {
+                 const uint32_t *__restrict__ cmask, int W, int32_t *__restrict__ idx1 /* (B,N,ns1) or null */,
+                 int32_t *__restrict__ idx2 /* (B,N,ns2) or null */) {
     extern __shared__ float4 s_dyn[];
     const int n_pts_smem = CLOUD_IN_SMEM ? (N + kPeTile - 1) / kPeTile * kPeTile : kPeTile;
     float4 *s_pts = s_dyn;                                                   // n_pts_smem
@@ -688,6 +689,11 @@ pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int
     for (int s = 0; s < 2; ++s) {
         const int nss = s ? ns2 : ns1, stride = s ? st2 : st1;
         const unsigned short *rw = s ? rows2 : rows1;
+        if (int32_t *io = s ? idx2 : idx1) {  // the neighbour lists themselves (ball_query's output)
+            int32_t *ib = io + ((size_t)b * N + j0) * nss;
+            for (int e = tid; e < rows * nss; e += kPeThreads) ib[e] = rw[(e / nss) * stride + e % nss];
+        }
+        if ((s ? out2 : out1) == nullptr) continue;
         const size_t plane = (size_t)N * nss;
         float *out_b = (s ? out2 : out1) + (size_t)b * 6 * plane + (size_t)j0 * nss;
         const bool pow2 = (nss & (nss - 1)) == 0;
@@ -876,13 +882,13 @@ extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, f
         if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true, false>, smem, &cached)) return rc;
         pe_group2_kernel<true, false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
             xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
-            nullptr, 0);
+            nullptr, 0, nullptr, nullptr);
     } else {
         static size_t cached = 0;
         if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<false, false>, smem, &cached)) return rc;
         pe_group2_kernel<false, false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
             xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
-            nullptr, 0);
+            nullptr, 0, nullptr, nullptr);
     }
     return pem_launch_status();
 }
@@ -908,12 +914,10 @@ extern "C" int pem_pe_masks(const float *xyz, int B, int N, float centre_eps, fl
                              pem_cu_stream(stream));
 }
 
-extern "C" int pem_pe_group2_masked(const float *xyz, int B, int N, float centre_eps, float radius1,
-                                    int nsample1, float *out1, float radius2, int nsample2, float *out2,
-                                    const void *masks, size_t masks_bytes, pem_stream_t stream) {
+static int pe_masked_launch(const float *xyz, int B, int N, float centre_eps, float radius1, int nsample1,
+                            float *out1, int32_t *idx1, float radius2, int nsample2, float *out2, int32_t *idx2,
+                            const void *masks, size_t masks_bytes, pem_stream_t stream) {
     PEM_REQUIRE_PTR(xyz);
-    PEM_REQUIRE_PTR(out1);
-    PEM_REQUIRE_PTR(out2);
     PEM_REQUIRE_PTR(masks);
     PEM_REQUIRE(B > 0 && N > 0 && nsample1 > 0 && nsample2 > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(nsample1 <= 128 && nsample2 <= 128 && N <= 4096, PEM_E_UNSUPPORTED);  // cloud in smem
@@ -926,8 +930,27 @@ extern "C" int pem_pe_group2_masked(const float *xyz, int B, int N, float centre
     pe_group2_kernel<true, true><<<dim3((N + kPeCentres - 1) / kPeCentres, B), kPeThreads, smem,
                                   pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,
                                                            radius2 * radius2, nsample2, out2,
-                                                           (const uint32_t *)masks, (N + 31) / 32);
+                                                           (const uint32_t *)masks, (N + 31) / 32, idx1, idx2);
     return pem_launch_status();
+}
+
+extern "C" int pem_pe_group2_masked(const float *xyz, int B, int N, float centre_eps, float radius1,
+                                    int nsample1, float *out1, float radius2, int nsample2, float *out2,
+                                    const void *masks, size_t masks_bytes, pem_stream_t stream) {
+    PEM_REQUIRE_PTR(out1);
+    PEM_REQUIRE_PTR(out2);
+    return pe_masked_launch(xyz, B, N, centre_eps, radius1, nsample1, out1, nullptr, radius2, nsample2, out2,
+                            nullptr, masks, masks_bytes, stream);
+}
+
+extern "C" int pem_pe_neighbours_masked(const float *xyz, int B, int N, float centre_eps, float radius1,
+                                        int nsample1, int32_t *idx1, float radius2, int nsample2,
+                                        int32_t *idx2, const void *masks, size_t masks_bytes,
+                                        pem_stream_t stream) {
+    PEM_REQUIRE_PTR(idx1);
+    PEM_REQUIRE_PTR(idx2);
+    return pe_masked_launch(xyz, B, N, centre_eps, radius1, nsample1, nullptr, idx1, radius2, nsample2, nullptr,
+                            idx2, masks, masks_bytes, stream);
 }
 
 // 64-byte per-instance pose records (R 9 | t 3 | score | proposal id | instance id | pad): the

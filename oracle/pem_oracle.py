@@ -333,6 +333,37 @@ def geo_embedding_indices(points, sigma_d=0.2, sigma_a=15.0, angle_k=3):
     return d_indices, a_indices, knn
 
 
+def pe_shared_mlp_amax(grouped, layers):
+    """PositionalEncoding's per-scale branch after the grouping (model/fine_point_matching.py:131-133,
+    139-141): SharedMLP([6,32,64,128], bn=True) = three times [1x1 Conv2d without bias ->
+    BatchNorm2d (eval) -> ReLU] (pointnet2/pytorch_utils.py:25-50,80-134), then amax over the
+    neighbours.  grouped (B,6,N,ns); layers = [(conv_w (Co,Ci), bn_w, bn_b, run_mean, run_var, eps)] * 3
+    -> (B,128,N)."""
+    x = _t(grouped).float()
+    for (w, g, b, m, v, eps) in layers:
+        w, g, b, m, v = (_t(z).float() for z in (w, g, b, m, v))
+        x = torch.nn.functional.conv2d(x, w.reshape(w.shape[0], w.shape[1], 1, 1))
+        x = torch.nn.functional.batch_norm(x, m, v, g, b, False, 0.0, float(eps))
+        x = torch.relu(x)
+    return torch.amax(x, dim=3)
+
+
+def positional_encoding(pts, branch1, branch2, w3, b3, r1=0.1, ns1=32, r2=0.2, ns2=64):
+    """PositionalEncoding.forward (model/fine_point_matching.py:113-144) on one cloud: both
+    QueryAndGroup scales with centre = pts + 1e-8, the two SharedMLP + amax branches, concatenation
+    and the final Conv1d(256, out_dim) without activation.  pts (B,N,3) -> (B,N,out_dim)."""
+    pts = _t(pts).float().contiguous()
+    ctr = (pts + 0.00000001).contiguous()
+    feat = pts.transpose(1, 2).contiguous()
+    g1, _ = query_and_group(pts.numpy(), ctr.numpy(), feat.numpy(), r1, ns1)
+    g2, _ = query_and_group(pts.numpy(), ctr.numpy(), feat.numpy(), r2, ns2)
+    f1 = pe_shared_mlp_amax(torch.from_numpy(g1), branch1)
+    f2 = pe_shared_mlp_amax(torch.from_numpy(g2), branch2)
+    x = torch.cat([f1, f2], dim=1)                                                   # (B,256,N)
+    y = torch.nn.functional.conv1d(x, _t(w3).float().reshape(w3.shape[0], w3.shape[1], 1), _t(b3).float())
+    return y.transpose(1, 2), f1, f2
+
+
 def rotation_angle_deg(Ra, Rb):
     """Geodesic angle via the chord formula 2*asin(||Ra-Rb||_F / (2*sqrt(2))) in fp64
     (fp32 acos((tr-1)/2) bottoms out near 0.03 deg)."""

@@ -130,6 +130,45 @@ O.geo_embedding_indices(cpu_pts)
 row("geo_embedding_indices reference arithmetic on CPU, 4x197 (torch, all host threads)",
     (_time.perf_counter() - t0) * 1e3)
 
+# rank 1: PositionalEncoding front end (fine_point_matching.py:102-144): groups -> SharedMLP -> amax, fused
+PE = pkg.positional_encoding
+gen = torch.Generator().manual_seed(0)
+def _branch():
+    layers, ci = [], 6
+    for co in (32, 64, 128):
+        layers.append((torch.randn(co, ci, generator=gen) * (2.0 / ci) ** 0.5, 0.5 + torch.rand(co, generator=gen),
+                       0.3 * torch.randn(co, generator=gen), 0.2 * torch.randn(co, generator=gen),
+                       0.5 + torch.rand(co, generator=gen), 1e-5))
+        ci = co
+    return layers
+L1, L2 = _branch(), _branch()
+br1, br2 = [tuple(t.to(dev) for t in PE.fold_branch(L)) for L in (L1, L2)]
+w3pe, b3pe = (torch.randn(256, 256, generator=gen) * 0.05).to(dev), torch.randn(256, generator=gen).to(dev)
+pooled = torch.empty(2 * B, 2048, 256, device=dev)
+i1, i2 = PE.pe_neighbours(both, masks)
+ms1 = timeit(lambda: PE.pe_branch(both, i1, br1, pooled, 0))
+ms2 = timeit(lambda: PE.pe_branch(both, i2, br2, pooled, 128))
+fl = lambda ns: 2.0 * 2 * B * 2048 * ns * (6 * 32 + 32 * 64 + 64 * 128)
+row("pe_mlp branch ns=32, 32 clouds (group+SharedMLP+amax fused, split-bf16 tcgen05)", ms1, algorithmic_tflops=fl(32) / ms1 / 1e9,
+    executed_mma_tflops=3 * fl(32) / ms1 / 1e9)
+row("pe_mlp branch ns=64, 32 clouds", ms2, algorithmic_tflops=fl(64) / ms2 / 1e9, executed_mma_tflops=3 * fl(64) / ms2 / 1e9)
+ms = timeit(lambda: PE.positional_encoding(both, br1, br2, w3pe, b3pe, masks=masks))
+row("positional_encoding 32 clouds end to end (neighbour lists + 2 branches + Linear 256)", ms)
+def _torch_pe():  # the reference's formulation in plain PyTorch fp32 on the same GPU (grouped tensor + conv2d + bn + relu + amax)
+    g1, g2 = pu.pe_group2_masked(both, masks)
+    outs = []
+    for grp, layers in ((g1, L1), (g2, L2)):
+        x = grp
+        for (w, gw, gb, rm, rv, eps) in layers:
+            x = torch.nn.functional.conv2d(x, w.to(dev).reshape(w.shape[0], w.shape[1], 1, 1))
+            x = torch.relu(torch.nn.functional.batch_norm(x, rm.to(dev), rv.to(dev), gw.to(dev), gb.to(dev), False, 0.0, eps))
+        outs.append(torch.amax(x, dim=3))
+    return torch.nn.functional.conv1d(torch.cat(outs, 1), w3pe[:, :, None], b3pe)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+ms = timeit(_torch_pe, iters=3, warm=2)
+row("positional_encoding 32 clouds, plain PyTorch fp32 (grouped tensor materialised, cuDNN convs)", ms)
+
 # ------------------------------------------------------------------ configs[3]: scoring sweep
 sp, sf, _ = mu.sample_pts_feats(pm, b["dense_fm"], 196, True)
 tp, tf, _ = mu.sample_pts_feats(po, b["dense_fo"], 196, True)

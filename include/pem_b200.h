@@ -286,11 +286,12 @@ int pem_weighted_procrustes(const float *src, const float *ref, const float *wei
  *                             ball_query(radius_s, nsample_s, xyz, xyz + centre_eps) for s in {1,2}
  *                             (bit-identical), through the candidate masks of pem_pe_masks;
  *   pem_pe_mlp                one PE branch: (neighbour - centre | neighbour) -> SharedMLP [6,32,64,128]
- *                             (1x1 conv without bias, BatchNorm in eval mode folded into scale / shift,
- *                             ReLU; pointnet2/pytorch_utils.py:25-50,80-134) -> amax over the
+ *                             (1x1 conv without bias, BatchNorm in eval mode, ReLU;
+ *                             pointnet2/pytorch_utils.py:25-50,80-134) -> amax over the
  *                             neighbours (fine_point_matching.py:131-133), as three chained split-bf16
  *                             tcgen05 GEMMs per 128 (centre, neighbour) rows.
- * w1 (32,6), w2 (64,32), w3 (128,64) row-major; scale, shift (224) = the three layers' channels back to
+ * w1 (32,6), w2 (64,32), w3 (128,64) row-major WITH the BatchNorm scale g / sqrt(var + eps) of their
+ * output channel multiplied in; shift (224) = b - mean * scale of the three layers' channels back to
  * back; out (B,N,ldo) point-major, this branch in channels [ch_off, ch_off+128) -- two calls fill the
  * (B,N,256) input of the final Conv1d(256, out_dim) = Linear.  nsample in {32, 64, 128}, N <= 4096.
  */
@@ -298,8 +299,8 @@ int pem_pe_neighbours_masked(const float *xyz, int B, int N, float centre_eps, f
                              int nsample1, int32_t *idx1, float radius2, int nsample2, int32_t *idx2,
                              const void *masks, size_t masks_bytes, pem_stream_t stream);
 int pem_pe_mlp(const float *xyz, const int32_t *idx, int B, int N, int nsample, float centre_eps,
-               const float *w1, const float *w2, const float *w3, const float *scale,
-               const float *shift, float *out, int ldo, int ch_off, pem_stream_t stream);
+               const float *w1, const float *w2, const float *w3, const float *shift, float *out,
+               int ldo, int ch_off, pem_stream_t stream);
 
 /*
  * GeometricStructureEmbedding.get_embedding_indices (model/transformer.py:304-341):

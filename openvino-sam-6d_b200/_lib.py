@@ -51,7 +51,7 @@ SIGNATURES = {
     "pem_pe_group2_masked": (c_i, [c_p, c_i, c_i, c_f, c_f, c_i, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "pem_fine_fused_pass": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_sz, c_p]),
     "pem_pe_neighbours_masked": (c_i, [c_p, c_i, c_i, c_f, c_f, c_i, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),
-    "pem_pe_mlp": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "pem_pe_mlp": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
     "pem_geo_embedding_indices": (c_i, [c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     "pem_pack_records": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
     "pem_weighted_procrustes": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),

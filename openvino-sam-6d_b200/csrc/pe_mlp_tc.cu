@@ -13,8 +13,8 @@
 //     neighbour lists and the cloud in shared memory, as bf16 hi + lo, in a SWIZZLE_128B operand tile;
 //   * warp 0 issues tcgen05.mma kind::f16 M128 x N{32,64,128} x K16: A_hi W_hi + A_hi W_lo + A_lo W_hi
 //     (split-bf16, fp32-class accuracy) against weights that stay resident in shared memory;
-//   * the row threads read the layer's accumulator out of TMEM, apply the folded BatchNorm affine and
-//     the ReLU, split the result again and write it as the next layer's operand tile;
+//   * the row threads read the layer's accumulator out of TMEM, add the BatchNorm shift (its scale is
+//     folded into the weights by the caller), apply the ReLU, split the result again and write it as the next layer's operand tile;
 //   * after the third layer a 31-shuffle transpose reduce takes the maximum over the 32 rows of a warp
 //     (one centre at ns = 32, half a centre at ns = 64) and lane L writes channel L of each 32-channel
 //     group: (B, N, ldo) point-major, ready for the final Linear / Conv1d(256, out_dim).
@@ -39,7 +39,7 @@ struct PmSmem {
     uint8_t w3[2][kPmC3 * 128];
     uint8_t a[G][2][2][kPmRows * 128];   // per group: two operand tiles (ping-pong between layers), hi / lo
     float4 cloud[kPmMaxN / G];
-    float scale[kPmC1 + kPmC2 + kPmC3], shift[kPmC1 + kPmC2 + kPmC3];  // folded BatchNorm per channel
+    alignas(16) float shift[kPmC1 + kPmC2 + kPmC3];  // BatchNorm shift per channel (its scale is folded into the weights)
     float comb[G][4][kPmC3];             // per-quadrant maxima (ns = 64: two quadrants per centre)
     uint64_t bar_a[G], bar_d[G];
     uint32_t tmem_base;
@@ -86,8 +86,7 @@ template <int NS, int G>
 __global__ void __launch_bounds__(32 + G * kPmRows, 1)
 pe_mlp_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx, int B, int N, float eps,
               const float *__restrict__ w1, const float *__restrict__ w2, const float *__restrict__ w3,
-              const float *__restrict__ scale, const float *__restrict__ shift, float *__restrict__ out,
-              int ldo, int ch_off) {
+              const float *__restrict__ shift, float *__restrict__ out, int ldo, int ch_off) {
     static_assert(kPmRows % NS == 0 || NS == 128, "whole centres per warp group");
     static_assert(NS == 32 || NS == 64 || NS == 128, "neighbours per centre");
     constexpr int kThreads = 32 + G * kPmRows;  // warp 0: MMA issuer; then 4 row warps per group
@@ -118,10 +117,7 @@ pe_mlp_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx, in
     pm_stage_weights(w1, kPmC1, kPmC0, 16, sm.w1[0], sm.w1[1]);
     pm_stage_weights(w2, kPmC2, kPmC1, 32, sm.w2[0], sm.w2[1]);
     pm_stage_weights(w3, kPmC3, kPmC2, 64, sm.w3[0], sm.w3[1]);
-    for (int c = tid; c < kPmC1 + kPmC2 + kPmC3; c += kThreads) {
-        sm.scale[c] = __ldg(scale + c);
-        sm.shift[c] = __ldg(shift + c);
-    }
+    for (int c = tid; c < kPmC1 + kPmC2 + kPmC3; c += kThreads) sm.shift[c] = __ldg(shift + c);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -183,12 +179,11 @@ pe_mlp_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx, in
                 tmem_ld32(lane_addr + dcol + c, v);
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
+                    const float4 s0 = lds_f4(&sm.shift[ch0 + c + g8 * 8]), s1 = lds_f4(&sm.shift[ch0 + c + g8 * 8 + 4]);
+                    const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                     float y[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int ch = ch0 + c + g8 * 8 + k;
-                        y[k] = fmaxf(fmaf(v[g8 * 8 + k], sm.scale[ch], sm.shift[ch]), 0.f);
-                    }
+                    for (int k = 0; k < 8; ++k) y[k] = fmaxf(v[g8 * 8 + k] + sh[k], 0.f);
                     uint4 h, l;
                     pm_split8(y, h, l);
                     const uint32_t off = sw128_offset(row, (c >> 3) + g8);
@@ -246,9 +241,12 @@ pe_mlp_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx, in
                 float v[32];
                 tmem_ld32(lane_addr + kPmD3 + c, v);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const int ch = kPmC1 + kPmC2 + c + k;
-                    v[k] = valid ? fmaxf(fmaf(v[k], sm.scale[ch], sm.shift[ch]), 0.f) : 0.f;
+                for (int k = 0; k < 32; k += 4) {
+                    const float4 s4 = lds_f4(&sm.shift[kPmC1 + kPmC2 + c + k]);
+                    v[k] = valid ? fmaxf(v[k] + s4.x, 0.f) : 0.f;
+                    v[k + 1] = valid ? fmaxf(v[k + 1] + s4.y, 0.f) : 0.f;
+                    v[k + 2] = valid ? fmaxf(v[k + 2] + s4.z, 0.f) : 0.f;
+                    v[k + 3] = valid ? fmaxf(v[k + 3] + s4.w, 0.f) : 0.f;
                 }
                 const float m = warp_transpose_reduce<true>(v);  // lane L: channel c + L over 32 rows
                 if (NS == 32) {
@@ -290,14 +288,13 @@ using namespace pem;
 using namespace pem::tc;
 
 extern "C" int pem_pe_mlp(const float *xyz, const int32_t *idx, int B, int N, int nsample, float centre_eps,
-                          const float *w1, const float *w2, const float *w3, const float *scale,
-                          const float *shift, float *out, int ldo, int ch_off, pem_stream_t stream) {
+                          const float *w1, const float *w2, const float *w3, const float *shift,
+                          float *out, int ldo, int ch_off, pem_stream_t stream) {
     PEM_REQUIRE_PTR(xyz);
     PEM_REQUIRE_PTR(idx);
     PEM_REQUIRE_PTR(w1);
     PEM_REQUIRE_PTR(w2);
     PEM_REQUIRE_PTR(w3);
-    PEM_REQUIRE_PTR(scale);
     PEM_REQUIRE_PTR(shift);
     PEM_REQUIRE_PTR(out);
     PEM_REQUIRE(B > 0 && N > 0 && ldo >= ch_off + kPmC3 && ch_off >= 0, PEM_E_SHAPE);
@@ -312,7 +309,7 @@ extern "C" int pem_pe_mlp(const float *xyz, const int32_t *idx, int B, int N, in
     cudaStream_t st = pem_cu_stream(stream);
     auto go = [&](auto kern, size_t smem, int threads, size_t *cached) -> int {
         if (int rc = pem_ensure_dyn_smem(kern, smem, cached)) return rc;
-        kern<<<grid, threads, smem, st>>>(xyz, idx, B, N, centre_eps, w1, w2, w3, scale, shift, out, ldo, ch_off);
+        kern<<<grid, threads, smem, st>>>(xyz, idx, B, N, centre_eps, w1, w2, w3, shift, out, ldo, ch_off);
         return pem_launch_status();
     };
     static size_t cached[6] = {0, 0, 0, 0, 0, 0};

@@ -11,17 +11,17 @@ from . import pointnet2_utils as _pu
 
 def fold_branch(layers):
     """layers: three (conv_weight (Co,Ci[,1,1]), bn_weight, bn_bias, running_mean, running_var, eps).
-    Returns (w1, w2, w3, scale, shift): BatchNorm in eval mode, y = (x - mean) / sqrt(var + eps) * g + b,
-    folded into one affine per channel (pytorch_utils.py:80-134: the convolution has no bias when bn)."""
-    ws, sc, sh = [], [], []
+    Returns (w1, w2, w3, shift): BatchNorm in eval mode, y = (x - mean) / sqrt(var + eps) * g + b, folded
+    into the layer -- its scale g / sqrt(var + eps) into the rows of the weight matrix, the rest into one
+    shift per channel (pytorch_utils.py:80-134: the convolution has no bias when bn)."""
+    ws, sh = [], []
     for (w, g, b, m, v, eps) in layers:
         w = torch.as_tensor(w).float()
         g, b, m, v = (torch.as_tensor(z).float().to(w.device) for z in (g, b, m, v))
         s = g / torch.sqrt(v + float(eps))
-        ws.append(w.reshape(w.shape[0], -1).contiguous())
-        sc.append(s)
+        ws.append((w.reshape(w.shape[0], -1) * s[:, None]).contiguous())
         sh.append(b - m * s)
-    return ws[0], ws[1], ws[2], torch.cat(sc).contiguous(), torch.cat(sh).contiguous()
+    return ws[0], ws[1], ws[2], torch.cat(sh).contiguous()
 
 
 def branch_from_module(shared_mlp):
@@ -52,12 +52,12 @@ def pe_neighbours(xyz, masks=None, radius1=0.1, nsample1=32, radius2=0.2, nsampl
 
 def pe_branch(xyz, idx, branch, out, ch_off, centre_eps=1e-8):
     """One branch into channels [ch_off, ch_off+128) of out (B,N,ld): group -> SharedMLP -> amax."""
-    w1, w2, w3, scale, shift = (t.to(xyz.device).contiguous() for t in branch)
+    w1, w2, w3, shift = (t.to(xyz.device).contiguous() for t in branch)
     B, N, _ = xyz.shape
     with torch.cuda.device(xyz.device):
         _lib.check(_lib.lib().pem_pe_mlp(xyz.data_ptr(), idx.data_ptr(), B, N, idx.shape[2], float(centre_eps),
-                                         w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), scale.data_ptr(),
-                                         shift.data_ptr(), out.data_ptr(), out.shape[2], int(ch_off),
+                                         w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), shift.data_ptr(),
+                                         out.data_ptr(), out.shape[2], int(ch_off),
                                          _ext._stream()), "pem_pe_mlp")
     return out
 

@@ -316,6 +316,48 @@ int pem_geo_embedding_indices(const float *points, int B, int N, int angle_k, fl
                               float sigma_a, float *d_indices, float *a_indices, pem_stream_t stream);
 
 /*
+ * Host-side instance preparation of the inference script, on the device.
+ * Replaces the geometric lines of get_test_data (run_inference_custom_pytorch.py:295-351) and the
+ * helpers it calls (utils/data_utils.py: get_point_cloud_from_depth :92-110, get_bbox :125-160,
+ * get_resize_rgb_choose :112-123).  The RGB crop / cv2.resize and the RLE decoding stay with the caller.
+ *
+ * precision: 0 = float32 arithmetic (the reference under its pinned numpy 1.26, where a float32 array
+ * combined with the float64 camera scalars stays float32), 1 = float64 rounded once at the end (the same
+ * lines under NumPy >= 2).  One IEEE operation per numpy operation in either mode.
+ *
+ * pem_depth_to_metres      depth_m = float32(raw) * depth_scale / 1000                        (:295)
+ * pem_backproject_depth    cloud (H*W,3) fp32: ((x - cx) * z / fx, (y - cy) * z / fy, z)        (:296)
+ * pem_instance_candidates  per detection d of masks (D,H,W) uint8, one CTA each:              (:311-331)
+ *                            mask & depth > 0; dropped unless more than 32 pixels; square box of get_bbox;
+ *                            crop-flat indices of the masked pixels in ascending order; their mean as
+ *                            numpy takes it (sequential sum over the rows); survivors of
+ *                            |p - mean| < dist_thresh (= radius * 1.2 as the caller's numpy evaluates
+ *                            it); dropped when fewer than 4 survive.
+ *                          info (D,8) int32 = valid | pixels in the crop | survivors | y1 | y2 | x1 | x2 | 0;
+ *                          the survivors' indices stay in `scratch` (pem_instance_scratch_bytes).
+ * pem_instance_sample      after the HOST has drawn `pick` (n_kept,n_sample) int64 positions into each kept
+ *                          detection's survivor list with numpy's generator (np.random.choice in the
+ *                          reference's order, :333-338 -- the draw is what makes a seed reproducible, so it
+ *                          is not re-implemented): pts (n_kept,n_sample,3) fp32, rgb_choose
+ *                          (n_kept,n_sample) int64 = get_resize_rgb_choose of the drawn pixels, choose
+ *                          (optional) their crop-flat indices.  det_ids (n_kept) = kept detection numbers.
+ *                          A pick outside [0, survivors) yields rgb_choose = -1.
+ */
+int pem_depth_to_metres(const uint16_t *raw, int H, int W, float depth_scale, float *depth_m,
+                        pem_stream_t stream);
+int pem_backproject_depth(const float *depth_m, int H, int W, double fx, double fy, double cx, double cy,
+                          int precision, float *cloud, pem_stream_t stream);
+size_t pem_instance_scratch_bytes(int D, int H, int W);
+int pem_instance_candidates(const float *depth_m, const uint8_t *masks, int D, int H, int W, double fx,
+                            double fy, double cx, double cy, int precision, double dist_thresh,
+                            int32_t *info, void *scratch, size_t scratch_bytes, pem_stream_t stream);
+int pem_instance_sample(const float *depth_m, int H, int W, double fx, double fy, double cx, double cy,
+                        int precision, const int32_t *info, const void *scratch, size_t scratch_bytes,
+                        int D, const int32_t *det_ids, int n_kept, const int64_t *pick, int n_sample,
+                        int img_size, float *pts, int64_t *rgb_choose, int64_t *choose,
+                        pem_stream_t stream);
+
+/*
  * Pack the per-instance result into the 64-byte record the multi-GPU gather moves
  * (no reference counterpart): records (B,16) fp32 = R (9) | t (3) | pose_score |
  * proposal id | instance id | 0.  proposal_id and instance_id may be NULL.

@@ -15,6 +15,7 @@ _lib = None
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int
 c_f = ctypes.c_float
+c_d = ctypes.c_double
 c_ll = ctypes.c_longlong
 c_sz = ctypes.c_size_t
 
@@ -53,6 +54,12 @@ SIGNATURES = {
     "pem_pe_neighbours_masked": (c_i, [c_p, c_i, c_i, c_f, c_f, c_i, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "pem_pe_mlp": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
     "pem_geo_embedding_indices": (c_i, [c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    "pem_depth_to_metres": (c_i, [c_p, c_i, c_i, c_f, c_p, c_p]),
+    "pem_backproject_depth": (c_i, [c_p, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_p, c_p]),
+    "pem_instance_scratch_bytes": (c_sz, [c_i, c_i, c_i]),
+    "pem_instance_candidates": (c_i, [c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_d, c_p, c_p, c_sz, c_p]),
+    "pem_instance_sample": (c_i, [c_p, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_p, c_p, c_sz, c_i, c_p, c_i, c_p,
+                                  c_i, c_i, c_p, c_p, c_p, c_p]),
     "pem_pack_records": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
     "pem_weighted_procrustes": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
 }

@@ -371,3 +371,110 @@ def rotation_angle_deg(Ra, Rb):
     Rb = _t(Rb).double()
     chord = (Ra - Rb).flatten(-2).norm(dim=-1) / (2.0 * np.sqrt(2.0))
     return torch.rad2deg(2.0 * torch.asin(chord.clamp(max=1.0)))
+
+
+# ---- host-side instance preparation -------------------------------
+def _prep_dtype(precision):
+    """The reference pins numpy 1.26 (SAM-6D/requirements.txt:32), where a float32 array combined with
+    the float64 camera scalars stays float32 ("f32"); under NumPy >= 2 (NEP 50, this container) the
+    same lines promote to float64 ("f64").  Both are restated; K's dtype selects the arithmetic."""
+    assert precision in ("f32", "f64")
+    return np.float32 if precision == "f32" else np.float64
+
+
+def point_cloud_from_depth(depth, K, precision="f64"):
+    """get_point_cloud_from_depth (utils/data_utils.py:92-110) without a bbox: (H,W) metres -> (H,W,3).
+    pt0 = (x - cx) * z / fx, pt1 = (y - cy) * z / fy, pt2 = z, one rounding per operation."""
+    dt = _prep_dtype(precision)
+    K = np.asarray(K).astype(dt)
+    H, W = depth.shape
+    xmap = np.broadcast_to(np.arange(W)[None, :], (H, W)).astype(np.float32)
+    ymap = np.broadcast_to(np.arange(H)[:, None], (H, W)).astype(np.float32)
+    z = depth.astype(np.float32)
+    pt0 = (xmap - K[0, 2]) * z / K[0, 0]
+    pt1 = (ymap - K[1, 2]) * z / K[1, 1]
+    return np.stack([pt0, pt1, z.astype(pt0.dtype)]).transpose((1, 2, 0))
+
+
+def mask_bbox(label):
+    """get_bbox (utils/data_utils.py:125-160): tight box of the mask, made square with side
+    min(max(rows, cols), min(H, W)) around the integer centre, shifted back inside the image."""
+    H, W = label.shape
+    rows = np.where(np.any(label, axis=1))[0]
+    cols = np.where(np.any(label, axis=0))[0]
+    rmin, rmax, cmin, cmax = int(rows[0]), int(rows[-1]) + 1, int(cols[0]), int(cols[-1]) + 1
+    b = min(max(rmax - rmin, cmax - cmin), min(H, W))
+    cr, cc = int((rmin + rmax) / 2), int((cmin + cmax) / 2)
+    half = int(b / 2)
+    rmin, rmax, cmin, cmax = cr - half, cr + half, cc - half, cc + half
+    if rmin < 0:
+        rmax, rmin = rmax - rmin, 0
+    if cmin < 0:
+        cmax, cmin = cmax - cmin, 0
+    if rmax > H:
+        rmin, rmax = rmin - (rmax - H), H
+    if cmax > W:
+        cmin, cmax = cmin - (cmax - W), W
+    return [rmin, rmax, cmin, cmax]
+
+
+def resize_rgb_choose(choose, bbox, img_size):
+    """get_resize_rgb_choose (utils/data_utils.py:112-123): crop-flat pixel index -> index in the
+    img_size x img_size resized crop, floor(row * img_size / crop_h) * img_size + floor(col * ...)."""
+    rmin, rmax, cmin, cmax = bbox
+    ratio_h, ratio_w = img_size / (rmax - rmin), img_size / (cmax - cmin)
+    row, col = choose // (cmax - cmin), choose % (cmax - cmin)
+    return (np.floor(row * ratio_h) * img_size + np.floor(col * ratio_w)).astype(np.int64)
+
+
+def instance_candidates(depth, cloud, mask, dist_thresh):
+    """The geometric part of get_test_data's per-detection loop up to the random draw
+    (run_inference_custom_pytorch.py:311-331): mask & depth > 0, more than 32 pixels, square bbox,
+    crop-flat indices of the masked pixels in row-major order, their points, the SEQUENTIAL mean
+    numpy takes over axis 0, and the distance filter against dist_thresh = radius * 1.2; fewer than 4
+    survivors drop the detection.  Returns None or (bbox, choose, cloud) of the survivors."""
+    m = np.logical_and(mask > 0, depth > 0)
+    if np.sum(m) <= 32:
+        return None
+    y1, y2, x1, x2 = bbox = mask_bbox(m)
+    choose = m[y1:y2, x1:x2].astype(np.float32).flatten().nonzero()[0]
+    pts = cloud[y1:y2, x1:x2, :].reshape(-1, 3)[choose, :]
+    acc = np.zeros(3, pts.dtype)
+    for i in range(pts.shape[0]):  # np.mean(axis=0) of a C-contiguous (n,3) array adds row after row
+        acc = acc + pts[i]
+    centre = acc / pts.dtype.type(pts.shape[0])
+    d = pts - centre[None, :]
+    s = d * d
+    flag = np.sqrt((s[:, 0] + s[:, 1]) + s[:, 2]) < dist_thresh
+    if np.sum(flag) < 4:
+        return None
+    return bbox, choose[flag], pts[flag]
+
+
+def prepare_instances(depth, K, masks, scores, radius, n_sample, img_size, rng, precision="f64"):
+    """get_test_data's detection loop (run_inference_custom_pytorch.py:303-361) minus the RGB crop:
+    returns pts (n,n_sample,3) f32, rgb_choose (n,n_sample) i64, score (n,), kept detection indices,
+    and the whole cloud.  `rng` is numpy's global-style generator (np.random or a RandomState); the
+    draws happen in the reference's order so the same seed gives the same sample."""
+    dt = _prep_dtype(precision)
+    cloud = point_cloud_from_depth(depth, K, precision)
+    radius = np.float32(radius)
+    # `flag = norm < radius * 1.2`: numpy 1.26 multiplies in float64 and compares in float32 after
+    # rounding the scalar; NumPy >= 2 multiplies in float32 and compares exactly
+    thresh = np.float32(float(radius) * 1.2) if precision == "f32" else radius * np.float32(1.2)
+    pts_all, rc_all, sc_all, kept = [], [], [], []
+    for i in range(len(masks)):
+        cand = instance_candidates(depth, cloud, masks[i], dt(thresh))
+        if cand is None:
+            continue
+        bbox, choose, pts = cand
+        if len(choose) <= n_sample:
+            pick = rng.choice(np.arange(len(choose)), n_sample)
+        else:
+            pick = rng.choice(np.arange(len(choose)), n_sample, replace=False)
+        pts_all.append(pts[pick].astype(np.float32))
+        rc_all.append(resize_rgb_choose(choose[pick], bbox, img_size))
+        sc_all.append(scores[i])
+        kept.append(i)
+    return (np.stack(pts_all), np.stack(rc_all), np.asarray(sc_all, np.float32), kept,
+            cloud.reshape(-1, 3))

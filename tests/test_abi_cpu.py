@@ -61,6 +61,13 @@ def test_argument_validation_without_gpu(pkg):
     assert lib.pem_fine_fused(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, p, p, p, None, None, None, None, p, 16,
                               None) == -4
     assert lib.pem_fine_fused_pass(p, p, 1, 8, 8, 64, 0.1, 7, p, 1 << 30, None) == -3
+    # instance preparation
+    assert lib.pem_instance_scratch_bytes(3, 480, 640) == 3 * 480 * 640 * 4
+    assert lib.pem_backproject_depth(p, 4, 4, 1.0, 1.0, 0.0, 0.0, 2, p, None) == -3     # precision is 0 or 1
+    assert lib.pem_depth_to_metres(None, 4, 4, 1.0, p, None) == -1
+    assert lib.pem_instance_candidates(p, p, 1, 4, 4, 1.0, 1.0, 0.0, 0.0, 0, 0.2, p, p, 8, None) == -4
+    assert lib.pem_instance_sample(p, 4, 4, 1.0, 1.0, 0.0, 0.0, 0, p, p, 64, 1, p, 0, p, 8, 224, p, p, None,
+                                   None) == -2                                           # no kept detection
     assert lib.pem_fps_workspace_bytes(4, 2048) == 0
     assert lib.pem_fps_workspace_bytes(2, 210000) == 0 and lib.pem_fps_workspace_bytes(2, 300000) == 2 * 300000 * 4
     assert lib.pem_fine_workspace_bytes(16, 2048, 2048) > 16 * 2049 * 4 * 6

@@ -130,6 +130,50 @@ O.geo_embedding_indices(cpu_pts)
 row("geo_embedding_indices reference arithmetic on CPU, 4x197 (torch, all host threads)",
     (_time.perf_counter() - t0) * 1e3)
 
+# rank 4: instance preparation of one 480x640 RGB-D frame with 16 detections (get_test_data's loop)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_instance_prep import _scene  # noqa: E402
+dm, mk, sc_ = _scene(1, 480, 640, 16)
+Kc = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1]])
+d_dm, d_mk = torch.from_numpy(dm).to(dev), torch.from_numpy(mk).to(dev)
+def _prep():
+    return pkg.data_utils.prepare_instances(d_dm, Kc, d_mk, sc_, 0.21, 2048, 224, rng=np.random.RandomState(0))
+for _ in range(3):
+    res = _prep()
+torch.cuda.synchronize()
+t0 = _time.perf_counter()
+for _ in range(10):
+    res = _prep()
+torch.cuda.synchronize()
+ms = (_time.perf_counter() - t0) * 100
+_L = pkg._lib.lib()
+_nb = _L.pem_instance_scratch_bytes(16, 480, 640)
+_scr, _inf = torch.empty(_nb, dtype=torch.uint8, device=dev), torch.empty((16, 8), dtype=torch.int32, device=dev)
+ms_k = timeit(lambda: _L.pem_instance_candidates(d_dm.data_ptr(), d_mk.data_ptr(), 16, 480, 640, 572.4114, 573.57043,
+                                                 325.2611, 242.04899, 1, 0.252, _inf.data_ptr(), _scr.data_ptr(), _nb,
+                                                 None))
+row("instance_candidates_kernel<f64> 480x640, 16 detections (one CTA each; largest mask %d points)"
+    % int(_inf[:, 1].max().item()), ms_k)
+row("prepare_instances 480x640, 16 detections (%d kept; wall clock incl. the host draw and its sync)" % len(res["kept"]), ms)
+t0 = _time.perf_counter()
+O.prepare_instances(dm, Kc, mk, sc_, 0.21, 2048, 224, np.random.RandomState(0), "f64")
+row("prepare_instances reference arithmetic on CPU (numpy, oracle's sequential mean in a Python loop)",
+    (_time.perf_counter() - t0) * 1e3)
+t0 = _time.perf_counter()
+wp = O.point_cloud_from_depth(dm, Kc, "f64")
+for i_ in range(16):  # the reference's own numpy lines per detection (timing only)
+    m_ = np.logical_and(mk[i_] > 0, dm > 0)
+    if m_.sum() <= 32:
+        continue
+    y1_, y2_, x1_, x2_ = O.mask_bbox(m_)
+    ch_ = m_[y1_:y2_, x1_:x2_].astype(np.float32).flatten().nonzero()[0]
+    cl_ = wp.copy()[y1_:y2_, x1_:x2_, :].reshape(-1, 3)[ch_, :]
+    fl_ = np.linalg.norm(cl_ - np.mean(cl_, axis=0)[None, :], axis=1) < 0.252
+    ch_, cl_ = ch_[fl_], cl_[fl_]
+    ci_ = np.random.choice(np.arange(len(ch_)), 2048, replace=len(ch_) <= 2048)
+    O.resize_rgb_choose(ch_[ci_], [y1_, y2_, x1_, x2_], 224)
+row("prepare_instances: the reference's numpy lines on the CPU, same frame", (_time.perf_counter() - t0) * 1e3)
+
 # rank 1: PositionalEncoding front end (fine_point_matching.py:102-144): groups -> SharedMLP -> amax, fused
 PE = pkg.positional_encoding
 gen = torch.Generator().manual_seed(0)

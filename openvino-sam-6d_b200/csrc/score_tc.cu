@@ -21,11 +21,16 @@
 //     tiles, so no tensor work is wasted on padding 151 points to 256;
 //   * warps 2-9 ("row threads", two per TMEM lane = tile row, one per half of the columns)
 //     transform their point, write their half of the A row (generic stores + proxy fence), and
-//     later reduce their lane of the accumulator with 3-input minima straight out of TMEM;
+//     later reduce their lane of the accumulator with 3-input minima straight out of TMEM
+//     (PARTS = 4 puts four threads on a row; measured 6 % slower, kept as a development knob);
 //   * warp 1 issues M128 x N256 x K8 MMAs: 2 per 256-model-point chunk, accumulator chunks double
 //     buffered in the 512 TMEM columns; A tiles double buffered so tile t+1 is built while tile t
 //     is reduced;
 //   * distances land in shared memory, and each hypothesis is summed in a fixed order.
+// Bound: every pair value crosses the TMEM read port once.  Measured here: 128 KB per chunk per SM in
+// ~980 cycles = 128 B/clk/SM (32 B/clk per scheduler quadrant), whatever the split of the columns over
+// warps (2 or 4 per row) and whether or not a warp keeps a second load in flight -- the port, not issue
+// or latency, sets the pace (ncu: issue slots 37 % busy, ALU pipe 43 %, tensor pipe 30 %).
 // More than 1024 model points are taken in blocks of 1024: the tiles of a batch of hypotheses run
 // once per block and the running minima wait in shared memory.  The SIMT kernel (coarse.cu) remains
 // for shapes this one does not take (more than 4096 model points or 256 query points).
@@ -39,15 +44,15 @@ constexpr int kSChunk = 256;         // model points per accumulator buffer
 constexpr int kSMaxNm = 1024;        // model points held in shared memory (128 B per row)
 constexpr int kSMaxN1 = 256;         // query points per instance
 constexpr int kSBatchHyps = 40;      // hypotheses whose distances fit in shared memory at once
-constexpr int kSRowThreads = 256;
-constexpr int kSThreads = 64 + kSRowThreads;
 constexpr uint32_t kSIdesc = make_idesc_tf32(kSRows, kSChunk);
 
+// PARTS = row threads per tile row, each reducing 256 / PARTS columns of every chunk (2 or 4)
+template <int PARTS>
 struct ScoreSmem {
     uint8_t b[kSMaxNm * 128];        // model operand
     uint8_t a[2][kSRows * 128];      // query tiles
     float dis[kSBatchHyps * kSMaxN1];
-    float comb[2][kSRows];           // best of column half 1, handed to the half-0 thread of the row
+    float comb[2][PARTS - 1][kSRows];  // best of column parts 1.., handed to the part-0 thread of the row
     float px[kSMaxN1], py[kSMaxN1], pz[kSMaxN1];  // compacted foreground points
     float Rt[kSBatchHyps][12];       // R (row-major) | t of the hypotheses of the batch
     int nfg;
@@ -55,16 +60,19 @@ struct ScoreSmem {
     uint32_t tmem_base;
 };
 
+template <int N>
 __device__ __forceinline__ void row_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kSRowThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
 }
 
-__global__ void __launch_bounds__(kSThreads, 1)
+template <int PARTS>
+__global__ void __launch_bounds__(64 + 128 * PARTS, 1)
 score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const int32_t *__restrict__ sel,
                 int P, int H, const float *__restrict__ pts1, const float *__restrict__ w1, int N1,
                 const float *__restrict__ model, int Nm, int cpi, float *__restrict__ scores) {
     extern __shared__ uint8_t smem_raw[];
-    ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int kSRowThreads = 128 * PARTS, kSThreads = 64 + kSRowThreads, kSCols = kSChunk / PARTS;
+    ScoreSmem<PARTS> &sm = *reinterpret_cast<ScoreSmem<PARTS> *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id(), tid = threadIdx.x;
     const int b = blockIdx.x / cpi, slice = blockIdx.x - b * cpi;
     const int hpc = (H + cpi - 1) / cpi;                       // hypotheses per CTA
@@ -191,15 +199,16 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                     }
                 } else if (warp >= 2) {
                     // ================================ row threads =================================
-                    const int quad = warp & 3, half = (warp - 2) >> 2;
+                    const int quad = warp & 3, part = (warp - 2) >> 2;
                     const int et = quad * 32 + lane;  // tile row = TMEM lane
 
-                    // transform the point of tile row `et` and write this thread's half of the A row
+                    // transform the point of tile row `et` and write this thread's share of the A row
                     auto build = [&](int r0, uint32_t seq) {
                         const int buf = seq & 1;
                         mbar_wait(smem_u32(&sm.a_empty[buf]), ((seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
                         const int row = r0 + et;
-                        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                        float4 c[4];
+                        c[0] = c[1] = c[2] = c[3] = make_float4(0.f, 0.f, 0.f, 0.f);
                         float q2 = 0.f;
                         if (row < rows) {
                             const int hh = row / nfg, i = row - hh * nfg;
@@ -212,16 +221,15 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                             q2 = qx * qx + qy * qy + qz * qz;
                             const float xh = to_tf32(qx), yh = to_tf32(qy), zh = to_tf32(qz);
                             const float xl = to_tf32(qx - xh), yl = to_tf32(qy - yh), zl = to_tf32(qz - zh);
-                            if (half == 0) {
-                                c0 = make_float4(xh, yh, zh, xh);
-                                c1 = make_float4(yh, zh, xl, yl);
-                            } else {
-                                c0 = make_float4(zl, xl, yl, zl);
-                                c1 = make_float4(1.f, 1.f, 0.f, 0.f);
-                            }
+                            c[0] = make_float4(xh, yh, zh, xh);
+                            c[1] = make_float4(yh, zh, xl, yl);
+                            c[2] = make_float4(zl, xl, yl, zl);
+                            c[3] = make_float4(1.f, 1.f, 0.f, 0.f);
                         }
-                        *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half)) = c0;
-                        *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2 * half + 1)) = c1;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)  // 16 K slots = 4 float4, shared out between the parts
+                            if (k * PARTS / 4 == part)
+                                *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, k)) = c[k];
                         fence_proxy_async_smem();
                         mbar_arrive(smem_u32(&sm.a_full[buf]));
                         return q2;
@@ -239,11 +247,20 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                             mbar_wait(smem_u32(&sm.tmem_full[cb]), (chunk_seq >> 1) & 1);
                             tc_fence_after();
                             {
-                                float v[kSChunk / 2];
-                                tmem_ld128(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                               (uint32_t)(cb * kSChunk + half * (kSChunk / 2)), v);
+                                float v[kSCols];
+                                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                                    (uint32_t)(cb * kSChunk + part * kSCols);
+                                if constexpr (kSCols == 128) {
+                                    tmem_ld128(ta, v);
+                                } else {
+                                    uint32_t r[64];
+                                    tmem_ld64_issue(ta, r);
+                                    tmem_ld64_wait(r);
 #pragma unroll
-                                for (int q = 0; q < kSChunk / 2; q += 8) {
+                                    for (int q = 0; q < 64; ++q) v[q] = __uint_as_float(r[q]);
+                                }
+#pragma unroll
+                                for (int q = 0; q < kSCols; q += 8) {
                                     m0 = fminf(fminf(m0, v[q]), v[q + 1]);
                                     m1 = fminf(fminf(m1, v[q + 2]), v[q + 3]);
                                     m2 = fminf(fminf(m2, v[q + 4]), v[q + 5]);
@@ -256,10 +273,12 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                         }
                         const float best = fminf(fminf(m0, m1), fminf(m2, m3));
                         const int par = tile_seq & 1;
-                        if (half == 1) sm.comb[par][et] = best;
-                        row_barrier();
-                        if (half == 0 && r0 + et < rows) {
-                            float d = fminf(best, sm.comb[par][et]);
+                        if (part > 0) sm.comb[par][part - 1][et] = best;
+                        row_barrier<kSRowThreads>();
+                        if (part == 0 && r0 + et < rows) {
+                            float d = best;
+#pragma unroll
+                            for (int k = 0; k < PARTS - 1; ++k) d = fminf(d, sm.comb[par][k][et]);
                             if (!first) d = fminf(d, sm.dis[r0 + et]);  // minimum over the earlier model blocks
                             sm.dis[r0 + et] = last ? sqrtf(fmaxf(q2 + d, 0.f)) : d;  // clamp, then sqrt
                         }
@@ -296,6 +315,8 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
 
 }  // namespace tc
 
+static int g_score_parts = 2;  // row threads per tile row (development knob: 2 or 4; 4 measured 6 % slower)
+
 // returns PEM_E_UNSUPPORTED for shapes the tensor-core kernel does not take (the caller falls back
 // to the SIMT kernel)
 int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
@@ -307,11 +328,20 @@ int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cpi = max(1, min(sms / B, (H + 7) / 8));  // CTAs per instance
-    const size_t smem = sizeof(ScoreSmem) + 1024;
-    static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(score_tc_kernel, smem, &cached)) return rc;
-    score_tc_kernel<<<B * cpi, kSThreads, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
+    if (g_score_parts == 2) {
+        const size_t smem = sizeof(ScoreSmem<2>) + 1024;
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(score_tc_kernel<2>, smem, &cached)) return rc;
+        score_tc_kernel<2><<<B * cpi, 64 + 256, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
+    } else {
+        const size_t smem = sizeof(ScoreSmem<4>) + 1024;
+        static size_t cached = 0;
+        if (int rc = pem_ensure_dyn_smem(score_tc_kernel<4>, smem, &cached)) return rc;
+        score_tc_kernel<4><<<B * cpi, 64 + 512, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
+    }
     return pem_launch_status();
 }
 
 }  // namespace pem
+
+extern "C" void pem_dev_set_score_parts(int parts) { pem::g_score_parts = parts == 4 ? 4 : 2; }

@@ -149,6 +149,10 @@ def test_score_hypotheses_tensor_core_vs_simt_and_oracle(pkg, oracle, dev, Nm, H
     simt = pkg.model_utils.score_hypotheses(*args).cpu()
     L.pem_dev_set_score_simt(0)
     tc = pkg.model_utils.score_hypotheses(*args).cpu()
+    L.pem_dev_set_score_parts(4)   # four row threads per tile row instead of two: same arithmetic
+    tc2 = pkg.model_utils.score_hypotheses(*args).cpu()
+    L.pem_dev_set_score_parts(2)
+    assert torch.equal(tc, tc2)
     if nfg == 0:
         assert (tc == 0).all() and (simt == 0).all()
         return

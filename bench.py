@@ -43,6 +43,8 @@ def workload_config(args, world):
         "feat_dim": 256, "n_model": 1024, "n_proposal1": 6000, "n_proposal2": 300,
         "parallelism": "instance-sharded dp%d, pose-record all_gather" % world,
         "l2": "flushed between timed steps (256 MB memset outside the event pair)",
+        "fine_gemm": getattr(args, "fine_precision", "fp16") + " tcgen05 (fp32 accumulation; pose parity bars "
+                     "0.1 deg / 1e-4 asserted for this mode in tests/test_tensorcore_gpu.py)",
     }
 
 
@@ -134,7 +136,7 @@ def run_b200(args, rank, world, local_rank):
     B, K, W = args.batch, args.steps, args.warmup
     ids = [rank * B + i for i in range(B)]
     host = pkg.synth.make_batch(ids)
-    stage = pkg.stage.GeometricStage(B, dev)
+    stage = pkg.stage.GeometricStage(B, dev, fine_precision=args.fine_precision)
     stage.instance_ids.copy_(torch.tensor(ids, dtype=torch.float32))
     stage.load(host)
     gathered = torch.empty((world * B, 16), dtype=torch.float32, device=dev)  # every rank's records
@@ -179,7 +181,7 @@ def run_b200(args, rank, world, local_rank):
     pin = pkg.stage.PipelinedStage.pin_inputs(host)
     h2d = sum(v.numel() * v.element_size() for v in pin.values())
     d2h = B * 16 * 4
-    pipe = pkg.stage.PipelinedStage(B, dev, depth=2)
+    pipe = pkg.stage.PipelinedStage(B, dev, depth=2, fine_precision=args.fine_precision)
     pipe.load_constants(host)
     for s_ in pipe.stages:
         s_.instance_ids.copy_(torch.tensor(ids, dtype=torch.float32))
@@ -244,7 +246,8 @@ def _peaks():
 
 
 def dominant_kernel_roofline(pkg, stage, flush):
-    """The stage's dominant kernel: fine_tc_kernel (fine_tc.cu), the tcgen05 split-bf16 GEMM with a
+    """The stage's dominant kernel: fine_tc_kernel (fine_tc.cu), the tcgen05 GEMM (one fp16 product per
+    element by default; split-bf16 = three products with --fine-precision split_bf16) with a
     reducing epilogue that pem_fine_fused launches for its two full passes per step (softmax
     statistics; foreground labels + weighted sums) and once more, ragged, for the background-column
     correction.  Each of the two full launches is timed alone with CUDA events on its launch stream
@@ -252,22 +255,23 @@ def dominant_kernel_roofline(pkg, stage, flush):
     their mean.
 
     Algorithmic flops per launch = 2*N1*N2*C per instance (the cosine matrix once; DESIGN.md
-    section 4).  The kernel EXECUTES 3x that on the tensor cores (hi*hi + hi*lo + lo*hi), reported
-    as executed_mma_tflops next to the measured cuBLAS bf16 peak."""
+    section 4).  In split-bf16 mode the kernel EXECUTES 3x that on the tensor cores (hi*hi + hi*lo +
+    lo*hi), reported as executed_mma_tflops next to the measured cuBLAS bf16 peak."""
     L, st = pkg._lib.lib(), stage.stream.cuda_stream
     B, N, C, Nm = stage.B, stage.N, stage.C, stage.Nm
     p = lambda t: t.data_ptr()
     peaks, which = _peaks()
 
     def fused():
-        pkg._lib.check(L.pem_fine_fused(p(stage.feats[0]), p(stage.feats[1]), p(stage.pts[0]), p(stage.pts[1]),
-                                        p(stage.model), B, N, N, C, Nm, stage.temp, stage.dis_thres, p(stage.R),
-                                        p(stage.t), p(stage.score), None, None, None, None, p(stage.ws),
-                                        stage.ws_bytes, st), "fine_fused")
+        pkg._lib.check(L.pem_fine_fused_ex(p(stage.feats[0]), p(stage.feats[1]), p(stage.pts[0]), p(stage.pts[1]),
+                                           p(stage.model), B, N, N, C, Nm, stage.temp, stage.dis_thres,
+                                           stage.fine_precision, p(stage.R), p(stage.t), p(stage.score), None,
+                                           None, None, None, p(stage.ws), stage.ws_bytes, st), "fine_fused")
 
     def one_pass(k):
-        pkg._lib.check(L.pem_fine_fused_pass(p(stage.feats[0]), p(stage.feats[1]), B, N, N, C, stage.temp, k,
-                                             p(stage.ws), stage.ws_bytes, st), "fine_fused_pass")
+        pkg._lib.check(L.pem_fine_fused_pass_ex(p(stage.feats[0]), p(stage.feats[1]), B, N, N, C, stage.temp, k,
+                                                stage.fine_precision, p(stage.ws), stage.ws_bytes, st),
+                       "fine_fused_pass")
 
     def timed(fn, iters=10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,17 +295,21 @@ def dominant_kernel_roofline(pkg, stage, flush):
     achieved = flops / (ms / 1e3) / 1e12
     peak = float(peaks["bf16_tflops"])
     traffic = None
+    single = stage.fine_precision == 1
+    nprod = 1.0 if single else 3.0
+    summary = "r1_fine_tc_fp16_ncu_summary.json" if single else "r1_fine_tc_ncu_summary.json"
     try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_fine_tc_ncu_summary.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", summary)) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    return {"kernel": "fine_tc_kernel (tcgen05 cta_group::2 split-bf16 GEMM %dx%dx%d per instance, reducing "
-                      "epilogue; mean of the stats and the label+wsum launch)" % (N, N, C),
+    return {"kernel": "fine_tc_kernel (tcgen05 cta_group::2 %s GEMM %dx%dx%d per instance, reducing "
+                      "epilogue; mean of the stats and the label+wsum launch)"
+                      % ("fp16" if single else "split-bf16", N, N, C),
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "ms_per_launch": ms,
             "ms_per_launch_by_pass": {"stats": pass_ms[0], "label+wsum": pass_ms[1]},
-            "executed_mma_tflops": 3.0 * achieved, "executed_frac": 3.0 * achieved / peak,
+            "executed_mma_tflops": nprod * achieved, "executed_frac": nprod * achieved / peak,
             "fused_fine_op_ms": fused_ms,
             "peak_source": which + ", burst bf16 (kernel timed alone)"}
 
@@ -338,6 +346,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="instances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fine-precision", default="fp16", choices=["fp16", "split_bf16"],
+                    help="arithmetic of the fused fine GEMM (include/pem_b200.h PEM_PREC_*); both pass the "
+                         "pose parity bars of tests/test_tensorcore_gpu.py")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -261,6 +261,25 @@ int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const fl
                    pem_stream_t stream);
 
 /*
+ * The same with the GEMM arithmetic chosen by the caller:
+ *   PEM_PREC_SPLIT_BF16  every product as bf16 hi*hi + hi*lo + lo*hi (three MMAs): logits to ~1e-5,
+ *                        what pem_fine_fused does;
+ *   PEM_PREC_FP16        one fp16 x fp16 product with fp32 accumulation.  The operands are unit
+ *                        vectors (|x| <= 1, no range problem; 2^-12 relative per element): logits to
+ *                        ~1e-3 of their +-1/temp range, final pose within 1e-3 deg / 1e-5 radius
+ *                        units of the split form on the parity cases (bar: 0.1 deg, 1e-4), at a third
+ *                        of the tensor work and half the operand traffic.  The background row and
+ *                        column stay exact fp32 dot products in both modes.
+ */
+#define PEM_PREC_SPLIT_BF16 0
+#define PEM_PREC_FP16 1
+int pem_fine_fused_ex(const float *f1, const float *f2, const float *pts1, const float *pts2,
+                      const float *model, int B, int N1, int N2, int C, int Nm, float temp,
+                      float dis_thres, int precision, float *R, float *t, float *score, float *w1,
+                      float *w2, float *rowsum, float *pred, void *workspace, size_t workspace_bytes,
+                      pem_stream_t stream);
+
+/*
  * Profiling hook (no reference counterpart): re-run ONE reducing GEMM pass of pem_fine_fused on the
  * operands and constants a previous pem_fine_fused call with the same shapes left in `workspace`:
  * pass 1 softmax statistics, 4 foreground labels + weighted sums over all columns (the two full
@@ -269,6 +288,10 @@ int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const fl
  */
 int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
                         int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream);
+/* ... after a pem_fine_fused_ex call of the same `precision` (pem_fine_fused_pass = SPLIT_BF16) */
+int pem_fine_fused_pass_ex(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
+                           int pass, int precision, void *workspace, size_t workspace_bytes,
+                           pem_stream_t stream);
 
 /*
  * Weighted Procrustes (MU:343-436) for B' problems of n points each, one CTA per

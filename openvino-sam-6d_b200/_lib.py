@@ -47,6 +47,9 @@ SIGNATURES = {
     "pem_feature_similarity_tc": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "pem_fine_fused": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p,
                              c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "pem_fine_fused_ex": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_p,
+                                c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "pem_fine_fused_pass_ex": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_p, c_sz, c_p]),
     "pem_pe_masks_bytes": (c_sz, [c_i, c_i]),
     "pem_pe_masks": (c_i, [c_p, c_i, c_i, c_f, c_f, c_f, c_i, c_p, c_sz, c_p]),
     "pem_pe_group2_masked": (c_i, [c_p, c_i, c_i, c_f, c_f, c_i, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),

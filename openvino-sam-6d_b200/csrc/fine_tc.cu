@@ -60,6 +60,7 @@ constexpr int TM = 2 * BM, TN = 2 * BN;     // rows per step / columns per strip
 constexpr int kChunkBytes = BM * BK * 2;    // 16 KB
 constexpr int kStages = 5;
 constexpr int kMaxKC = 4;                   // C <= 256
+constexpr int kMaxStages = kStages + kMaxKC; // single-product mode: the unused b_lo buffers extend the ring to 9 slots
 constexpr uint32_t kTmemCols = 2 * TN;      // double-buffered 128 x 256 accumulator: all of TMEM
 
 enum Mode { kStore = 0, kStats = 1, kLabel = 2, kWsum = 3, kLabelW = 4 };  // kLabelW = kLabel + kWsum in one pass
@@ -70,6 +71,8 @@ struct Params {
     int n_msteps, n_strips; // Mp / 256 row steps, Np / 256 column strips
     int spt, n_splits;     // row steps per task, tasks per (instance, strip)
     int KC;                // C / 64
+    int ring;              // single-product mode: ring slots (2..9)
+    int single;            // 1: one fp16 product per element (operands = fp16 of the normalised rows); 0: split-bf16, three products
     float temp;            // logits = cos / temp
     float c1, c2;          // e = exp2(cos * c1 - c2)
     // kStore: element (i,j) of the GEMM goes to atten[b][i + off][j + off], row length Cn + off
@@ -94,12 +97,12 @@ struct Params {
 struct Smem {
     // operand buffers first: SWIZZLE_128B needs 1024-byte alignment
     uint8_t b_hi[kMaxKC][kChunkBytes];   // resident: this CTA's 128 columns of the strip of B'
-    uint8_t b_lo[kMaxKC][kChunkBytes];
+    uint8_t b_lo[kMaxKC][kChunkBytes];   // (single-product mode: no lo operand -- these are four more ring slots)
     uint8_t a[kStages][kChunkBytes];     // streamed: this CTA's 128 rows of a step of A' (hi or lo)
     float4 G[TN];                        // per-column constants of the task (kWsum)
     alignas(16) float colc[TN];          // per-column constants of the task (kLabel: log2 colsum)
     float colred[4][TN];                 // per-quadrant column results
-    uint64_t full[kStages], empty[kStages], b_full[kMaxKC], b_empty[kMaxKC], tmem_full[2], tmem_empty[2];
+    uint64_t full[kMaxStages], empty[kMaxStages], b_full[kMaxKC], b_empty[kMaxKC], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
@@ -113,6 +116,11 @@ __device__ __forceinline__ void epi_barrier() {
 // element and holds the tensor pipe at 76 %: 71 us instead of 69 us -- the extra barrier traffic
 // costs more than the latency hiding gains.  The kernel is written for either.)
 __host__ __device__ constexpr int epi_warps(int /*mode*/) { return 8; }
+// With ONE product per element (Params::single) the MMAs of a tile take a third of the time and the
+// epilogue becomes the limit (measured with the MMAs switched off: 42 us statistics, 60 us merged
+// pass, against 19 us of MMAs): four warps per quadrant (64 columns each) give every scheduler four
+// warps to hide the TMEM-load and MUFU latencies behind.
+constexpr int kEpiWarpsSingle = 16;
 
 struct Task {
     int b, n, m0, m1;  // instance, column strip, row steps [m0, m1)
@@ -132,12 +140,13 @@ __device__ __forceinline__ Task decode_task(const Params &p, int task) {
     return t;
 }
 
-template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * epi_warps(MODE), 1)
+template <int MODE, int EPW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const Params p) {
-    constexpr uint32_t kIdesc = make_idesc(TM, TN);
-    constexpr int EPW = epi_warps(MODE), EPT = 32 * EPW;  // epilogue warps / threads
+    const uint32_t kIdesc = p.single ? make_idesc_f16(TM, TN) : make_idesc(TM, TN);
+    const int n_hl = p.single ? 1 : 2;                    // streamed chunks per (step, K chunk): hi [, lo]
+    constexpr int EPT = 32 * EPW;                         // epilogue threads
     constexpr int NPW = EPW / 4;                          // column parts of a strip (one per warp of a quadrant)
     constexpr int WC = TN / NPW;                          // accumulator columns per epilogue warp
 
@@ -145,11 +154,15 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id();
     const int crank = (int)cluster_ctarank();  // 0 = leader CTA of the pair
+    // the streamed ring: a[0..4], or b_lo[0..3] + a[0..4] (contiguous) when there is no lo operand
+    const int n_stages = p.single ? min(kMaxStages, max(2, p.ring)) : kStages;
+    const uint32_t ring0 = p.single ? smem_u32(sm.b_lo[0]) + (uint32_t)(kMaxStages - n_stages) * kChunkBytes
+                                    : smem_u32(sm.a[0]);
     const int n_tasks = p.B * p.n_strips * p.n_splits;
     const int task0 = (int)blockIdx.x >> 1, task_step = (int)gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(smem_u32(&sm.full[s]), 1);
             mbar_init(smem_u32(&sm.empty[s]), 1);
         }
@@ -197,15 +210,15 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_wait(smem_u32(&sm.b_empty[kc]), b_phase ^ 1);
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&sm.b_full[kc]);
-                            if (crank == 0) mbar_expect_tx(bar, 4u * kChunkBytes);
+                            if (crank == 0) mbar_expect_tx(bar, 2u * n_hl * kChunkBytes);
                             tma_load_2d_pair(&tmB, bar & kPeerBitMask, smem_u32(sm.b_hi[kc]), kc * BK, rowB);
-                            tma_load_2d_pair(&tmB, bar & kPeerBitMask, smem_u32(sm.b_lo[kc]), kc * BK,
-                                             p.B * p.Np + rowB);
+                            if (n_hl == 2)
+                                tma_load_2d_pair(&tmB, bar & kPeerBitMask, smem_u32(sm.b_lo[kc]), kc * BK,
+                                                 p.B * p.Np + rowB);
                         }
                         __syncwarp();
                     }
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {
+                    for (int hl = 0; hl < n_hl; ++hl) {
                         mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&sm.full[stage]);
@@ -213,12 +226,12 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (crank == 0) mbar_arrive(bar);
                             } else {
                                 if (crank == 0) mbar_expect_tx(bar, 2u * kChunkBytes);
-                                tma_load_2d_pair(&tmA, bar & kPeerBitMask, smem_u32(sm.a[stage]), kc * BK,
+                                tma_load_2d_pair(&tmA, bar & kPeerBitMask, ring0 + (uint32_t)stage * kChunkBytes, kc * BK,
                                                  hl * p.B * p.Mp + rowA);
                             }
                         }
                         __syncwarp();
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -242,25 +255,30 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kc = 0; kc < p.KC; ++kc) {
                         if (m == t.m0) mbar_wait(smem_u32(&sm.b_full[kc]), b_phase);
                         const uint64_t bh = desc(smem_u32(sm.b_hi[kc])), bl = desc(smem_u32(sm.b_lo[kc]));
-                        // A_hi chunk: A_hi*B_hi + A_hi*B_lo
+                        // A_hi chunk: A_hi*B_hi + A_hi*B_lo (single: the only product)
                         mbar_wait(smem_u32(&sm.full[stage]), phase);
                         tc_fence_after();
-                        uint64_t ad = desc(smem_u32(sm.a[stage]));
+                        uint64_t ad = desc(ring0 + (uint32_t)stage * kChunkBytes);
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {  // +32 bytes per K=16 step: +2 in the address field
                                 if (p.dev & 1) break;
                                 tc_mma_bf16_pair(d, ad + 2 * k, bh + 2 * k, kIdesc, (kc | k) != 0);
-                                tc_mma_bf16_pair(d, ad + 2 * k, bl + 2 * k, kIdesc, 1);
+                                if (n_hl == 2) tc_mma_bf16_pair(d, ad + 2 * k, bl + 2 * k, kIdesc, 1);
                             }
                             tc_commit_pair(smem_u32(&sm.empty[stage]));  // frees the slot once these retire
+                            if (n_hl == 1) {
+                                if (m == t.m1 - 1) tc_commit_pair(smem_u32(&sm.b_empty[kc]));
+                                if (kc == p.KC - 1) tc_commit_pair(smem_u32(&sm.tmem_full[acc]));
+                            }
                         }
                         __syncwarp();
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                        if (n_hl == 1) continue;
                         // A_lo chunk: A_lo*B_hi
                         mbar_wait(smem_u32(&sm.full[stage]), phase);
                         tc_fence_after();
-                        ad = desc(smem_u32(sm.a[stage]));
+                        ad = desc(ring0 + (uint32_t)stage * kChunkBytes);
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
@@ -273,7 +291,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (kc == p.KC - 1) tc_commit_pair(smem_u32(&sm.tmem_full[acc]));  // accumulator ready
                         }
                         __syncwarp();
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
@@ -453,7 +471,8 @@ __global__ void __launch_bounds__(256, 4)
 tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloat16 *__restrict__ outa,
                const float *__restrict__ fb, int rows_b, int rows_pb, __nv_bfloat16 *__restrict__ outb,
                int B, int C, int normalize, int skip, float *__restrict__ bg_a /* (B,rows_pa) */,
-               float *__restrict__ bg_b /* (B,rows_pb) */, float *__restrict__ s00 /* (B) */) {
+               float *__restrict__ bg_b /* (B,rows_pb) */, float *__restrict__ s00 /* (B) */,
+               int single /* 1: the hi plane holds fp16(x), no lo plane is written */) {
     // both operands in one launch: warps [0, B*rows_pa/2) prepare A', the rest prepare B'
     int gr = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * kPrepRows;
     const bool second = gr >= B * rows_pa;
@@ -482,6 +501,11 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
     };
     auto inv_of = [&](float ss) { return normalize ? fmaxf(sqrtf(warp_sum(ss)), 1e-12f) : 1.f; };
     auto split_store = [&](float4 v, uint2 *hi, uint2 *lo, int q) {  // 4 values -> bf16 hi / lo, 8 bytes each
+        if (single) {  // one fp16 value per element (|x| <= 1: no range problem, 2^-12 relative)
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            hi[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+            return;
+        }
         const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
         const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
         const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y),
@@ -508,7 +532,10 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
 #pragma unroll
             for (int it = 0; it < NQ; ++it) {
                 const int q = it * 32 + lane;
-                if (q < nq) { hi[q] = make_uint2(0u, 0u); lo[q] = make_uint2(0u, 0u); }
+                if (q < nq) {
+                    hi[q] = make_uint2(0u, 0u);
+                    if (!single) lo[q] = make_uint2(0u, 0u);
+                }
             }
             if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
             continue;
@@ -659,7 +686,7 @@ __global__ void __launch_bounds__(1024)
 tc_bg_gather_kernel(const float *__restrict__ fgcol, int Cn, int Np, int C, int B,
                     const __nv_bfloat16 *__restrict__ Bm /* (2, B*Np, C) */, const float4 *__restrict__ Gall,
                     __nv_bfloat16 *__restrict__ Bc /* (2, B*Np, C) */, float4 *__restrict__ Gc,
-                    int *__restrict__ strip_count /* (B) */) {
+                    int *__restrict__ strip_count /* (B) */, int n_planes /* 2: hi + lo, 1: hi only */) {
     __shared__ int s_list[4096];
     __shared__ int s_warp[32];
     __shared__ int s_total;
@@ -701,8 +728,8 @@ tc_bg_gather_kernel(const float *__restrict__ fgcol, int Cn, int Np, int C, int 
     // gather the rows (hi and lo halves, 16 bytes per thread and trip), zero the padding
     const int v4 = C / 8;  // uint4 per row half
     const size_t half_rows = (size_t)B * Np;
-    for (int e = part_id * 1024 + tid; e < padded * 2 * v4; e += 1024 * n_parts) {
-        const int q = e / (2 * v4), r = e - q * 2 * v4, part = r / v4, x = r - part * v4;
+    for (int e = part_id * 1024 + tid; e < padded * n_planes * v4; e += 1024 * n_parts) {
+        const int q = e / (n_planes * v4), r = e - q * n_planes * v4, part = r / v4, x = r - part * v4;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
         if (q < nbg)
             val = __ldg(reinterpret_cast<const uint4 *>(Bm + (part * half_rows + (size_t)b * Np + s_list[q]) * C) + x);
@@ -718,7 +745,8 @@ tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restric
                       const float *__restrict__ w1, int R, int Mp, int n_part,
                       float *__restrict__ rowsumA, float *__restrict__ pred,
                       const float *__restrict__ corr4 /* (B,n_part_c,4,Mp) or null */, int n_part_c,
-                      const int *__restrict__ strip_count /* (B): live strips of corr4 */) {
+                      const int *__restrict__ strip_count /* (B): live strips of corr4 */,
+                      int parts_per_strip) {
     const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     float a[4] = {0.f, 0.f, 0.f, 0.f};
@@ -727,7 +755,7 @@ tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restric
         for (int k = 0; k < 4; ++k) a[k] += rowpart4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
     if (corr4) {  // take the background columns' share out again (two partials per live strip)
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const int live = 2 * strip_count[b];
+        const int live = parts_per_strip * strip_count[b];
         for (int t = 0; t < live; ++t)
 #pragma unroll
             for (int k = 0; k < 4; ++k) c[k] += corr4[(((size_t)b * n_part_c + t) * 4 + k) * Mp + i];
@@ -814,7 +842,7 @@ static Ws carve(void *base, int B, int rows1, int rows2, int C) {
     w.s00 = (float *)take(B * 4);
     w.lbg = (float *)take(B * 8);
     w.rowmax = (float *)take(B * 4 * ns * Mp * 4);
-    w.rowpart_c = (float *)take(B * 2 * ns * 4 * Mp * 4);
+    w.rowpart_c = (float *)take(B * 4 * ns * 4 * Mp * 4);
     w.fgcol = (float *)take(B * Np * 4);
     w.Gall = (float4 *)take(B * Np * 16);
     w.Gc = (float4 *)take(B * Np * 16);
@@ -847,16 +875,27 @@ static int num_sms() {
 
 static int g_steps_per_task = 0;  // development knob: 0 = choose automatically
 static int g_fine_passes = 2;     // development knob: 3 = the original three full GEMM passes
+static int g_epi_warps_single = kEpiWarpsSingle;  // development knob: epilogue warps of the single-product mode (8 or 16)
+
+// epilogue warps per CTA / row partials per strip for these parameters
+static int g_ring_single = kMaxStages;            // development knob: ring slots of the single-product mode
+static int epw_of(const Params &p) { return p.single ? g_epi_warps_single : 8; }
 
 // rows1 x rows2 GEMM per instance
-static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp) {
+static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp, int single = 0) {
     if (C % BK != 0 || C > BK * kMaxKC) return PEM_E_UNSUPPORTED;
     if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
     p.B = B; p.R = rows1; p.Cn = rows2;
     p.Mp = pad_to(rows1, TM); p.Np = pad_to(rows2, TN);
     p.n_msteps = p.Mp / TM; p.n_strips = p.Np / TN; p.KC = C / BK;
     // Row steps per task: short tasks balance the CTA pairs (a pair runs ceil(tasks / pairs) of
-    // them) at the price of one strip reload (hidden) and one column fold per task.
+    // them) at the price of one strip reload (hidden) and one column fold per task.  With one
+    // product per element the MMAs of a step take a third of the time and the pass runs at the
+    // L2 -> shared-memory streaming rate (~16 B/clk per SM measured): a strip reload then costs about
+    // as much as half a step of streamed rows, so long tasks win (statistics pass of 16 instances:
+    // 46 us at 2 steps per task, 40 us at 8).
+    p.single = single;
+    const double reload = single ? 0.75 : 0.25;
     const int pairs = max(1, num_sms() / 2);
     int best = p.n_msteps;
     double best_cost = 1e30;
@@ -869,6 +908,7 @@ static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp
     }
     p.spt = g_steps_per_task > 0 ? min(g_steps_per_task, p.n_msteps) : best;
     p.n_splits = (p.n_msteps + p.spt - 1) / p.spt;
+    p.ring = g_ring_single;
     p.temp = temp;
     p.c1 = 1.4426950408889634f / temp;
     p.c2 = 1.4426950408889634f / temp;
@@ -881,22 +921,28 @@ static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const fl
                         float *s00) {
     const int grid = (B * (p.Mp + p.Np) / kPrepRows + 7) / 8;
     auto go = [&](auto kern) {
-        kern<<<grid, 256, 0, st>>>(f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip, bg_a, bg_b, s00);
+        kern<<<grid, 256, 0, st>>>(f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip, bg_a, bg_b, s00,
+                                   p.single);
     };
     if (C <= 128) go(tc_prep_kernel<1>);
     else go(tc_prep_kernel<2>);
 }
 
-template <int MODE>
-static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
-    constexpr int kThreads = 64 + 32 * epi_warps(MODE);
+template <int MODE, int EPW>
+static int launch_pass_w(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
+    constexpr int kThreads = 64 + 32 * EPW;
     const size_t smem = sizeof(Smem) + 1024;
     static size_t cached = 0;
-    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE>, smem, &cached)) return rc;
+    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE, EPW>, smem, &cached)) return rc;
     const int n_tasks = p.B * p.n_strips * p.n_splits;
     const int pairs = min(max(1, num_sms() / 2), n_tasks);  // one cluster of two CTAs per SM pair
-    fine_tc_kernel<MODE><<<2 * pairs, kThreads, smem, st>>>(tmA, tmB, p);
+    fine_tc_kernel<MODE, EPW><<<2 * pairs, kThreads, smem, st>>>(tmA, tmB, p);
     return pem_launch_status();
+}
+template <int MODE>
+static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
+    if (MODE != kStore && epw_of(p) == 16) return launch_pass_w<MODE, MODE == kStore ? 8 : 16>(tmA, tmB, p, st);
+    return launch_pass_w<MODE, 8>(tmA, tmB, p, st);
 }
 
 }  // namespace tc
@@ -907,6 +953,8 @@ using namespace pem::tc;
 
 extern "C" void pem_dev_set_fine_steps_per_task(int v) { g_steps_per_task = v; }
 extern "C" void pem_dev_set_fine_passes(int v) { g_fine_passes = v == 3 ? 3 : 2; }
+extern "C" void pem_dev_set_fine_epi_warps(int v) { g_epi_warps_single = v == 8 ? 8 : 16; }
+extern "C" void pem_dev_set_fine_ring(int v) { g_ring_single = v < 2 ? 2 : v > kMaxStages ? kMaxStages : v; }
 
 // fine.cu
 namespace pem {
@@ -946,11 +994,12 @@ extern "C" int pem_feature_similarity_tc(const float *f1, const float *f2, int B
     return launch_pass<kStore>(tmA, tmB, p, st);
 }
 
-extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const float *pts2,
-                              const float *model, int B, int N1, int N2, int C, int Nm, float temp,
-                              float dis_thres, float *R, float *t, float *score, float *w1_out,
-                              float *w2_out, float *rowsum_out, float *pred_out, void *workspace,
-                              size_t workspace_bytes, pem_stream_t stream) {
+extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *pts1, const float *pts2,
+                                 const float *model, int B, int N1, int N2, int C, int Nm, float temp,
+                                 float dis_thres, int precision, float *R, float *t, float *score,
+                                 float *w1_out, float *w2_out, float *rowsum_out, float *pred_out,
+                                 void *workspace, size_t workspace_bytes, pem_stream_t stream) {
+    PEM_REQUIRE(precision == PEM_PREC_SPLIT_BF16 || precision == PEM_PREC_FP16, PEM_E_UNSUPPORTED);
     PEM_REQUIRE_PTR(f1);
     PEM_REQUIRE_PTR(f2);
     PEM_REQUIRE_PTR(pts1);
@@ -962,7 +1011,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE((uintptr_t)f1 % 16 == 0 && (uintptr_t)f2 % 16 == 0, PEM_E_UNSUPPORTED);  // 16-byte row loads
     Params p{};
-    if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;  // the background token stays out of the GEMM
+    // the background token stays out of the GEMM
+    if (int rc = fill_common(p, B, N1, N2, C, temp, precision == PEM_PREC_FP16)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
@@ -978,7 +1028,8 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
 
     const int mx = max(p.Mp, p.Np);
-    const int n_part = 2 * p.n_strips, planes = 2 * p.n_splits;
+    const int pps = epw_of(p) / 4;  // row partials per strip: one per epilogue warp of a quadrant
+    const int n_part = pps * p.n_strips, planes = 2 * p.n_splits;
     const bool two_pass = g_fine_passes == 2 && p.Np <= 4096;
     // pass 1: softmax statistics
     p.rowpart = w.rowpart;
@@ -996,13 +1047,13 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         p.G = w.Gall;
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
-        const int n_part_m = (epi_warps(kLabelW) / 4) * p.n_strips;  // row partials of the merged pass
+        const int n_part_m = n_part;
         tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
             w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part_m,
             planes, p.c1, p.c2, w1, w2_out, nullptr, w.fgcol);
         // the background columns, compacted, and a short ragged pass that takes their share out again
         tc_bg_gather_kernel<<<dim3(B, 8), 1024, 0, st>>>(w.fgcol, p.Cn, p.Np, C, B, w.Bm, w.Gall, w.Bc, w.Gc,
-                                                w.strip_count);
+                                                w.strip_count, p.single ? 1 : 2);
         CUtensorMap tmC;
         if (int rc = make_operand_map(&tmC, w.Bc, (size_t)2 * B * p.Np, C)) return rc;
         Params pc = p;
@@ -1012,7 +1063,7 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         pc.strip_major = 1;
         if (int rc = launch_pass<kWsum>(tmA, tmC, pc, st)) return rc;
         tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
-            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part_m, rsA, pred, w.rowpart_c, n_part, w.strip_count);
+            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part_m, rsA, pred, w.rowpart_c, n_part, w.strip_count, pps);
     } else {
         // pass 2: foreground labels
         p.rowmaxpart = w.rowpart;
@@ -1025,11 +1076,20 @@ extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
         tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
-            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, 0, nullptr);
+            w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, 0, nullptr, pps);
     }
     // weighted Procrustes + pose score (fine.cu)
     return fine_tail_launch(pred, pts1, rsA, w1, model, B, N1, Nm, dis_thres, w.counters, R, t,
                             score, st);
+}
+
+extern "C" int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const float *pts2,
+                              const float *model, int B, int N1, int N2, int C, int Nm, float temp,
+                              float dis_thres, float *R, float *t, float *score, float *w1_out,
+                              float *w2_out, float *rowsum_out, float *pred_out, void *workspace,
+                              size_t workspace_bytes, pem_stream_t stream) {
+    return pem_fine_fused_ex(f1, f2, pts1, pts2, model, B, N1, N2, C, Nm, temp, dis_thres, PEM_PREC_SPLIT_BF16, R,
+                             t, score, w1_out, w2_out, rowsum_out, pred_out, workspace, workspace_bytes, stream);
 }
 
 // Development: time one GEMM pass (mode 1 stats, 2 label, 3 wsum) with parts of the kernel disabled
@@ -1038,7 +1098,7 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
                                  int flags, int mode, int prep, void *workspace, size_t workspace_bytes,
                                  pem_stream_t stream) {
     Params p{};
-    if (int rc = fill_common(p, B, N1, N2, C, temp)) return rc;
+    if (int rc = fill_common(p, B, N1, N2, C, temp, (flags >> 3) & 1)) return rc;
     cudaStream_t st = pem_cu_stream(stream);
     Ws w = carve(workspace, B, N1, N2, C);
     if (workspace_bytes < w.bytes) return PEM_E_WORKSPACE;
@@ -1047,7 +1107,7 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
-    p.dev = flags;
+    p.dev = flags & 7;  // (bit 3: the single-product fp16 mode; `prep` must have run in the same mode)
     p.rowpart = p.rowmaxpart = p.rowpart4 = w.rowpart;
     p.colpart = w.colpart;
     p.lrs = w.lrs;
@@ -1063,13 +1123,22 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
 }
 
 // One reducing GEMM pass on its own (profiling hook, see pem_b200.h)
-extern "C" int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
-                                   int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream) {
+extern "C" int pem_fine_fused_pass_ex(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
+                                      int pass, int precision, void *workspace, size_t workspace_bytes,
+                                      pem_stream_t stream) {
+    PEM_REQUIRE(precision == PEM_PREC_SPLIT_BF16 || precision == PEM_PREC_FP16, PEM_E_UNSUPPORTED);
     PEM_REQUIRE_PTR(f1);
     PEM_REQUIRE_PTR(f2);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0, PEM_E_SHAPE);
     PEM_REQUIRE(pass >= 1 && pass <= 4, PEM_E_UNSUPPORTED);
     PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
-    return pem_dev_fine_pass(f1, f2, B, N1, N2, C, temp, 0, pass, 0, workspace, workspace_bytes, stream);
+    return pem_dev_fine_pass(f1, f2, B, N1, N2, C, temp, precision == PEM_PREC_FP16 ? 8 : 0, pass, 0, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
+                                   int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream) {
+    return pem_fine_fused_pass_ex(f1, f2, B, N1, N2, C, temp, pass, PEM_PREC_SPLIT_BF16, workspace, workspace_bytes,
+                                  stream);
 }

@@ -171,6 +171,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with A = B = F16 (format field 0): 11 significant bits instead of 8
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- CTA pairs (tcgen05 cta_group::2): one MMA spans two SMs of a cluster
 // TMA load whose completion is signalled on the LEADER CTA's mbarrier (`leader_bar` = own barrier
 // address with the CTA-parity bit cleared)

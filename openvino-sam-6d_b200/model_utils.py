@@ -168,12 +168,18 @@ def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, return_st
     return R, t, score
 
 
+FINE_PRECISIONS = {"split_bf16": 0, "fp16": 1}  # PEM_PREC_* of include/pem_b200.h
+
+
 def compute_fine_Rt_fused(feat1, feat2, pts1, pts2, model_pts=None, temp=0.1, dis_thres=0.15,
-                          return_stages=False):
+                          return_stages=False, precision="split_bf16"):
     """compute_feature_similarity(feat1, feat2, 'cosine', temp, True) followed by
     compute_fine_Rt(...), fused: the attention matrix never exists in memory.
     feat1 (B,N1+1,C), feat2 (B,N2+1,C) carry the background token in row 0
-    (fine_point_matching.py:48-51)."""
+    (fine_point_matching.py:48-51).  precision: "split_bf16" (three bf16 products per element,
+    fp32-class logits) or "fp16" (one fp16 product, logits to ~1e-3 of +-1/temp)."""
+    if precision not in FINE_PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(FINE_PRECISIONS))
     f1, f2 = _f32c(feat1, "feat1"), _f32c(feat2, "feat2")
     pts1, pts2 = _f32c(pts1, "pts1"), _f32c(pts2, "pts2")
     model_pts = pts2 if model_pts is None else _f32c(model_pts, "model_pts")
@@ -192,11 +198,11 @@ def compute_fine_Rt_fused(feat1, feat2, pts1, pts2, model_pts=None, temp=0.1, di
     ws = _ws(nbytes, dev)
     p = lambda x: None if x is None else x.data_ptr()
     with torch.cuda.device(dev):
-        _lib.check(L.pem_fine_fused(f1.data_ptr(), f2.data_ptr(), pts1.data_ptr(), pts2.data_ptr(),
-                                    model_pts.data_ptr(), B, N1, N2, C, Nm, float(temp),
-                                    float(dis_thres), R.data_ptr(), t.data_ptr(), score.data_ptr(),
-                                    p(w1), p(w2), p(row), p(pred), ws.data_ptr(), nbytes,
-                                    _ext._stream()), "pem_fine_fused")
+        _lib.check(L.pem_fine_fused_ex(f1.data_ptr(), f2.data_ptr(), pts1.data_ptr(), pts2.data_ptr(),
+                                       model_pts.data_ptr(), B, N1, N2, C, Nm, float(temp),
+                                       float(dis_thres), FINE_PRECISIONS[precision], R.data_ptr(),
+                                       t.data_ptr(), score.data_ptr(), p(w1), p(w2), p(row), p(pred),
+                                       ws.data_ptr(), nbytes, _ext._stream()), "pem_fine_fused_ex")
     if return_stages:
         return R, t, score, {"w1": w1, "w2": w2, "row": row, "pred": pred}
     return R, t, score

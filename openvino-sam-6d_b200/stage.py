@@ -27,19 +27,21 @@ import torch
 
 from . import _lib
 
+FINE_PRECISIONS = {"split_bf16": 0, "fp16": 1}  # PEM_PREC_* of include/pem_b200.h
 PE_SCALES = ((0.1, 32), (0.2, 64))  # config/base.yaml:48-49, fine_point_matching.py:103
 
 
 class GeometricStage:
     def __init__(self, batch, device, n_dense=2048, n_sparse=196, feat_dim=256, n_model=1024,
                  n_proposal1=6000, n_proposal2=300, temp=0.1, dis_thres=0.15, use_graph=True,
-                 fine_mode="fused"):
+                 fine_mode="fused", fine_precision="fp16"):
         self.B, self.N, self.M, self.C, self.Nm = batch, n_dense, n_sparse, feat_dim, n_model
         self.P1, self.P2, self.temp, self.dis_thres = n_proposal1, n_proposal2, temp, dis_thres
         self.dev = torch.device(device)
         self.L = _lib.lib()
         self.n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.fine_mode = fine_mode
+        self.fine_precision = FINE_PRECISIONS[fine_precision]  # PEM_PREC_* of the fused fine GEMM
         B, N, M, C, Nm, P1, P2 = batch, n_dense, n_sparse, feat_dim, n_model, n_proposal1, n_proposal2
         f32 = dict(dtype=torch.float32, device=self.dev)
         i32 = dict(dtype=torch.int32, device=self.dev)
@@ -168,10 +170,10 @@ class GeometricStage:
                                  p(self.sparse_fine[blk]), 0, st), "gather fine"); n += 1
         # 4. fine
         if self.fine_mode == "fused":
-            ck(L.pem_fine_fused(p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]),
-                                p(self.model), B, N, N, C, Nm, self.temp, self.dis_thres, p(self.R),
-                                p(self.t), p(self.score), None, None, None, None, p(self.ws),
-                                self.ws_bytes, st), "fine_fused"); n += 10
+            ck(L.pem_fine_fused_ex(p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]),
+                                   p(self.model), B, N, N, C, Nm, self.temp, self.dis_thres,
+                                   self.fine_precision, p(self.R), p(self.t), p(self.score), None, None,
+                                   None, None, p(self.ws), self.ws_bytes, st), "fine_fused"); n += 10
         else:
             self._enqueue_fine_materialised(); n += 12
         self.stream.wait_stream(self.side)  # join

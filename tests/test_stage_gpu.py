@@ -20,11 +20,11 @@ def cpu_result(pkg, oracle):
     return batch, R, t, s, st
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_stage_matches_cpu_reference(pkg, oracle, dev, cpu_result, use_graph):
+@pytest.mark.parametrize("use_graph,fine_precision", [(False, "fp16"), (True, "fp16"), (True, "split_bf16")])
+def test_stage_matches_cpu_reference(pkg, oracle, dev, cpu_result, use_graph, fine_precision):
     batch, oR, ot, os_, ost = cpu_result
     B = 2
-    stage = pkg.stage.GeometricStage(B, dev, use_graph=use_graph)
+    stage = pkg.stage.GeometricStage(B, dev, use_graph=use_graph, fine_precision=fine_precision)
     stage.load(batch)
     for _ in range(2):  # second run replays the captured graph
         stage.run()

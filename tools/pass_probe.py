@@ -20,17 +20,20 @@ ws = torch.empty(nb, dtype=torch.uint8, device=dev)
 R = torch.empty(B, 9, device=dev); t = torch.empty(B, 3, device=dev); sc = torch.empty(B, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 lib = pkg._lib.lib()
-rc = lib.pem_fine_fused(f1.data_ptr(), f2.data_ptr(), b["dense_pm"].data_ptr(), b["dense_po"].data_ptr(), b["model"].data_ptr(),
-                        B, N, N, C, b["model"].shape[1], 0.1, 0.15, R.data_ptr(), t.data_ptr(), sc.data_ptr(),
-                        None, None, None, None, ws.data_ptr(), nb, st)
+SINGLE = int(os.environ.get("SINGLE", 0))  # 1: the single-product fp16 mode (flag bit 3)
+L.pem_dev_set_fine_epi_warps(int(os.environ.get("EPW", 16)))
+L.pem_dev_set_fine_ring(int(os.environ.get("RING", 9)))
+rc = lib.pem_fine_fused_ex(f1.data_ptr(), f2.data_ptr(), b["dense_pm"].data_ptr(), b["dense_po"].data_ptr(), b["model"].data_ptr(),
+                           B, N, N, C, b["model"].shape[1], 0.1, 0.15, SINGLE, R.data_ptr(), t.data_ptr(), sc.data_ptr(),
+                           None, None, None, None, ws.data_ptr(), nb, st)
 assert rc == 0, rc
 torch.cuda.synchronize()
-for spt in (0,):
+for spt in [int(x) for x in os.environ.get("SPT", "0").split(",")]:
     L.pem_dev_set_fine_steps_per_task(spt)
-    for mode in (1, 4, 2, 3):  # statistics, labels + weighted sums (merged), labels, weighted sums
-        for flags in (0, 4, 2, 6, 7):
+    for mode in [int(x) for x in os.environ.get("MODES", "1,4,2,3").split(",")]:  # statistics, labels + weighted sums (merged), labels, weighted sums
+        for flags in [int(x) for x in os.environ.get("FLAGS", "0,4,2,6,7").split(",")]:
             def run(prep=0):
-                rc = L.pem_dev_fine_pass(f1.data_ptr(), f2.data_ptr(), B, N, N, C, 0.1, flags, mode, prep, ws.data_ptr(), nb, st)
+                rc = L.pem_dev_fine_pass(f1.data_ptr(), f2.data_ptr(), B, N, N, C, 0.1, flags | (8 * SINGLE), mode, prep, ws.data_ptr(), nb, st)
                 assert rc == 0, rc
             for _ in range(3): run()
             torch.cuda.synchronize()
@@ -39,4 +42,4 @@ for spt in (0,):
             for _ in range(10): run()
             e1.record(); torch.cuda.synchronize()
             names = [n for bit, n in ((1, "noMMA"), (2, "noLoad"), (4, "noEpi")) if flags & bit]
-            print(f"steps/task {spt} mode {mode} {'+'.join(names) or 'full'}: pass {e0.elapsed_time(e1) / 10 * 1e3:.1f} us", flush=True)
+            print(f"single {SINGLE} epw {os.environ.get('EPW', 16)} ring {os.environ.get('RING', 9)} steps/task {spt} mode {mode} {'+'.join(names) or 'full'}: pass {e0.elapsed_time(e1) / 10 * 1e3:.1f} us", flush=True)

@@ -50,6 +50,8 @@
 //               32 columns + a 4-quadrant combine in shared memory) into one partial plane per
 //               (row split, CTA).  Validity masks are folded into the per-row / per-column
 //               constants (+inf offsets).
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 
 namespace pem {
@@ -319,16 +321,27 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // steps of the task (cheapest in instructions).  kLabelW has no registers to spare for that:
             // it folds each 32-column chunk across the warp's 32 rows at once (31-shuffle transpose
             // reduce) and keeps only lane L's column of every chunk.
+            // The arithmetic is issued as fp32 PAIRS (FFMA2 / FADD2, tc_ptx.cuh) over adjacent columns:
+            // the epilogue is what bounds the single-product passes, and it is bound by issue slots.
             constexpr bool COLREG = MODE == kStats || MODE == kLabel;
-            float colacc[COLREG ? WC : 1];
+            float colacc[MODE == kLabel ? WC : 1];          // kLabel: column maxima
+            uint64_t colacc2[MODE == kStats ? WC / 2 : 1];  // kStats: column sums, two columns per register pair
             float cmx[WC / 32];
 #pragma unroll
-            for (int q = 0; q < (COLREG ? WC : 1); ++q) colacc[q] = LAB ? -INFINITY : 0.f;
+            for (int q = 0; q < (MODE == kLabel ? WC : 1); ++q) colacc[q] = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < (MODE == kStats ? WC / 2 : 1); ++q) colacc2[q] = 0ull;
 #pragma unroll
             for (int q = 0; q < WC / 32; ++q) cmx[q] = -INFINITY;
-            // per-column constants of the task (+inf keeps padded columns out of the row max)
-            if (LAB && ep_tid < TN) sm.colc[ep_tid] = p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
-            if (WS && ep_tid < TN) sm.G[ep_tid] = p.G[(size_t)b * p.Np + n * TN + ep_tid];
+            // per-column constants of the task.  colc = -log2 colsum_j (-inf keeps padded columns out of
+            // the row max).  G is stored by column PAIRS: G[2k] = (w, w', x, x'), G[2k+1] = (y, y', z, z')
+            // of columns 2k and 2k+1, so that one LDS.128 feeds two FFMA2.
+            if (LAB && ep_tid < TN) sm.colc[ep_tid] = -p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
+            if (WS && ep_tid < TN) {
+                const float4 g = p.G[(size_t)b * p.Np + n * TN + ep_tid];
+                float *gp = reinterpret_cast<float *>(&sm.G[ep_tid & ~1]) + (ep_tid & 1);
+                gp[0] = g.w; gp[2] = g.x; gp[4] = g.y; gp[6] = g.z;
+            }
             if (LAB || WS) epi_barrier<EPT>();
 
             for (int m = t.m0; m < t.m1; ++m) {
@@ -338,7 +351,10 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (MODE == kStats) rowc = row_ok ? kc2 : INFINITY;  // e = 0 for padded rows
                 if (LAB) rowc = p.lrs[(size_t)b * p.Mp + gi];  // +inf for padded rows
                 float rm = -INFINITY;                           // label: row maximum
-                float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;   // statistics / weighted sums
+                // statistics: two pairs of row sums; weighted sums: (even, odd column) pairs of w, x, y, z
+                uint64_t a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
+                const uint64_t K1 = pack2(kc1, kc1), K2X = pack2(kc2x, kc2x), NROW = pack2(-rowc, -rowc),
+                               NC2 = pack2(-2.0f * kc2, -2.0f * kc2);
                 mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
                 tc_fence_after();
                 // columns per TMEM load: 16 where 128 column accumulators already fill the registers
@@ -358,30 +374,44 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (c * CW + q < ncols) dst[q] = __fdiv_rn(v[q], ktemp);
                         }
                     } else if (MODE == kStats) {
-                        if (ncols >= WC) {
+                        // two pairs at a time: the adds do not wait on each other.  MASK: the last strip's
+                        // padded columns contribute nothing (a separate copy: predicated-off selects would
+                        // still take issue slots on every other strip)
+                        auto stats_chunk = [&](auto mask_tag) {
+                            constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll
-                            for (int q = 0; q < CW; ++q) {
-                                const float e = ex2(fmaf(v[q], kc1, -rowc));
-                                r0 += e;
-                                colacc[c * CW + q] += e;
+                            for (int q = 0; q < CW; q += 4) {
+                                float e0, e1, e2, e3;
+                                unpack2(fma2(pack2(v[q], v[q + 1]), K1, NROW), e0, e1);
+                                unpack2(fma2(pack2(v[q + 2], v[q + 3]), K1, NROW), e2, e3);
+                                e0 = ex2(e0); e1 = ex2(e1); e2 = ex2(e2); e3 = ex2(e3);
+                                if (MASK) {
+                                    if (c * CW + q >= ncols) e0 = 0.f;
+                                    if (c * CW + q + 1 >= ncols) e1 = 0.f;
+                                    if (c * CW + q + 2 >= ncols) e2 = 0.f;
+                                    if (c * CW + q + 3 >= ncols) e3 = 0.f;
+                                }
+                                const uint64_t p01 = pack2(e0, e1), p23 = pack2(e2, e3);
+                                a0 = add2(a0, p01);
+                                a1 = add2(a1, p23);
+                                colacc2[(c * CW + q) / 2] = add2(colacc2[(c * CW + q) / 2], p01);
+                                colacc2[(c * CW + q) / 2 + 1] = add2(colacc2[(c * CW + q) / 2 + 1], p23);
                             }
-                        } else {  // last strip: mask padded columns
-#pragma unroll
-                            for (int q = 0; q < CW; ++q) {
-                                const float e = (c * CW + q < ncols) ? ex2(fmaf(v[q], kc1, -rowc)) : 0.f;
-                                r0 += e;
-                                colacc[c * CW + q] += e;
-                            }
-                        }
+                        };
+                        if (ncols >= WC) stats_chunk(std::false_type{});
+                        else stats_chunk(std::true_type{});
                     }
                     if (LAB) {
 #pragma unroll
                         for (int q = 0; q < CW; q += 4) {
-                            const float4 cc = lds_f4(&sm.colc[half * WC + c * CW + q]);
+                            const float4 cc = lds_f4(&sm.colc[half * WC + c * CW + q]);  // -log2 colsum_j
                             // 2 s/temp - log colsum_j (row side), 2 s/temp - log rowsum_i (column side)
-                            rm = fmaxf(fmaxf(rm, fmaf(v[q], kc2x, -cc.x)), fmaf(v[q + 1], kc2x, -cc.y));
-                            rm = fmaxf(fmaxf(rm, fmaf(v[q + 2], kc2x, -cc.z)), fmaf(v[q + 3], kc2x, -cc.w));
-                            if (COLREG) {
+                            float t0, t1, t2, t3;
+                            unpack2(fma2(pack2(v[q], v[q + 1]), K2X, pack2(cc.x, cc.y)), t0, t1);
+                            unpack2(fma2(pack2(v[q + 2], v[q + 3]), K2X, pack2(cc.z, cc.w)), t2, t3);
+                            rm = fmaxf(fmaxf(rm, t0), t1);
+                            rm = fmaxf(fmaxf(rm, t2), t3);
+                            if (MODE == kLabel) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
                                     colacc[c * CW + q + u] = fmaxf(colacc[c * CW + q + u], fmaf(v[q + u], kc2x, -rowc));
@@ -390,18 +420,21 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (WS) {
 #pragma unroll
-                        for (int q = 0; q < CW; ++q) {
-                            const float u = ex2(fmaf(v[q], kc2x, -2.0f * kc2));  // e^2
-                            const float4 g = lds_f4(&sm.G[half * WC + c * CW + q]);
-                            r0 = fmaf(u, g.w, r0);
-                            r1 = fmaf(u, g.x, r1);
-                            r2 = fmaf(u, g.y, r2);
-                            r3 = fmaf(u, g.z, r3);
+                        for (int q = 0; q < CW; q += 2) {
+                            float u0, u1;
+                            unpack2(fma2(pack2(v[q], v[q + 1]), K2X, NC2), u0, u1);  // e^2
+                            const uint64_t u = pack2(ex2(u0), ex2(u1));
+                            const float4 gA = lds_f4(&sm.G[half * WC + c * CW + q]);      // (w, w', x, x')
+                            const float4 gB = lds_f4(&sm.G[half * WC + c * CW + q + 1]);  // (y, y', z, z')
+                            a0 = fma2(u, pack2(gA.x, gA.y), a0);
+                            a1 = fma2(u, pack2(gA.z, gA.w), a1);
+                            a2 = fma2(u, pack2(gB.x, gB.y), a2);
+                            a3 = fma2(u, pack2(gB.z, gB.w), a3);
                         }
                     }
                     if constexpr (LAB && !COLREG) {  // column side of the labels for this chunk (v is dead after this)
 #pragma unroll
-                        for (int q = 0; q < CW; ++q) v[q] = fmaf(v[q], kc2x, -rowc);
+                        for (int q = 0; q < CW; q += 2) unpack2(fma2(pack2(v[q], v[q + 1]), K2X, NROW), v[q], v[q + 1]);
                         cmx[c] = fmaxf(cmx[c], warp_transpose_reduce<true>(v));
                     }
                 }
@@ -412,11 +445,11 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // per-(row, half-strip) partials: consecutive lanes = consecutive rows
                 const size_t pr = ((size_t)b * NPW * p.n_strips + NPW * n + half);
-                if (MODE == kStats) p.rowpart[pr * p.Mp + gi] = r0;
+                if (MODE == kStats) p.rowpart[pr * p.Mp + gi] = sum2(a0) + sum2(a1);
                 if (LAB) p.rowmaxpart[pr * p.Mp + gi] = rm;
                 if (WS) {
                     float *dst = p.rowpart4 + pr * 4 * p.Mp + gi;
-                    dst[0] = r0; dst[p.Mp] = r1; dst[2 * p.Mp] = r2; dst[3 * p.Mp] = r3;
+                    dst[0] = sum2(a0); dst[p.Mp] = sum2(a1); dst[2 * p.Mp] = sum2(a2); dst[3 * p.Mp] = sum2(a3);
                 }
             }
             // fold the column accumulators across the 32 lanes, then across the 4 quadrants;
@@ -427,7 +460,10 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (COLREG) {
                         float v[32];
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = colacc[c * 32 + q];
+                        for (int q = 0; q < 32; q += 2) {
+                            if (MODE == kStats) unpack2(colacc2[(c * 32 + q) / 2], v[q], v[q + 1]);
+                            else { v[q] = colacc[c * 32 + q]; v[q + 1] = colacc[c * 32 + q + 1]; }
+                        }
                         sm.colred[quad][half * WC + c * 32 + lane] = warp_transpose_reduce<LAB>(v);
                     } else {
                         sm.colred[quad][half * WC + c * 32 + lane] = cmx[c];
@@ -466,38 +502,68 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (16-byte loads, 8-byte bf16x4 stores, every access of the warp one contiguous run; both rows'
 // loads are in flight together).  rows_pa and rows_pb are even.
 constexpr int kPrepRows = 2;
+// Persistent: every warp walks the row pairs with a stride and loads the NEXT pair's rows before it
+// works on the current one, so the global loads of one pair fly under the arithmetic and the stores
+// of the previous one (a warp per pair that loads, reduces, stores and exits ran at 3.3 TB/s).
 template <int NQ>  // ceil(C / 128): float4 per lane and row
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloat16 *__restrict__ outa,
                const float *__restrict__ fb, int rows_b, int rows_pb, __nv_bfloat16 *__restrict__ outb,
                int B, int C, int normalize, int skip, float *__restrict__ bg_a /* (B,rows_pa) */,
                float *__restrict__ bg_b /* (B,rows_pb) */, float *__restrict__ s00 /* (B) */,
                int single /* 1: the hi plane holds fp16(x), no lo plane is written */) {
-    // both operands in one launch: warps [0, B*rows_pa/2) prepare A', the rest prepare B'
-    int gr = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * kPrepRows;
-    const bool second = gr >= B * rows_pa;
-    if (second) gr -= B * rows_pa;
-    const float *f = second ? fb : fa, *fo = second ? fa : fb;
-    const int rows = second ? rows_b : rows_a, rows_p = second ? rows_pb : rows_pa;
-    const int rows_o = second ? rows_a : rows_b;
-    __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
-    if (gr >= B * rows_p) return;
-    const int b = gr / rows_p, i0 = gr - b * rows_p, lane = lane_id();  // rows i0, i0+1 of instance b
+    const int lane = lane_id();
     const int nq = C >> 2;  // float4 per row
-    float *bg = second ? bg_b : bg_a;
-    // a row as NQ float4 per lane (zero beyond the row); sum of squares (unreduced)
-    auto load_row = [&](const float *row, float4 (&x)[NQ]) {
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int total = B * (rows_pa + rows_pb) / kPrepRows;  // row pairs: A' first, then B'
+    // where a pair lives: operand, instance, first row
+    struct Where { bool second; int b, i0, gr; };
+    auto locate = [&](int pair) {
+        Where w;
+        w.gr = pair * kPrepRows;
+        w.second = w.gr >= B * rows_pa;
+        if (w.second) w.gr -= B * rows_pa;
+        const int rows_p = w.second ? rows_pb : rows_pa;
+        w.b = w.gr / rows_p;
+        w.i0 = w.gr - w.b * rows_p;
+        return w;
+    };
+    // raw loads of a pair's rows (zero beyond the row / for padding rows); nothing waits on them here
+    auto fetch = [&](int pair, float4 (&x)[kPrepRows][NQ]) {
+        const Where w = locate(pair);
+        const float *f = w.second ? fb : fa;
+        const int rows = w.second ? rows_b : rows_a;
+#pragma unroll
+        for (int r = 0; r < kPrepRows; ++r) {
+            const bool live = w.i0 + r < rows;
+            const float *row = f + ((size_t)w.b * (rows + skip) + skip + w.i0 + r) * C;
+#pragma unroll
+            for (int it = 0; it < NQ; ++it) {
+                const int q = it * 32 + lane;
+                x[r][it] = (live && q < nq) ? __ldg(reinterpret_cast<const float4 *>(row) + q)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    auto sumsq = [&](const float4 (&x)[NQ]) {
         float s = 0.f;
 #pragma unroll
         for (int it = 0; it < NQ; ++it) {
-            const int q = it * 32 + lane;
-            x[it] = q < nq ? __ldg(reinterpret_cast<const float4 *>(row) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             s = fmaf(x[it].x, x[it].x, s);
             s = fmaf(x[it].y, x[it].y, s);
             s = fmaf(x[it].z, x[it].z, s);
             s = fmaf(x[it].w, x[it].w, s);
         }
         return s;
+    };
+    // a row as NQ float4 per lane (zero beyond the row); sum of squares (unreduced)
+    auto load_row = [&](const float *row, float4 (&x)[NQ]) {
+#pragma unroll
+        for (int it = 0; it < NQ; ++it) {
+            const int q = it * 32 + lane;
+            x[it] = q < nq ? __ldg(reinterpret_cast<const float4 *>(row) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return sumsq(x);
     };
     auto inv_of = [&](float ss) { return normalize ? fmaxf(sqrtf(warp_sum(ss)), 1e-12f) : 1.f; };
     auto split_store = [&](float4 v, uint2 *hi, uint2 *lo, int q) {  // 4 values -> bf16 hi / lo, 8 bytes each
@@ -513,63 +579,79 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
         hi[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
         lo[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
     };
-    float4 x[kPrepRows][NQ], tk[NQ];
-    float ss[kPrepRows];
+
+    int pair = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (pair >= total) return;
+    float4 x[kPrepRows][NQ], xn[kPrepRows][NQ], tk[NQ];
+    fetch(pair, x);
+    for (; pair < total; pair += n_warps) {
+        const bool more = pair + n_warps < total;
+        if (more) fetch(pair + n_warps, xn);
+        const Where w = locate(pair);
+        const bool second = w.second;
+        const int b = w.b, i0 = w.i0, gr = w.gr;  // rows i0, i0+1 of instance b
+        const float *f = second ? fb : fa, *fo = second ? fa : fb;
+        const int rows = second ? rows_b : rows_a, rows_p = second ? rows_pb : rows_pa;
+        const int rows_o = second ? rows_a : rows_b;
+        __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
+        float *bg = second ? bg_b : bg_a;
+        const float *tok = fo + (size_t)b * (rows_o + skip) * C;  // the other set's background token
+        float inv_tok = 1.f;
+        if (skip) inv_tok = inv_of(load_row(tok, tk));
 #pragma unroll
-    for (int r = 0; r < kPrepRows; ++r) {
-        ss[r] = 0.f;
-        if (i0 + r < rows) ss[r] = load_row(f + ((size_t)b * (rows + skip) + skip + i0 + r) * C, x[r]);
-    }
-    const float *tok = fo + (size_t)b * (rows_o + skip) * C;  // the other set's background token
-    float inv_tok = 1.f;
-    if (skip) inv_tok = inv_of(load_row(tok, tk));
+        for (int r = 0; r < kPrepRows; ++r) {
+            const int i = i0 + r;
+            uint2 *hi = reinterpret_cast<uint2 *>(out + (size_t)(gr + r) * C),
+                  *lo = reinterpret_cast<uint2 *>(out + ((size_t)B * rows_p + gr + r) * C);
+            if (i >= rows) {  // padding rows
 #pragma unroll
-    for (int r = 0; r < kPrepRows; ++r) {
-        const int i = i0 + r;
-        uint2 *hi = reinterpret_cast<uint2 *>(out + (size_t)(gr + r) * C),
-              *lo = reinterpret_cast<uint2 *>(out + ((size_t)B * rows_p + gr + r) * C);
-        if (i >= rows) {  // padding rows
+                for (int it = 0; it < NQ; ++it) {
+                    const int q = it * 32 + lane;
+                    if (q < nq) {
+                        hi[q] = make_uint2(0u, 0u);
+                        if (!single) lo[q] = make_uint2(0u, 0u);
+                    }
+                }
+                if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
+                continue;
+            }
+            // x * (1/norm) instead of the reference's x / norm: at most 1 ulp apart, far below the
+            // 2^-17 of the hi/lo split that follows, and 8 IEEE divisions per lane cheaper
+            const float rinv = 1.0f / inv_of(sumsq(x[r]));
+            float dot = 0.f;
 #pragma unroll
             for (int it = 0; it < NQ; ++it) {
                 const int q = it * 32 + lane;
-                if (q < nq) {
-                    hi[q] = make_uint2(0u, 0u);
-                    if (!single) lo[q] = make_uint2(0u, 0u);
+                if (q >= nq) continue;
+                float4 v = x[r][it];
+                if (normalize) { v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv; }
+                split_store(v, hi, lo, q);
+                if (skip) {
+                    dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot);
+                    dot = fmaf(v.z, tk[it].z, dot); dot = fmaf(v.w, tk[it].w, dot);
                 }
             }
-            if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
-            continue;
-        }
-        // x * (1/norm) instead of the reference's x / norm: at most 1 ulp apart, far below the
-        // 2^-17 of the hi/lo split that follows, and 8 IEEE divisions per lane cheaper
-        const float rinv = 1.0f / inv_of(ss[r]);
-        float dot = 0.f;
+            if (!skip) continue;
+            dot = __fdiv_rn(warp_sum(dot), inv_tok);
+            if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
+            if (!second && i == 0) {  // the corner: background token x background token
+                float4 own[NQ];
+                const float inv_own = inv_of(load_row(f + (size_t)b * (rows + skip) * C, own));
+                float d0 = 0.f;
 #pragma unroll
-        for (int it = 0; it < NQ; ++it) {
-            const int q = it * 32 + lane;
-            if (q >= nq) continue;
-            float4 v = x[r][it];
-            if (normalize) { v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv; }
-            split_store(v, hi, lo, q);
-            if (skip) {
-                dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot);
-                dot = fmaf(v.z, tk[it].z, dot); dot = fmaf(v.w, tk[it].w, dot);
+                for (int it = 0; it < NQ; ++it) {
+                    d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0);
+                    d0 = fmaf(own[it].z, tk[it].z, d0); d0 = fmaf(own[it].w, tk[it].w, d0);
+                }
+                d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
+                if (lane == 0) s00[b] = d0;
             }
         }
-        if (!skip) continue;
-        dot = __fdiv_rn(warp_sum(dot), inv_tok);
-        if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
-        if (!second && i == 0) {  // the corner: background token x background token
-            float4 own[NQ];
-            const float inv_own = inv_of(load_row(f + (size_t)b * (rows + skip) * C, own));
-            float d0 = 0.f;
+        if (more) {
 #pragma unroll
-            for (int it = 0; it < NQ; ++it) {
-                d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0);
-                d0 = fmaf(own[it].z, tk[it].z, d0); d0 = fmaf(own[it].w, tk[it].w, d0);
-            }
-            d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
-            if (lane == 0) s00[b] = d0;
+            for (int r = 0; r < kPrepRows; ++r)
+#pragma unroll
+                for (int it = 0; it < NQ; ++it) x[r][it] = xn[r][it];
         }
     }
 }
@@ -586,6 +668,35 @@ tc_store_bg_kernel(const float *__restrict__ bg_a, const float *__restrict__ bg_
     if (k < Cn) dst[k + 1] = __fdiv_rn(bg_b[(size_t)b * Np + k], temp);
 }
 
+// The finish kernels fold per-(row, column part) and per-(column, plane) partials.  A block of 256
+// threads serves 64 rows / columns with FOUR sub-threads each (thread = sub * 64 + item: loads stay
+// coalesced along the rows): a sub-thread folds every fourth partial with its loads in flight
+// together, the four results meet in shared memory in a fixed order (deterministic).  One thread per
+// row with a serial loop over 32..128 partials was latency bound (5-9 us per kernel).
+constexpr int kFinishItems = 64, kFinishSub = 4;
+template <bool MAX>
+__device__ __forceinline__ float part_fold(const float *__restrict__ base, size_t stride, int n, int sub) {
+    float a = MAX ? -INFINITY : 0.f;
+#pragma unroll 8
+    for (int t = sub; t < n; t += kFinishSub) {
+        const float v = base[(size_t)t * stride];
+        a = MAX ? fmaxf(a, v) : a + v;
+    }
+    return a;
+}
+// result valid in sub-thread 0; `red` is reused by consecutive calls (barriers inside)
+template <bool MAX>
+__device__ __forceinline__ float sub_fold(float v, float (*red)[kFinishItems], int item, int sub) {
+    __syncthreads();
+    red[sub][item] = v;
+    __syncthreads();
+    if (sub != 0) return v;
+    float a = red[0][item];
+#pragma unroll
+    for (int q = 1; q < kFinishSub; ++q) a = MAX ? fmaxf(a, red[q][item]) : a + red[q][item];
+    return a;
+}
+
 // after pass 1: row / column sums from their partials (fixed order: deterministic) plus the
 // background column / row term, reciprocals and log2; +inf logs mark padded rows / columns
 __global__ void __launch_bounds__(256)
@@ -598,7 +709,10 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
                        const float *__restrict__ pts2 /* (B,Cn,3) or null */,
                        float4 *__restrict__ Gall /* (B,Np) or null: 1/colsum_j * (x_j, y_j, z_j, 1), EVERY column */) {
     __shared__ float red[32];
-    const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float red4[kFinishSub][kFinishItems];
+    const int b = blockIdx.y, B = gridDim.y;
+    const int item = threadIdx.x % kFinishItems, sub = threadIdx.x / kFinishItems;
+    const int k = blockIdx.x * kFinishItems + item;
     if (blockIdx.x == gridDim.x - 1) {  // one EXTRA block per instance: sums of the background row and column
         float sr = 0.f, sc = 0.f;
         for (int j = threadIdx.x; j < Cn; j += blockDim.x) sr += ex2(fmaf(bg_b[(size_t)b * Np + j], c1, -c2));
@@ -609,33 +723,36 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
         if (threadIdx.x == 0) { lbg[2 * b] = log2f(sr + e00); lbg[2 * b + 1] = log2f(sc + e00); }
         return;
     }
-    if (k < Mp) {
+    // rows: the partials of row k are shared by the four sub-threads, then folded in a fixed order
+    {
         float s = 0.f;
-        if (k < R) {
-            for (int t = 0; t < n_part; ++t) s += rowpart[((size_t)b * n_part + t) * Mp + k];
-            s += ex2(fmaf(bg_a[(size_t)b * Mp + k], c1, -c2));
+        if (k < R) s = part_fold<false>(rowpart + (size_t)b * n_part * Mp + k, Mp, n_part, sub);
+        s = sub_fold<false>(s, red4, item, sub);
+        if (sub == 0 && k < Mp) {
+            if (k < R) s += ex2(fmaf(bg_a[(size_t)b * Mp + k], c1, -c2));
+            const bool ok = k < R && s > 0.f;
+            inv_rowsum[(size_t)b * Mp + k] = ok ? 1.0f / s : 0.f;
+            lrs[(size_t)b * Mp + k] = ok ? log2f(s) : INFINITY;
         }
-        const bool ok = k < R && s > 0.f;
-        inv_rowsum[(size_t)b * Mp + k] = ok ? 1.0f / s : 0.f;
-        lrs[(size_t)b * Mp + k] = ok ? log2f(s) : INFINITY;
     }
-    if (k < Np) {
+    {
         float s = 0.f;
-        if (k < Cn) {
-            for (int q = 0; q < planes; ++q) s += colpart[((size_t)q * B + b) * Np + k];
-            s += ex2(fmaf(bg_b[(size_t)b * Np + k], c1, -c2));
-        }
-        const bool ok = k < Cn && s > 0.f;
-        const float ic = ok ? 1.0f / s : 0.f;
-        inv_colsum[(size_t)b * Np + k] = ic;
-        lcs[(size_t)b * Np + k] = ok ? log2f(s) : INFINITY;
-        if (Gall) {
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < Cn) {
-                const float *q = pts2 + ((size_t)b * Cn + k) * 3;
-                g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+        if (k < Cn) s = part_fold<false>(colpart + (size_t)b * Np + k, (size_t)B * Np, planes, sub);
+        s = sub_fold<false>(s, red4, item, sub);
+        if (sub == 0 && k < Np) {
+            if (k < Cn) s += ex2(fmaf(bg_b[(size_t)b * Np + k], c1, -c2));
+            const bool ok = k < Cn && s > 0.f;
+            const float ic = ok ? 1.0f / s : 0.f;
+            inv_colsum[(size_t)b * Np + k] = ic;
+            lcs[(size_t)b * Np + k] = ok ? log2f(s) : INFINITY;
+            if (Gall) {
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < Cn) {
+                    const float *q = pts2 + ((size_t)b * Cn + k) * 3;
+                    g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+                }
+                Gall[(size_t)b * Np + k] = g;
             }
-            Gall[(size_t)b * Np + k] = g;
         }
     }
 }
@@ -651,30 +768,38 @@ tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__rest
                        int planes, float c1, float c2, float *__restrict__ w1 /* (B,R) */,
                        float *__restrict__ w2_out /* (B,Cn) or null */, float4 *__restrict__ G /* or null */,
                        float *__restrict__ fgcol /* (B,Np) or null: 1 = foreground or padding, 0 = background */) {
-    const int b = blockIdx.y, B = gridDim.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float red4[kFinishSub][kFinishItems];
+    const int b = blockIdx.y, B = gridDim.y;
+    const int item = threadIdx.x % kFinishItems, sub = threadIdx.x / kFinishItems;
+    const int k = blockIdx.x * kFinishItems + item;
     const float lrs0 = lbg[2 * b], lcs0 = lbg[2 * b + 1], c2x = 2.0f * c1;
-    if (k < R) {
+    {
         float m = -INFINITY;
-        for (int t = 0; t < n_part; ++t) m = fmaxf(m, rowmaxpart[((size_t)b * n_part + t) * Mp + k]);
-        w1[(size_t)b * R + k] = m > fmaf(bg_a[(size_t)b * Mp + k], c2x, -lcs0) ? 1.f : 0.f;  // label1 > 0
+        if (k < R) m = part_fold<true>(rowmaxpart + (size_t)b * n_part * Mp + k, Mp, n_part, sub);
+        m = sub_fold<true>(m, red4, item, sub);
+        if (sub == 0 && k < R)
+            w1[(size_t)b * R + k] = m > fmaf(bg_a[(size_t)b * Mp + k], c2x, -lcs0) ? 1.f : 0.f;  // label1 > 0
     }
-    if (k < Np) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool isbg = false;
-        if (k < Cn) {
-            float cm = -INFINITY;
-            for (int q = 0; q < planes; ++q) cm = fmaxf(cm, colpart[((size_t)q * B + b) * Np + k]);
-            const bool fg = cm > fmaf(bg_b[(size_t)b * Np + k], c2x, -lrs0);  // label2 > 0
-            isbg = !fg;
-            if (w2_out) w2_out[(size_t)b * Cn + k] = fg ? 1.f : 0.f;
-            if (fg) {
-                const float ic = inv_colsum[(size_t)b * Np + k];
-                const float *q = pts2 + ((size_t)b * Cn + k) * 3;
-                g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+    {
+        float cm = -INFINITY;
+        if (k < Cn) cm = part_fold<true>(colpart + (size_t)b * Np + k, (size_t)B * Np, planes, sub);
+        cm = sub_fold<true>(cm, red4, item, sub);
+        if (sub == 0 && k < Np) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool isbg = false;
+            if (k < Cn) {
+                const bool fg = cm > fmaf(bg_b[(size_t)b * Np + k], c2x, -lrs0);  // label2 > 0
+                isbg = !fg;
+                if (w2_out) w2_out[(size_t)b * Cn + k] = fg ? 1.f : 0.f;
+                if (fg) {
+                    const float ic = inv_colsum[(size_t)b * Np + k];
+                    const float *q = pts2 + ((size_t)b * Cn + k) * 3;
+                    g = make_float4(ic * q[0], ic * q[1], ic * q[2], ic);
+                }
             }
+            if (G) G[(size_t)b * Np + k] = g;
+            if (fgcol) fgcol[(size_t)b * Np + k] = isbg ? 0.f : 1.f;
         }
-        if (G) G[(size_t)b * Np + k] = g;
-        if (fgcol) fgcol[(size_t)b * Np + k] = isbg ? 0.f : 1.f;
     }
 }
 
@@ -747,21 +872,28 @@ tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restric
                       const float *__restrict__ corr4 /* (B,n_part_c,4,Mp) or null */, int n_part_c,
                       const int *__restrict__ strip_count /* (B): live strips of corr4 */,
                       int parts_per_strip) {
-    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < n_part; ++t)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] += rowpart4[(((size_t)b * n_part + t) * 4 + k) * Mp + i];
-    if (corr4) {  // take the background columns' share out again (two partials per live strip)
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const int live = parts_per_strip * strip_count[b];
-        for (int t = 0; t < live; ++t)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] += corr4[(((size_t)b * n_part_c + t) * 4 + k) * Mp + i];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] -= c[k];
+    // sub-thread k folds component k (weight, x, y, z) of row i over all partials
+    __shared__ float red4[kFinishSub][kFinishItems];
+    const int b = blockIdx.y, item = threadIdx.x % kFinishItems, k = threadIdx.x / kFinishItems;
+    const int i = blockIdx.x * kFinishItems + item;
+    float ak = 0.f;
+    if (i < R) {
+        const float *src = rowpart4 + ((size_t)b * n_part * 4 + k) * Mp + i;
+#pragma unroll 8
+        for (int t = 0; t < n_part; ++t) ak += src[(size_t)t * 4 * Mp];
+        if (corr4) {  // take the background columns' share out again (parts_per_strip partials per live strip)
+            float c = 0.f;
+            const int live = parts_per_strip * strip_count[b];
+            const float *cs = corr4 + ((size_t)b * n_part_c * 4 + k) * Mp + i;
+#pragma unroll 4
+            for (int t = 0; t < live; ++t) c += cs[(size_t)t * 4 * Mp];
+            ak -= c;
+        }
     }
+    red4[k][item] = ak;
+    __syncthreads();
+    if (k != 0 || i >= R) return;
+    const float a[4] = {red4[0][item], red4[1][item], red4[2][item], red4[3][item]};
     const size_t ri = (size_t)b * R + i;
     const float f = w1[ri] * inv_rowsum[(size_t)b * Mp + i];
     const float sA = a[0] * f;
@@ -903,7 +1035,7 @@ static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp
         const int splits = (p.n_msteps + spt - 1) / spt;
         const long tasks = (long)B * p.n_strips * splits;
         const long rounds = (tasks + pairs - 1) / pairs;
-        const double cost = (double)rounds * (spt + 0.25);
+        const double cost = (double)rounds * (spt + reload);
         if (cost < best_cost) { best_cost = cost; best = spt; }
     }
     p.spt = g_steps_per_task > 0 ? min(g_steps_per_task, p.n_msteps) : best;
@@ -919,7 +1051,7 @@ static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp
 static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const float *f1, __nv_bfloat16 *A,
                         const float *f2, __nv_bfloat16 *Bm, int normalize, int skip, float *bg_a, float *bg_b,
                         float *s00) {
-    const int grid = (B * (p.Mp + p.Np) / kPrepRows + 7) / 8;
+    const int grid = min((B * (p.Mp + p.Np) / kPrepRows + 7) / 8, 3 * num_sms());  // persistent, 3 CTAs per SM
     auto go = [&](auto kern) {
         kern<<<grid, 256, 0, st>>>(f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip, bg_a, bg_b, s00,
                                    p.single);
@@ -1035,7 +1167,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
     p.rowpart = w.rowpart;
     p.colpart = w.colpart;
     if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
-    tc_finish_stats_kernel<<<dim3((mx + 255) / 256 + 1, B), 256, 0, st>>>(
+    tc_finish_stats_kernel<<<dim3((mx + kFinishItems - 1) / kFinishItems + 1, B), 256, 0, st>>>(
         w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, w.s00, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
         w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs, w.lbg, pts2, two_pass ? w.Gall : nullptr);
     p.lrs = w.lrs;
@@ -1048,7 +1180,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
         const int n_part_m = n_part;
-        tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+        tc_finish_label_kernel<<<dim3((mx + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
             w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part_m,
             planes, p.c1, p.c2, w1, w2_out, nullptr, w.fgcol);
         // the background columns, compacted, and a short ragged pass that takes their share out again
@@ -1057,25 +1189,41 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
         CUtensorMap tmC;
         if (int rc = make_operand_map(&tmC, w.Bc, (size_t)2 * B * p.Np, C)) return rc;
         Params pc = p;
+        // Only the first strip_count[b] strips of an instance are live here (one, as a rule): short tasks,
+        // so that the few live (instance, strip) pairs spread over the CTA pairs instead of 8 steps in a row
+        // on 16 of them.
+        {
+            const int pairs = max(1, num_sms() / 2);
+            int best = 1;
+            double best_cost = 1e30;
+            for (int spt = p.n_msteps; spt >= 1; --spt) {
+                const int splits = (p.n_msteps + spt - 1) / spt;
+                const long rounds = ((long)B * splits + pairs - 1) / pairs;
+                const double cost = (double)rounds * (spt + (p.single ? 0.75 : 0.25));
+                if (cost <= best_cost) { best_cost = cost; best = spt; }
+            }
+            pc.spt = g_steps_per_task > 0 ? p.spt : best;
+            pc.n_splits = (p.n_msteps + pc.spt - 1) / pc.spt;
+        }
         pc.G = w.Gc;
         pc.rowpart4 = w.rowpart_c;
         pc.strip_count = w.strip_count;
         pc.strip_major = 1;
         if (int rc = launch_pass<kWsum>(tmA, tmC, pc, st)) return rc;
-        tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
+        tc_finish_wsum_kernel<<<dim3((N1 + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
             w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part_m, rsA, pred, w.rowpart_c, n_part, w.strip_count, pps);
     } else {
         // pass 2: foreground labels
         p.rowmaxpart = w.rowpart;
         if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
-        tc_finish_label_kernel<<<dim3((mx + 255) / 256, B), 256, 0, st>>>(
+        tc_finish_label_kernel<<<dim3((mx + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
             w.rowpart, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
             planes, p.c1, p.c2, w1, w2_out, w.G, nullptr);
         // pass 3: weighted row sums -> correspondences
         p.G = w.G;
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
-        tc_finish_wsum_kernel<<<dim3((N1 + 255) / 256, B), 256, 0, st>>>(
+        tc_finish_wsum_kernel<<<dim3((N1 + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
             w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, 0, nullptr, pps);
     }
     // weighted Procrustes + pose score (fine.cu)

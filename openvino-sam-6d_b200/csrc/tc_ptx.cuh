@@ -158,6 +158,32 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100): two IEEE fp32 operations per issued instruction.
+// A pair lives in an aligned 64-bit register; pack2(x, x) becomes a scalar broadcast operand.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t p, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float sum2(uint64_t p) {
+    float a, b;
+    unpack2(p, a, b);
+    return a + b;
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4 | LBO (ignored for swizzled K-major, canonical 1) << 16 |
 // SBO = 1024 B (8 rows x 128 B) >> 4 << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61

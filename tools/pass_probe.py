@@ -35,7 +35,7 @@ for spt in [int(x) for x in os.environ.get("SPT", "0").split(",")]:
             def run(prep=0):
                 rc = L.pem_dev_fine_pass(f1.data_ptr(), f2.data_ptr(), B, N, N, C, 0.1, flags | (8 * SINGLE), mode, prep, ws.data_ptr(), nb, st)
                 assert rc == 0, rc
-            for _ in range(3): run()
+            for _ in range(20): run()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -11,6 +11,7 @@ b = {k: v.to(dev) for k, v in pkg.synth.replicate_batch(base, B // 4).items()}
 bg = b["bg"][:, None, :]
 f1, f2 = torch.cat([bg, b["dense_fm"]], 1).contiguous(), torch.cat([bg, b["dense_fo"]], 1).contiguous()
 for _ in range(int(os.environ.get("ITERS", 3))):
-    R, t, s = pkg.model_utils.compute_fine_Rt_fused(f1, f2, b["dense_pm"], b["dense_po"], b["model"], 0.1, 0.15)
+    R, t, s = pkg.model_utils.compute_fine_Rt_fused(f1, f2, b["dense_pm"], b["dense_po"], b["model"], 0.1, 0.15,
+                                                    precision=os.environ.get("PRECISION", "fp16"))
 torch.cuda.synchronize()
 print("score", s[:4].tolist())

@@ -235,6 +235,7 @@ weighted_procrustes_kernel(const float *__restrict__ src, const float *__restric
                            float *__restrict__ Rout, float *__restrict__ tout,
                            int *__restrict__ zero3 /* (B,3) scratch to clear, or null */) {
     __shared__ double s_red[32];
+    pdl_enter();
     const int b = blockIdx.x, tid = threadIdx.x;
     if (zero3 && tid < 3) zero3[3 * b + tid] = 0;
     const float *S = src + (size_t)b * n * 3, *Rf = ref + (size_t)b * n * 3;
@@ -309,6 +310,7 @@ fine_pose_score_kernel(const float *__restrict__ pts1, const float *__restrict__
     extern __shared__ float4 s_model[];
     __shared__ float s_best[kPsParts][kPsPoints];
     __shared__ int s_h[kPsLanes / 32], s_f[kPsLanes / 32];
+    pdl_enter();
     const int b = blockIdx.y, tid = threadIdx.x;
     const int pt = tid & (kPsLanes - 1), part = tid / kPsLanes;  // part is warp-uniform
     const float *mb = model + (size_t)b * Nm * 3;
@@ -415,12 +417,13 @@ int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA,
                      const float *model, int B, int N1, int Nm, float dis_thres, int *counters,
                      float *R, float *t, float *score, cudaStream_t st) {
     // (the Procrustes kernel also zeroes the pose-score counters of its instance)
-    weighted_procrustes_kernel<<<B, 256, 0, st>>>(pred, pts1, rowsumA, N1, 0.0f, 1e-5f, R, t, counters);
+    pem_launch_pdl(weighted_procrustes_kernel, dim3(B), dim3(256), 0, st, pred, pts1, rowsumA, N1, 0.0f, 1e-5f, R, t,
+                   counters);
     const size_t smem = (size_t)Nm * sizeof(float4);
     static size_t cached = 40 * 1024;
     if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
-    fine_pose_score_kernel<<<dim3((N1 + kPsPoints - 1) / kPsPoints, B), kPsThreads, smem, st>>>(
-        pts1, w1, R, t, model, N1, Nm, dis_thres, counters, score);
+    pem_launch_pdl(fine_pose_score_kernel, dim3((N1 + kPsPoints - 1) / kPsPoints, B), dim3(kPsThreads), smem, st, pts1,
+                   w1, R, t, model, N1, Nm, dis_thres, counters, score);
     return pem_launch_status();
 }
 

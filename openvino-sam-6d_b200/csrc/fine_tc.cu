@@ -190,6 +190,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     cluster_sync_all();  // the peer's barriers and TMEM exist before anything targets them
+    pdl_enter();         // everything above is local; global memory is touched only below
 
     // Both single-issuer roles run with warp-uniform control flow (all 32 lanes loop and wait);
     // only the instruction issue is predicated on an elected lane, so addresses and
@@ -512,6 +513,7 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
                int B, int C, int normalize, int skip, float *__restrict__ bg_a /* (B,rows_pa) */,
                float *__restrict__ bg_b /* (B,rows_pb) */, float *__restrict__ s00 /* (B) */,
                int single /* 1: the hi plane holds fp16(x), no lo plane is written */) {
+    pdl_enter();
     const int lane = lane_id();
     const int nq = C >> 2;  // float4 per row
     const int n_warps = gridDim.x * (blockDim.x >> 5);
@@ -710,6 +712,7 @@ tc_finish_stats_kernel(const float *__restrict__ rowpart, const float *__restric
                        float4 *__restrict__ Gall /* (B,Np) or null: 1/colsum_j * (x_j, y_j, z_j, 1), EVERY column */) {
     __shared__ float red[32];
     __shared__ float red4[kFinishSub][kFinishItems];
+    pdl_enter();
     const int b = blockIdx.y, B = gridDim.y;
     const int item = threadIdx.x % kFinishItems, sub = threadIdx.x / kFinishItems;
     const int k = blockIdx.x * kFinishItems + item;
@@ -769,6 +772,7 @@ tc_finish_label_kernel(const float *__restrict__ rowmaxpart, const float *__rest
                        float *__restrict__ w2_out /* (B,Cn) or null */, float4 *__restrict__ G /* or null */,
                        float *__restrict__ fgcol /* (B,Np) or null: 1 = foreground or padding, 0 = background */) {
     __shared__ float red4[kFinishSub][kFinishItems];
+    pdl_enter();
     const int b = blockIdx.y, B = gridDim.y;
     const int item = threadIdx.x % kFinishItems, sub = threadIdx.x / kFinishItems;
     const int k = blockIdx.x * kFinishItems + item;
@@ -815,6 +819,7 @@ tc_bg_gather_kernel(const float *__restrict__ fgcol, int Cn, int Np, int C, int 
     __shared__ int s_list[4096];
     __shared__ int s_warp[32];
     __shared__ int s_total;
+    pdl_enter();
     const int b = blockIdx.x, tid = threadIdx.x, per = (Np + 1023) / 1024;  // Np <= 4096
     const int part_id = blockIdx.y, n_parts = gridDim.y;
     int flags = 0, cnt = 0;
@@ -874,6 +879,7 @@ tc_finish_wsum_kernel(const float *__restrict__ rowpart4, const float *__restric
                       int parts_per_strip) {
     // sub-thread k folds component k (weight, x, y, z) of row i over all partials
     __shared__ float red4[kFinishSub][kFinishItems];
+    pdl_enter();
     const int b = blockIdx.y, item = threadIdx.x % kFinishItems, k = threadIdx.x / kFinishItems;
     const int i = blockIdx.x * kFinishItems + item;
     float ak = 0.f;
@@ -1053,8 +1059,8 @@ static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const fl
                         float *s00) {
     const int grid = min((B * (p.Mp + p.Np) / kPrepRows + 7) / 8, 3 * num_sms());  // persistent, 3 CTAs per SM
     auto go = [&](auto kern) {
-        kern<<<grid, 256, 0, st>>>(f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip, bg_a, bg_b, s00,
-                                   p.single);
+        pem_launch_pdl(kern, dim3(grid), dim3(256), 0, st, f1, p.R, p.Mp, A, f2, p.Cn, p.Np, Bm, B, C, normalize, skip,
+                       bg_a, bg_b, s00, p.single);
     };
     if (C <= 128) go(tc_prep_kernel<1>);
     else go(tc_prep_kernel<2>);
@@ -1068,7 +1074,7 @@ static int launch_pass_w(const CUtensorMap &tmA, const CUtensorMap &tmB, const P
     if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE, EPW>, smem, &cached)) return rc;
     const int n_tasks = p.B * p.n_strips * p.n_splits;
     const int pairs = min(max(1, num_sms() / 2), n_tasks);  // one cluster of two CTAs per SM pair
-    fine_tc_kernel<MODE, EPW><<<2 * pairs, kThreads, smem, st>>>(tmA, tmB, p);
+    pem_launch_pdl(fine_tc_kernel<MODE, EPW>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, p);
     return pem_launch_status();
 }
 template <int MODE>
@@ -1167,7 +1173,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
     p.rowpart = w.rowpart;
     p.colpart = w.colpart;
     if (int rc = launch_pass<kStats>(tmA, tmB, p, st)) return rc;
-    tc_finish_stats_kernel<<<dim3((mx + kFinishItems - 1) / kFinishItems + 1, B), 256, 0, st>>>(
+    pem_launch_pdl(tc_finish_stats_kernel, dim3((mx + kFinishItems - 1) / kFinishItems + 1, B), dim3(256), 0, st, 
         w.rowpart, w.colpart, w.bg_a, w.bg_b, p.R, p.Cn, w.s00, p.Mp, p.Np, n_part, planes, p.c1, p.c2,
         w.inv_rowsum, w.lrs, w.inv_colsum, w.lcs, w.lbg, pts2, two_pass ? w.Gall : nullptr);
     p.lrs = w.lrs;
@@ -1180,11 +1186,11 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
         const int n_part_m = n_part;
-        tc_finish_label_kernel<<<dim3((mx + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
+        pem_launch_pdl(tc_finish_label_kernel, dim3((mx + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
             w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part_m,
             planes, p.c1, p.c2, w1, w2_out, nullptr, w.fgcol);
         // the background columns, compacted, and a short ragged pass that takes their share out again
-        tc_bg_gather_kernel<<<dim3(B, 8), 1024, 0, st>>>(w.fgcol, p.Cn, p.Np, C, B, w.Bm, w.Gall, w.Bc, w.Gc,
+        pem_launch_pdl(tc_bg_gather_kernel, dim3(B, 8), dim3(1024), 0, st, w.fgcol, p.Cn, p.Np, C, B, w.Bm, w.Gall, w.Bc, w.Gc,
                                                 w.strip_count, p.single ? 1 : 2);
         CUtensorMap tmC;
         if (int rc = make_operand_map(&tmC, w.Bc, (size_t)2 * B * p.Np, C)) return rc;
@@ -1210,20 +1216,20 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
         pc.strip_count = w.strip_count;
         pc.strip_major = 1;
         if (int rc = launch_pass<kWsum>(tmA, tmC, pc, st)) return rc;
-        tc_finish_wsum_kernel<<<dim3((N1 + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
+        pem_launch_pdl(tc_finish_wsum_kernel, dim3((N1 + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
             w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part_m, rsA, pred, w.rowpart_c, n_part, w.strip_count, pps);
     } else {
         // pass 2: foreground labels
         p.rowmaxpart = w.rowpart;
         if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
-        tc_finish_label_kernel<<<dim3((mx + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
+        pem_launch_pdl(tc_finish_label_kernel, dim3((mx + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
             w.rowpart, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
             planes, p.c1, p.c2, w1, w2_out, w.G, nullptr);
         // pass 3: weighted row sums -> correspondences
         p.G = w.G;
         p.rowpart4 = w.rowpart;
         if (int rc = launch_pass<kWsum>(tmA, tmB, p, st)) return rc;
-        tc_finish_wsum_kernel<<<dim3((N1 + kFinishItems - 1) / kFinishItems, B), 256, 0, st>>>(
+        pem_launch_pdl(tc_finish_wsum_kernel, dim3((N1 + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
             w.rowpart, w.inv_rowsum, w1, p.R, p.Mp, n_part, rsA, pred, nullptr, 0, nullptr, pps);
     }
     // weighted Procrustes + pose score (fine.cu)

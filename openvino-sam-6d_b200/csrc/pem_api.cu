@@ -23,3 +23,7 @@ extern "C" const char *pem_status_string(int status) {
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "unknown status";
 }
+
+// programmatic dependent launches on/off (development knob; default on)
+int g_pem_pdl = 1;
+extern "C" void pem_dev_set_pdl(int on) { g_pem_pdl = on ? 1 : 0; }

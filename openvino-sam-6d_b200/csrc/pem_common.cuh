@@ -39,9 +39,39 @@ static inline int pem_ensure_dyn_smem(Kern kern, size_t bytes, size_t *cached) {
 
 static inline cudaStream_t pem_cu_stream(pem_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL).  A kernel launched through pem_launch_pdl may be scheduled while
+// its predecessor on the stream is still running: its CTAs do their local prologue (barrier
+// initialisation, TMEM allocation, index arithmetic) and park in pdl_enter() until the predecessor has
+// completed and flushed, so launch latency and prologue hide under the predecessor's tail.  EVERY kernel
+// launched this way calls pem::pdl_enter() before its first global-memory access; a kernel that calls it
+// under a plain launch passes straight through.  Works across stream capture (the graph keeps the
+// programmatic edge).  pem_dev_set_pdl(0) turns all such launches back into plain ones.
+extern int g_pem_pdl;  // pem_api.cu
+template <typename... KArgs, typename... Args>
+static inline void pem_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pem_pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);  // status: pem_launch_status()
+}
+
 namespace pem {
 
 constexpr unsigned kFull = 0xffffffffu;
+
+// see pem_launch_pdl: wait for the predecessor grid (complete + visible), then let the successor be scheduled
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

@@ -8,6 +8,9 @@ import __graft_entry__ as g
 pkg = g.load_package()
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", 16))
+if os.environ.get("PDL") == "0":  # plain launches instead of programmatic dependent ones
+    import ctypes
+    ctypes.CDLL(pkg._lib.LIB_PATH).pem_dev_set_pdl(0)
 stage = pkg.stage.GeometricStage(B, dev)
 stage.load(pkg.synth.make_batch(list(range(B))))
 for _ in range(5):

@@ -16,6 +16,7 @@
 // The fused tcgen05 path that never materialises the matrix is in fine_tc.cu.
 #include "pem_common.cuh"
 #include "svd3.cuh"
+#include "tc_ptx.cuh"  // packed fp32 pairs (FFMA2)
 
 namespace pem {
 
@@ -235,6 +236,7 @@ weighted_procrustes_kernel(const float *__restrict__ src, const float *__restric
                            float *__restrict__ Rout, float *__restrict__ tout,
                            int *__restrict__ zero3 /* (B,3) scratch to clear, or null */) {
     __shared__ double s_red[32];
+    __shared__ double s_vec[9][33];
     pdl_enter();
     const int b = blockIdx.x, tid = threadIdx.x;
     if (zero3 && tid < 3) zero3[3 * b + tid] = 0;
@@ -257,8 +259,7 @@ weighted_procrustes_kernel(const float *__restrict__ src, const float *__restric
             c[3 + k] += w * (double)__ldg(Rf + 3 * i + k);
         }
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) c[k] = block_sum(c[k], s_red);
+    block_sum_n<6>(c, s_vec);
     const float cs[3] = {(float)c[0], (float)c[1], (float)c[2]};
     const float cr[3] = {(float)c[3], (float)c[4], (float)c[5]};
     double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -275,8 +276,7 @@ weighted_procrustes_kernel(const float *__restrict__ src, const float *__restric
 #pragma unroll
             for (int k = 0; k < 3; ++k) h[a * 3 + k] += (double)s3[a] * (double)r3[k];
     }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) h[k] = block_sum(h[k], s_red);
+    block_sum_n<9>(h, s_vec);
     if (tid == 0) {
         float H[3][3], Rm[3][3];
 #pragma unroll
@@ -336,12 +336,17 @@ fine_pose_score_kernel(const float *__restrict__ pts1, const float *__restrict__
     }
     __syncthreads();
     const int per = (Nm + kPsParts - 1) / kPsParts, m0 = part * per, m1 = min(Nm, m0 + per);
+    static_assert(kPsQ == 2, "the scan below works on one fp32 pair per thread");
+    const uint64_t QX = tc::pack2(qx[0], qx[1]), QY = tc::pack2(qy[0], qy[1]), QZ = tc::pack2(qz[0], qz[1]);
 #pragma unroll 4
-    for (int m = m0; m < m1; ++m) {
+    for (int m = m0; m < m1; ++m) {  // both queries per model point in three FFMA2 (same fp32 fmas as before)
         const float4 a = s_model[m];
-#pragma unroll
-        for (int u = 0; u < kPsQ; ++u)
-            best[u] = fminf(best[u], fmaf(qx[u], a.x, fmaf(qy[u], a.y, fmaf(qz[u], a.z, a.w))));
+        float d0, d1;
+        tc::unpack2(tc::fma2(QX, tc::pack2(a.x, a.x),
+                             tc::fma2(QY, tc::pack2(a.y, a.y), tc::fma2(QZ, tc::pack2(a.z, a.z), tc::pack2(a.w, a.w)))),
+                    d0, d1);
+        best[0] = fminf(best[0], d0);
+        best[1] = fminf(best[1], d1);
     }
 #pragma unroll
     for (int u = 0; u < kPsQ; ++u) s_best[part][u * kPsLanes + pt] = best[u];

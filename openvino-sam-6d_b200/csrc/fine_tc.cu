@@ -518,21 +518,33 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
     const int nq = C >> 2;  // float4 per row
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int total = B * (rows_pa + rows_pb) / kPrepRows;  // row pairs: A' first, then B'
+    // every warp owns a CONTIGUOUS range of pairs: the instance (and with it the other set's background
+    // token) changes at most once or twice per warp, and the position advances without divisions
+    const int per = (total + n_warps - 1) / n_warps;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const int p_begin = gw * per, p_end = min(total, p_begin + per);
+    if (p_begin >= p_end) return;
     // where a pair lives: operand, instance, first row
-    struct Where { bool second; int b, i0, gr; };
+    struct Where { bool second; int b, i0; };
     auto locate = [&](int pair) {
         Where w;
-        w.gr = pair * kPrepRows;
-        w.second = w.gr >= B * rows_pa;
-        if (w.second) w.gr -= B * rows_pa;
+        int gr = pair * kPrepRows;
+        w.second = gr >= B * rows_pa;
+        if (w.second) gr -= B * rows_pa;
         const int rows_p = w.second ? rows_pb : rows_pa;
-        w.b = w.gr / rows_p;
-        w.i0 = w.gr - w.b * rows_p;
+        w.b = gr / rows_p;
+        w.i0 = gr - w.b * rows_p;
         return w;
     };
+    auto advance = [&](Where &w) {
+        w.i0 += kPrepRows;
+        if (w.i0 >= (w.second ? rows_pb : rows_pa)) {
+            w.i0 = 0;
+            if (++w.b == B && !w.second) { w.b = 0; w.second = true; }
+        }
+    };
     // raw loads of a pair's rows (zero beyond the row / for padding rows); nothing waits on them here
-    auto fetch = [&](int pair, float4 (&x)[kPrepRows][NQ]) {
-        const Where w = locate(pair);
+    auto fetch = [&](const Where &w, float4 (&x)[kPrepRows][NQ]) {
         const float *f = w.second ? fb : fa;
         const int rows = w.second ? rows_b : rows_a;
 #pragma unroll
@@ -547,16 +559,25 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
             }
         }
     };
+    // arithmetic in fp32 pairs (FFMA2 / FMUL2): the kernel was issue bound (266 warp instructions per row)
     auto sumsq = [&](const float4 (&x)[NQ]) {
-        float s = 0.f;
+        uint64_t s = 0ull;
 #pragma unroll
         for (int it = 0; it < NQ; ++it) {
-            s = fmaf(x[it].x, x[it].x, s);
-            s = fmaf(x[it].y, x[it].y, s);
-            s = fmaf(x[it].z, x[it].z, s);
-            s = fmaf(x[it].w, x[it].w, s);
+            const uint64_t lo = pack2(x[it].x, x[it].y), hi = pack2(x[it].z, x[it].w);
+            s = fma2(lo, lo, s);
+            s = fma2(hi, hi, s);
         }
-        return s;
+        return sum2(s);
+    };
+    auto dot_of = [&](const float4 (&x)[NQ], const float4 (&y)[NQ]) {
+        uint64_t s = 0ull;
+#pragma unroll
+        for (int it = 0; it < NQ; ++it) {
+            s = fma2(pack2(x[it].x, x[it].y), pack2(y[it].x, y[it].y), s);
+            s = fma2(pack2(x[it].z, x[it].w), pack2(y[it].z, y[it].w), s);
+        }
+        return sum2(s);
     };
     // a row as NQ float4 per lane (zero beyond the row); sum of squares (unreduced)
     auto load_row = [&](const float *row, float4 (&x)[NQ]) {
@@ -582,24 +603,31 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
         lo[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
     };
 
-    int pair = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (pair >= total) return;
     float4 x[kPrepRows][NQ], xn[kPrepRows][NQ], tk[NQ];
-    fetch(pair, x);
-    for (; pair < total; pair += n_warps) {
-        const bool more = pair + n_warps < total;
-        if (more) fetch(pair + n_warps, xn);
-        const Where w = locate(pair);
+    Where w = locate(p_begin), wn = w;
+    fetch(w, x);
+    bool tk_second = false;
+    int tk_b = -1;
+    float rinv_tok = 1.f;  // 1 / |token|
+    for (int pair = p_begin; pair < p_end; ++pair) {
+        const bool more = pair + 1 < p_end;
+        if (more) {
+            advance(wn);
+            fetch(wn, xn);
+        }
         const bool second = w.second;
-        const int b = w.b, i0 = w.i0, gr = w.gr;  // rows i0, i0+1 of instance b
+        const int b = w.b, i0 = w.i0;  // rows i0, i0+1 of instance b
         const float *f = second ? fb : fa, *fo = second ? fa : fb;
         const int rows = second ? rows_b : rows_a, rows_p = second ? rows_pb : rows_pa;
         const int rows_o = second ? rows_a : rows_b;
+        const int gr = b * rows_p + i0;
         __nv_bfloat16 *out = second ? outb : outa;  // (2, B*rows_p, C)
         float *bg = second ? bg_b : bg_a;
-        const float *tok = fo + (size_t)b * (rows_o + skip) * C;  // the other set's background token
-        float inv_tok = 1.f;
-        if (skip) inv_tok = inv_of(load_row(tok, tk));
+        if (skip && (tk_b != b || tk_second != second)) {  // the other set's background token of this instance
+            rinv_tok = 1.0f / inv_of(load_row(fo + (size_t)b * (rows_o + skip) * C, tk));
+            tk_b = b;
+            tk_second = second;
+        }
 #pragma unroll
         for (int r = 0; r < kPrepRows; ++r) {
             const int i = i0 + r;
@@ -618,38 +646,29 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
                 continue;
             }
             // x * (1/norm) instead of the reference's x / norm: at most 1 ulp apart, far below the
-            // 2^-17 of the hi/lo split that follows, and 8 IEEE divisions per lane cheaper
-            const float rinv = 1.0f / inv_of(sumsq(x[r]));
-            float dot = 0.f;
+            // 2^-12 / 2^-17 of the rounding that follows, and 8 IEEE divisions per lane cheaper
+            const float rinv = normalize ? 1.0f / inv_of(sumsq(x[r])) : 1.f;
+            const uint64_t rinv2 = pack2(rinv, rinv);
 #pragma unroll
             for (int it = 0; it < NQ; ++it) {
+                float4 &v = x[r][it];
+                unpack2(mul2(pack2(v.x, v.y), rinv2), v.x, v.y);
+                unpack2(mul2(pack2(v.z, v.w), rinv2), v.z, v.w);
                 const int q = it * 32 + lane;
-                if (q >= nq) continue;
-                float4 v = x[r][it];
-                if (normalize) { v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv; }
-                split_store(v, hi, lo, q);
-                if (skip) {
-                    dot = fmaf(v.x, tk[it].x, dot); dot = fmaf(v.y, tk[it].y, dot);
-                    dot = fmaf(v.z, tk[it].z, dot); dot = fmaf(v.w, tk[it].w, dot);
-                }
+                if (q < nq) split_store(v, hi, lo, q);
             }
             if (!skip) continue;
-            dot = __fdiv_rn(warp_sum(dot), inv_tok);
+            const float dot = warp_sum(dot_of(x[r], tk)) * rinv_tok;  // cosine with the background token
             if (lane == 0) bg[(size_t)b * rows_p + i] = dot;
             if (!second && i == 0) {  // the corner: background token x background token
                 float4 own[NQ];
                 const float inv_own = inv_of(load_row(f + (size_t)b * (rows + skip) * C, own));
-                float d0 = 0.f;
-#pragma unroll
-                for (int it = 0; it < NQ; ++it) {
-                    d0 = fmaf(own[it].x, tk[it].x, d0); d0 = fmaf(own[it].y, tk[it].y, d0);
-                    d0 = fmaf(own[it].z, tk[it].z, d0); d0 = fmaf(own[it].w, tk[it].w, d0);
-                }
-                d0 = __fdiv_rn(__fdiv_rn(warp_sum(d0), inv_own), inv_tok);
+                const float d0 = __fdiv_rn(warp_sum(dot_of(own, tk)), inv_own) * rinv_tok;
                 if (lane == 0) s00[b] = d0;
             }
         }
         if (more) {
+            w = wn;
 #pragma unroll
             for (int r = 0; r < kPrepRows; ++r)
 #pragma unroll

@@ -119,4 +119,24 @@ __device__ __forceinline__ T block_sum(T v, T *smem /* >= 32 entries */) {
     return r;
 }
 
+// N block-wide sums behind ONE pair of barriers (fixed order: deterministic); results in every thread.
+// smem: N rows of 33 entries.
+template <int N, typename T>
+__device__ __forceinline__ void block_sum_n(T (&v)[N], T (*smem)[33]) {
+    const int w = warp_id(), l = lane_id(), nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) smem[k][w] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        T r = (l < nw) ? smem[k][l] : T(0);
+        v[k] = warp_sum(r);
+    }
+}
+
 }  // namespace pem

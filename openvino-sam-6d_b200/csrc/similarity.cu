@@ -7,6 +7,7 @@
 // fp32 reference mode of the fine stage; the tcgen05 split-bf16 fine kernel lives in
 // fine_tc.cu.
 #include "pem_common.cuh"
+#include "tc_ptx.cuh"  // packed fp32 pairs
 
 namespace pem {
 
@@ -119,10 +120,15 @@ similarity_nt_kernel(const float *__restrict__ A, const float *__restrict__ Bm, 
                 const float4 v = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * TN + n]);
                 bb[n] = v.x; bb[n + 1] = v.y; bb[n + 2] = v.z; bb[n + 3] = v.w;
             }
+            // two columns per instruction (FFMA2: the same fp32 fma per element, half the issue slots)
 #pragma unroll
-            for (int m = 0; m < TM; ++m)
+            for (int m = 0; m < TM; ++m) {
+                const uint64_t am = tc::pack2(a[m], a[m]);
 #pragma unroll
-                for (int n = 0; n < TN; ++n) acc[m][n] = fmaf(a[m], bb[n], acc[m][n]);
+                for (int n = 0; n < TN; n += 2)
+                    tc::unpack2(tc::fma2(am, tc::pack2(bb[n], bb[n + 1]), tc::pack2(acc[m][n], acc[m][n + 1])),
+                                acc[m][n], acc[m][n + 1]);
+            }
         }
         if (kt + 1 < nk) {
             s_store(buf ^ 1);

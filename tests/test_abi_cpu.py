@@ -61,6 +61,14 @@ def test_argument_validation_without_gpu(pkg):
     assert lib.pem_fine_fused(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, p, p, p, None, None, None, None, p, 16,
                               None) == -4
     assert lib.pem_fine_fused_pass(p, p, 1, 8, 8, 64, 0.1, 7, p, 1 << 30, None) == -3
+    # ... and their precision-taking forms: PEM_PREC_SPLIT_BF16 = 0, PEM_PREC_FP16 = 1, nothing else
+    assert lib.pem_fine_fused_ex(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, 2, p, p, p, None, None, None, None, p,
+                                 1 << 30, None) == -3
+    assert lib.pem_fine_fused_ex(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, 1, p, p, p, None, None, None, None, p,
+                                 16, None) == -4
+    assert lib.pem_fine_fused_ex(p, p, p, p, p, 1, 8, 8, 100, 8, 0.1, 0.15, 1, p, p, p, None, None, None, None, p,
+                                 1 << 30, None) == -3
+    assert lib.pem_fine_fused_pass_ex(p, p, 1, 8, 8, 64, 0.1, 1, 5, p, 1 << 30, None) == -3
     # instance preparation
     assert lib.pem_instance_scratch_bytes(3, 480, 640) == 3 * 480 * 640 * 4
     assert lib.pem_backproject_depth(p, 4, 4, 1.0, 1.0, 0.0, 0.0, 2, p, None) == -3     # precision is 0 or 1

@@ -87,6 +87,9 @@ struct Params {
     const float *lrs;      // (B,Mp)  log2(rowsum_i); +inf for padded rows
     const float *lcs;      // (B,Np)  log2(colsum_j); +inf for padded columns
     float *rowmaxpart;     // (B, 2*n_strips, Mp): max over the columns of the half-strip
+    // kLabelW: the column labels as predicates against thr_j = 2 c bg_b[j] - log2(background row sum)
+    const float *bg_b;     // (B,Np) cosine of column j with the background token (the background row)
+    const float *lbg;      // (B,2)  log2 of the background row / column sums
     // kWsum
     const float4 *G;       // (B,Np): w2_j/colsum_j * (x_j, y_j, z_j, 1); zero for padding
     float *rowpart4;       // (B, 2*n_strips, 4, Mp)
@@ -102,7 +105,8 @@ struct Smem {
     uint8_t b_lo[kMaxKC][kChunkBytes];   // (single-product mode: no lo operand -- these are four more ring slots)
     uint8_t a[kStages][kChunkBytes];     // streamed: this CTA's 128 rows of a step of A' (hi or lo)
     float4 G[TN];                        // per-column constants of the task (kWsum)
-    alignas(16) float colc[TN];          // per-column constants of the task (kLabel: log2 colsum)
+    alignas(16) float colc[TN];          // per-column constants of the task (kLabel: -log2 colsum)
+    alignas(16) float colthr[TN];        // kLabelW: the background threshold of every column
     float colred[4][TN];                 // per-quadrant column results
     uint64_t full[kMaxStages], empty[kMaxStages], b_full[kMaxKC], b_empty[kMaxKC], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
@@ -327,17 +331,19 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr bool COLREG = MODE == kStats || MODE == kLabel;
             float colacc[MODE == kLabel ? WC : 1];          // kLabel: column maxima
             uint64_t colacc2[MODE == kStats ? WC / 2 : 1];  // kStats: column sums, two columns per register pair
-            float cmx[WC / 32];
+            uint32_t cmask[WC / 32];  // kLabelW: bit (31 - q) = some row so far beats the background in column q of the chunk
+#pragma unroll
+            for (int q = 0; q < WC / 32; ++q) cmask[q] = 0u;
 #pragma unroll
             for (int q = 0; q < (MODE == kLabel ? WC : 1); ++q) colacc[q] = -INFINITY;
 #pragma unroll
             for (int q = 0; q < (MODE == kStats ? WC / 2 : 1); ++q) colacc2[q] = 0ull;
-#pragma unroll
-            for (int q = 0; q < WC / 32; ++q) cmx[q] = -INFINITY;
             // per-column constants of the task.  colc = -log2 colsum_j (-inf keeps padded columns out of
             // the row max).  G is stored by column PAIRS: G[2k] = (w, w', x, x'), G[2k+1] = (y, y', z, z')
             // of columns 2k and 2k+1, so that one LDS.128 feeds two FFMA2.
             if (LAB && ep_tid < TN) sm.colc[ep_tid] = -p.lcs[(size_t)b * p.Np + n * TN + ep_tid];
+            if (MODE == kLabelW && ep_tid < TN)  // exactly tc_finish_label_kernel's threshold (label2 > 0)
+                sm.colthr[ep_tid] = fmaf(p.bg_b[(size_t)b * p.Np + n * TN + ep_tid], kc2x, -p.lbg[2 * b]);
             if (WS && ep_tid < TN) {
                 const float4 g = p.G[(size_t)b * p.Np + n * TN + ep_tid];
                 float *gp = reinterpret_cast<float *>(&sm.G[ep_tid & ~1]) + (ep_tid & 1);
@@ -433,10 +439,27 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             a3 = fma2(u, pack2(gB.z, gB.w), a3);
                         }
                     }
-                    if constexpr (LAB && !COLREG) {  // column side of the labels for this chunk (v is dead after this)
+                    if constexpr (LAB && !COLREG) {
+                        // Column side of the labels.  Only "does any row beat the column's background entry"
+                        // is needed, and that threshold is known before the pass: thr_j - val_ij < 0 with
+                        // val = 2 s/temp - log rowsum_i, evaluated as fma(v, -k, +rowc) = -val (exact mirror of
+                        // the fma the maximum form uses) and a rounded difference, whose SIGN is exact -- the
+                        // same decision as max_i val_ij > thr_j, bit for bit.  The sign bits are shifted into a
+                        // mask (one SHF per element) instead of a 31-shuffle maximum per chunk and step.
+                        const uint64_t NK2X = pack2(-kc2x, -kc2x), PROW = pack2(rowc, rowc);
+                        uint32_t m = 0u;
 #pragma unroll
-                        for (int q = 0; q < CW; q += 2) unpack2(fma2(pack2(v[q], v[q + 1]), K2X, NROW), v[q], v[q + 1]);
-                        cmx[c] = fmaxf(cmx[c], warp_transpose_reduce<true>(v));
+                        for (int q = 0; q < CW; q += 4) {
+                            const float4 th = lds_f4(&sm.colthr[half * WC + c * CW + q]);
+                            float d0, d1, d2, d3;
+                            unpack2(add2(pack2(th.x, th.y), fma2(pack2(v[q], v[q + 1]), NK2X, PROW)), d0, d1);
+                            unpack2(add2(pack2(th.z, th.w), fma2(pack2(v[q + 2], v[q + 3]), NK2X, PROW)), d2, d3);
+                            m = shift_in_sign(m, d0);
+                            m = shift_in_sign(m, d1);
+                            m = shift_in_sign(m, d2);
+                            m = shift_in_sign(m, d3);
+                        }
+                        cmask[c] |= m;
                     }
                 }
                 // accumulator fully read: hand the TMEM buffer back to the MMA warp of the leader
@@ -466,8 +489,9 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             else { v[q] = colacc[c * 32 + q]; v[q + 1] = colacc[c * 32 + q + 1]; }
                         }
                         sm.colred[quad][half * WC + c * 32 + lane] = warp_transpose_reduce<LAB>(v);
-                    } else {
-                        sm.colred[quad][half * WC + c * 32 + lane] = cmx[c];
+                    } else {  // any row of the warp; column c*32 + L sits at bit 31 - L
+                        const uint32_t any = __reduce_or_sync(kFull, cmask[c]);
+                        sm.colred[quad][half * WC + c * 32 + lane] = (any >> (31 - lane)) & 1u ? INFINITY : -INFINITY;
                     }
                 }
                 epi_barrier<EPT>();
@@ -1203,6 +1227,8 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
         p.rowmaxpart = w.rowmax;
         p.G = w.Gall;
         p.rowpart4 = w.rowpart;
+        p.bg_b = w.bg_b;
+        p.lbg = w.lbg;
         if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
         const int n_part_m = n_part;
         pem_launch_pdl(tc_finish_label_kernel, dim3((mx + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
@@ -1289,6 +1315,8 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     if (mode == 4) {  // the merged pass of the two-pass path
         p.rowmaxpart = w.rowmax;
         p.G = w.Gall;
+        p.bg_b = w.bg_b;
+        p.lbg = w.lbg;
         return launch_pass<kLabelW>(tmA, tmB, p, st);
     }
     return mode == 3 ? launch_pass<kWsum>(tmA, tmB, p, st)

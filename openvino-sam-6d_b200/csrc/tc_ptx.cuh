@@ -183,6 +183,12 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// (m << 1) | sign bit of x: one funnel shift
+__device__ __forceinline__ uint32_t shift_in_sign(uint32_t m, float x) {
+    uint32_t r;
+    asm("shf.l.wrap.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(__float_as_uint(x)), "r"(m));
+    return r;
+}
 __device__ __forceinline__ float sum2(uint64_t p) {
     float a, b;
     unpack2(p, a, b);

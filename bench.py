@@ -133,6 +133,9 @@ def run_b200(args, rank, world, local_rank):
     pkg = entry.load_package()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if os.environ.get("PEM_PDL") == "0":  # development: plain launches instead of programmatic dependent ones
+        import ctypes
+        ctypes.CDLL(pkg._lib.LIB_PATH).pem_dev_set_pdl(0)
     B, K, W = args.batch, args.steps, args.warmup
     ids = [rank * B + i for i in range(B)]
     host = pkg.synth.make_batch(ids)

@@ -60,6 +60,14 @@ const char *pem_status_string(int status);
 size_t pem_fps_workspace_bytes(int B, int N);
 int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t *idx, void *workspace,
             size_t workspace_bytes, pem_stream_t stream);
+/*
+ * The same plus the sampled points themselves, new_xyz (B,M,3) = xyz[b, idx[b,j], :] -- the point half
+ * of sample_pts_feats (utils/model_utils.py:70-84: furthest_point_sample + gather_operation on the
+ * transposed cloud).  One launch where a cloud lives in one CTA (N <= 2048, the PEM shapes: the sampling
+ * thread stores the point it has just chosen); larger clouds run pem_fps and a row gather.
+ */
+int pem_fps_gather(const float *xyz, int B, int N, int M, int flags, int32_t *idx, float *new_xyz,
+                   void *workspace, size_t workspace_bytes, pem_stream_t stream);
 
 /*
  * gather_points (sampling.cpp:120-150; CPU loop :23-44; CUDA sampling_gpu.cu:13-35).

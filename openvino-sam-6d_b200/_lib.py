@@ -26,6 +26,7 @@ SIGNATURES = {
     "pem_status_string": (ctypes.c_char_p, [c_i]),
     "pem_fps_workspace_bytes": (c_sz, [c_i, c_i]),
     "pem_fps": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_sz, c_p]),
+    "pem_fps_gather": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "pem_gather": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "pem_gather_rows": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_p, c_ll, c_p]),
     "pem_transform_points": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p]),

@@ -61,13 +61,15 @@ __device__ __forceinline__ int cta_argmax(unsigned hi, unsigned lo, unsigned lon
 // otherwise they are re-read from the SoA shared-memory copy every step.
 template <int THREADS, int PPT, bool IN_REGS>
 __global__ void __launch_bounds__(THREADS, 1)
-fps_cta_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *__restrict__ idx) {
+fps_cta_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *__restrict__ idx,
+               float *__restrict__ new_xyz /* (B,M,3) or null: the sampled points themselves */) {
     extern __shared__ float s_soa[];  // x[N] | y[N] | z[N]
     __shared__ unsigned long long s_key[2][32];
     float *sx = s_soa, *sy = s_soa + N, *sz = s_soa + 2 * N;
     const int tid = threadIdx.x;
     const float *src = xyz + (size_t)blockIdx.x * N * 3;
     int32_t *out = idx + (size_t)blockIdx.x * M;
+    float *gout = new_xyz ? new_xyz + (size_t)blockIdx.x * M * 3 : nullptr;
 
     for (int e = tid; e < 3 * N; e += THREADS) {
         const int k = e / 3, c = e - 3 * k;
@@ -95,6 +97,9 @@ fps_cta_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *_
     if (tid == 0) out[0] = 0;
     for (int j = 1; j < M; ++j) {
         const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        if (gout && tid == 0) {  // the gather of the sampled point rides along (its own kernel cost 6 us)
+            gout[3 * (j - 1)] = cx; gout[3 * (j - 1) + 1] = cy; gout[3 * (j - 1) + 2] = cz;
+        }
         float best = -FLT_MAX;
         int arg = 0;
 #pragma unroll
@@ -113,6 +118,9 @@ fps_cta_kernel(const float *__restrict__ xyz, int N, int M, int skip, int32_t *_
         cur = cta_argmax<THREADS>(valid ? __float_as_uint(best) : 0u, valid ? ~(unsigned)arg : 0u,
                                   s_key[j & 1]);
         if (tid == 0) out[j] = cur;
+    }
+    if (gout && tid == 0) {
+        gout[3 * (M - 1)] = sx[cur]; gout[3 * (M - 1) + 1] = sy[cur]; gout[3 * (M - 1) + 2] = sz[cur];
     }
 }
 
@@ -259,12 +267,12 @@ fps_stream_kernel(const float *__restrict__ xyz, int N, int M, int skip, float *
 
 template <int THREADS, int PPT, bool IN_REGS>
 static int launch_fps_cta(const float *xyz, int B, int N, int M, int skip, int32_t *idx,
-                          cudaStream_t st) {
+                          cudaStream_t st, float *new_xyz = nullptr) {
     const size_t smem = (size_t)3 * N * sizeof(float);
     auto kern = fps_cta_kernel<THREADS, PPT, IN_REGS>;
     static size_t cached = 40 * 1024;  // static shared memory counts against the 48 KB default too
     if (int rc = pem_ensure_dyn_smem(kern, smem, &cached)) return rc;
-    kern<<<B, THREADS, smem, st>>>(xyz, N, M, skip, idx);
+    kern<<<B, THREADS, smem, st>>>(xyz, N, M, skip, idx, new_xyz);
     return pem_launch_status();
 }
 
@@ -774,6 +782,23 @@ extern "C" int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t
                 PEM_E_WORKSPACE);
     fps_stream_kernel<1024><<<B, 1024, 0, st>>>(xyz, N, M, skip, (float *)workspace, idx);
     return pem_launch_status();
+}
+
+// FPS + the gather of the sampled points (sample_pts_feats, MU:70-84, point half) in one launch where
+// the cloud lives in one CTA (N <= 2048: the PEM shapes); otherwise pem_fps followed by the row gather.
+extern "C" int pem_fps_gather(const float *xyz, int B, int N, int M, int flags, int32_t *idx,
+                              float *new_xyz, void *workspace, size_t workspace_bytes,
+                              pem_stream_t stream) {
+    PEM_REQUIRE_PTR(xyz);
+    PEM_REQUIRE_PTR(idx);
+    PEM_REQUIRE_PTR(new_xyz);
+    PEM_REQUIRE(B > 0 && N > 0 && M > 0, PEM_E_SHAPE);
+    cudaStream_t st = pem_cu_stream(stream);
+    const int skip = (flags & PEM_FPS_SKIP_NEAR_ORIGIN) ? 1 : 0;
+    if (N <= 1024) return launch_fps_cta<128, 8, true>(xyz, B, N, M, skip, idx, st, new_xyz);
+    if (N <= 2048 && g_fps_variant == 0) return launch_fps_cta<128, 16, true>(xyz, B, N, M, skip, idx, st, new_xyz);
+    if (int rc = pem_fps(xyz, B, N, M, flags, idx, workspace, workspace_bytes, stream)) return rc;
+    return pem_gather_rows(xyz, idx, B, N, 3, M, (long long)N * 3, 3, new_xyz, 0, stream);
 }
 
 extern "C" int pem_gather(const float *feat, const int32_t *idx, int B, int C, int N, int M,

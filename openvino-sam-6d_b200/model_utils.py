@@ -38,8 +38,21 @@ def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
     """FPS + point/feature gather.  pts (B,N,3), feats (B,N,C) -> (B,npoint,3), (B,npoint,C)
     [, idx (B,npoint) i32].  The gathers read the point-major tensors directly."""
     pts = _f32c(pts, "pts")
-    idx = furthest_point_sample(pts, npoint)
-    out_p = gather_rows(pts, idx)
+    B, N, _ = pts.shape
+    M = int(npoint)
+    if B == 0 or M == 0:
+        idx = furthest_point_sample(pts, npoint)
+        out_p = gather_rows(pts, idx)
+    else:  # the sampling kernel stores the points it chooses (pem_fps_gather): one launch fewer
+        L = _lib.lib()
+        idx = torch.empty((B, M), dtype=torch.int32, device=pts.device)
+        out_p = torch.empty((B, M, 3), dtype=torch.float32, device=pts.device)
+        nb = L.pem_fps_workspace_bytes(B, N)
+        ws = _ws(nb, pts.device) if nb else None
+        with torch.cuda.device(pts.device):
+            _lib.check(L.pem_fps_gather(pts.data_ptr(), B, N, M, 1, idx.data_ptr(), out_p.data_ptr(),
+                                        None if ws is None else ws.data_ptr(), nb, _ext._stream()),
+                       "pem_fps_gather")
     out_f = gather_rows(feats, idx)
     if return_index:
         return out_p, out_f, idx

@@ -131,9 +131,9 @@ class GeometricStage:
                                   p(self.pe_out[1][B:]), p(self.pe_masks) + half, half,
                                   self.side.cuda_stream), "pe_group2 unmoved cloud"); n += 1
         # 1. FPS on both clouds in one launch (2B clouds), then row gathers
-        ck(L.pem_fps(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), None, 0, st), "fps"); n += 1
-        ck(L.pem_gather_rows(p(self.pts), p(self.fps_idx), 2 * B, N, 3, M, N * 3, 3,
-                             p(self.sparse_pts), 0, st), "gather pts"); n += 1
+        # (the sampled points are stored by the sampling kernel itself: no separate gather launch)
+        ck(L.pem_fps_gather(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), p(self.sparse_pts), None, 0, st),
+           "fps + point gather"); n += 1
         # dense features live in rows 1.. of `feats`; gather into rows 1.. of `sparse_feats`
         ck(L.pem_gather_rows(p(self.feats) + 4 * C, p(self.fps_idx), 2 * B, N, C, M, (N + 1) * C, C,
                              p(self.sparse_feats) + 4 * C, (M + 1) * C, st), "gather feats"); n += 1

@@ -34,6 +34,25 @@ def test_fps_bit_exact(pkg, oracle, dev, B, N, M):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("B,N,M", [(1, 1, 1), (3, 100, 33), (4, 1024, 200), (32, 2048, 196), (2, 3000, 50), (1, 20000, 16),
+                                   (2, 5, 9)])
+def test_fps_gather_bit_exact(pkg, oracle, dev, B, N, M):
+    """pem_fps_gather: the indices of pem_fps and the sampled points themselves (the point half of
+    sample_pts_feats) -- from the sampling kernel where a cloud lives in one CTA, else FPS + row gather."""
+    p = _cloud(B, N, seed=3 * N + M)
+    g = p.to(dev)
+    idx = torch.full((B, M), -1, dtype=torch.int32, device=dev)
+    out = torch.full((B, M, 3), float("nan"), device=dev)
+    L = pkg._lib.lib()
+    nb = L.pem_fps_workspace_bytes(B, N)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+    pkg._lib.check(L.pem_fps_gather(g.data_ptr(), B, N, M, 1, idx.data_ptr(), out.data_ptr(), ws.data_ptr(), nb,
+                                    torch.cuda.current_stream().cuda_stream), "pem_fps_gather")
+    want = oracle.fps(p.numpy(), M)
+    np.testing.assert_array_equal(idx.cpu().numpy(), want)
+    np.testing.assert_array_equal(out.cpu().numpy(), np.take_along_axis(p.numpy(), want[..., None].astype(np.int64), 1))
+
+
 def test_fps_cuda_variant_rule(pkg, oracle, dev):
     """flags=0: the reference CUDA kernel's rule (no near-origin skip), lowest-index ties."""
     p = _cloud(2, 1500, seed=5)

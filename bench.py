@@ -254,8 +254,9 @@ def dominant_kernel_roofline(pkg, stage, flush):
     reducing epilogue that pem_fine_fused launches for its two full passes per step (softmax
     statistics; foreground labels + weighted sums) and once more, ragged, for the background-column
     correction.  Each of the two full launches is timed alone with CUDA events on its launch stream
-    (L2 flushed before every launch) through the profiling hook pem_fine_fused_pass; the figure is
-    their mean.
+    through the profiling hook pem_fine_fused_pass_ex -- L2 flushed, then the operand preparation kernel
+    (untimed), then the launch, i.e. the cache state the kernel meets inside the step; the figure is
+    their mean (the cold-L2 durations are reported next to it).
 
     Algorithmic flops per launch = 2*N1*N2*C per instance (the cosine matrix once; DESIGN.md
     section 4).  In split-bf16 mode the kernel EXECUTES 3x that on the tensor cores (hi*hi + hi*lo +
@@ -276,13 +277,16 @@ def dominant_kernel_roofline(pkg, stage, flush):
                                                 stage.fine_precision, p(stage.ws), stage.ws_bytes, st),
                        "fine_fused_pass")
 
-    def timed(fn, iters=10):
+    def timed(fn, iters=10, pre=None):
+        """mean duration of fn: L2 flushed, then `pre` (untimed; the producer of fn's inputs in the step), then fn"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ms = 0.0
         for _ in range(3):
             fn()
         for _ in range(iters):
             flush.zero_()
+            if pre is not None:
+                pre()
             e0.record(stage.stream)
             fn()
             e1.record(stage.stream)
@@ -292,7 +296,10 @@ def dominant_kernel_roofline(pkg, stage, flush):
 
     with torch.cuda.stream(stage.stream):
         fused_ms = timed(fused)  # also leaves operands and constants in the workspace for the passes
-        pass_ms = [timed(lambda k=k: one_pass(k)) for k in (1, 4)]
+        # as inside the step: the operand preparation has just run (operands L2-resident, as its consumer
+        # finds them), everything else flushed
+        pass_ms = [timed(lambda k=k: one_pass(k), pre=lambda: one_pass(0)) for k in (1, 4)]
+        cold_ms = [timed(lambda k=k: one_pass(k)) for k in (1, 4)]  # operands from HBM
     ms = sum(pass_ms) / 2
     flops = 2.0 * N * N * C * B
     achieved = flops / (ms / 1e3) / 1e12
@@ -312,6 +319,9 @@ def dominant_kernel_roofline(pkg, stage, flush):
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "ms_per_launch": ms,
             "ms_per_launch_by_pass": {"stats": pass_ms[0], "label+wsum": pass_ms[1]},
+            "ms_per_launch_by_pass_cold_l2": {"stats": cold_ms[0], "label+wsum": cold_ms[1]},
+            "timing": "CUDA events on the launch stream around each launch; before it the L2 is flushed and the "
+                      "operand preparation kernel re-run, as in the step (cold_l2: without that)",
             "executed_mma_tflops": nprod * achieved, "executed_frac": nprod * achieved / peak,
             "fused_fine_op_ms": fused_ms,
             "peak_source": which + ", burst bf16 (kernel timed alone)"}

@@ -296,7 +296,9 @@ int pem_fine_fused_ex(const float *f1, const float *f2, const float *pts1, const
  */
 int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
                         int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream);
-/* ... after a pem_fine_fused_ex call of the same `precision` (pem_fine_fused_pass = SPLIT_BF16) */
+/* ... after a pem_fine_fused_ex call of the same `precision` (pem_fine_fused_pass = SPLIT_BF16).  pass 0 =
+ * the operand preparation alone (normalise + convert): it precedes the passes in a step and leaves the
+ * operands in L2 for them, which is how bench.py times a pass as it runs inside the step. */
 int pem_fine_fused_pass_ex(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
                            int pass, int precision, void *workspace, size_t workspace_bytes,
                            pem_stream_t stream);

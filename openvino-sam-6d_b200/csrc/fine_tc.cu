@@ -1303,6 +1303,7 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     if (workspace_bytes < w.bytes) return PEM_E_WORKSPACE;
     if (prep)
         launch_prep(p, B, C, st, f1, w.A, f2, w.Bm, 1, 1, w.bg_a, w.bg_b, w.s00);
+    if (mode == 0) return pem_launch_status();  // the operand preparation only
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
@@ -1331,11 +1332,13 @@ extern "C" int pem_fine_fused_pass_ex(const float *f1, const float *f2, int B, i
     PEM_REQUIRE_PTR(f1);
     PEM_REQUIRE_PTR(f2);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0, PEM_E_SHAPE);
-    PEM_REQUIRE(pass >= 1 && pass <= 4, PEM_E_UNSUPPORTED);
+    PEM_REQUIRE(pass >= 0 && pass <= 4, PEM_E_UNSUPPORTED);
     PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
-    return pem_dev_fine_pass(f1, f2, B, N1, N2, C, temp, precision == PEM_PREC_FP16 ? 8 : 0, pass, 0, workspace,
-                             workspace_bytes, stream);
+    // pass 0: the operand preparation alone (what precedes the passes in a step and leaves the
+    // operands in L2 for them)
+    return pem_dev_fine_pass(f1, f2, B, N1, N2, C, temp, precision == PEM_PREC_FP16 ? 8 : 0, pass, pass == 0,
+                             workspace, workspace_bytes, stream);
 }
 
 extern "C" int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,

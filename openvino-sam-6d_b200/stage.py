@@ -23,6 +23,8 @@ whose row 0 is the background token and rows 1.. the dense features, ``model`` (
 ``rand`` (B,3*P1).  Output: ``records`` (B,16) fp32 = R (9), t (3), pose_score, proposal
 id, instance id, pad -- the 64-byte per-instance record the multi-GPU gather moves.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -41,6 +43,7 @@ class GeometricStage:
         self.L = _lib.lib()
         self.n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.fine_mode = fine_mode
+        self.side_after_similarity = os.environ.get("PEM_SIDE_EARLY") != "1"  # development switch
         self.fine_precision = FINE_PRECISIONS[fine_precision]  # PEM_PREC_* of the fused fine GEMM
         B, N, M, C, Nm, P1, P2 = batch, n_dense, n_sparse, feat_dim, n_model, n_proposal1, n_proposal2
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -127,9 +130,6 @@ class GeometricStage:
         # 2B CTAs of the FPS kernel instead of waiting for them in a second round)
         ck(L.pem_pe_masks(p(self.pts), 2 * B, N, 1e-8, max(r1, r2), 1e-3, max(1, self.n_sms - 2 * B),
                           p(self.pe_masks), self.pe_mask_bytes, self.side.cuda_stream), "pe_masks"); n += 1
-        ck(L.pem_pe_group2_masked(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
-                                  p(self.pe_out[1][B:]), p(self.pe_masks) + half, half,
-                                  self.side.cuda_stream), "pe_group2 unmoved cloud"); n += 1
         # 1. FPS on both clouds in one launch (2B clouds), then row gathers
         # (the sampled points are stored by the sampling kernel itself: no separate gather launch)
         ck(L.pem_fps_gather(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), p(self.sparse_pts), None, 0, st),
@@ -141,6 +141,17 @@ class GeometricStage:
         ck(L.pem_feature_similarity(p(self.sparse_feats[0]), p(self.sparse_feats[1]), B, M + 1, M + 1,
                                     C, self.temp, 1, p(self.atten_c), p(self.ws), self.ws_bytes, st),
            "coarse similarity"); n += 2
+        # The grouping of the unmoved cloud (bulk work, every SM) is held back until here: under the FPS it
+        # would spill over the feature gather and the similarity GEMM of the critical chain (both slowed by
+        # a third), while coarse_assign (64 CTAs) and the hypothesis kernel that follow are latency bound
+        # and leave most of the chip idle.
+        if self.side_after_similarity:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.side.wait_event(ev)
+        ck(L.pem_pe_group2_masked(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
+                                  p(self.pe_out[1][B:]), p(self.pe_masks) + half, half,
+                                  self.side.cuda_stream), "pe_group2 unmoved cloud"); n += 1
         ck(L.pem_coarse_assign(p(self.atten_c), B, M, M, p(self.w1c), p(self.w2c), p(self.cdf), st),
            "coarse_assign"); n += 1
         ck(L.pem_coarse_hypotheses(p(self.cdf), p(self.rand), p(self.sparse_pts[0]),

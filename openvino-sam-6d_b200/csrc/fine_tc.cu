@@ -8,13 +8,19 @@
 //             background token (row 0 of both feature sets) stays OUT of the GEMM: its row and
 //             column of the similarity matrix are 2 x 2049 exact fp32 dot products computed
 //             here, so the GEMM is exactly 2048 x 2048 per instance (no 2049 -> 2304 padding).
-//   GEMM      S = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (split-bf16: ~2^-17 relative, i.e.
-//             fp32-class logits; plain bf16 would move the pose by up to 0.05 deg) with the
-//             accumulator in TMEM, recomputed in passes whose epilogues reduce straight out of TMEM:
+//   GEMM      two arithmetics (PEM_PREC_*, include/pem_b200.h):
+//               split-bf16  S = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T  (~2^-17 relative, i.e. fp32-class
+//                           logits; plain bf16 would move the pose by up to 0.05 deg);
+//               fp16        S = A B^T on fp16(x) -- unit vectors: 2^-12 relative per element, logits to
+//                           ~1e-3 of +-1/temp, pose within 1e-4 deg of the oracle on the parity cases; a
+//                           third of the MMAs, no lo operand (its shared-memory buffers extend the ring);
+//             with the accumulator in TMEM, recomputed in passes whose epilogues reduce straight out of TMEM
+//             (arithmetic in packed fp32 pairs, FFMA2 / FADD2):
 //               pass 1  e = exp(s/temp - 1/temp);  row sums, column sums      (softmax stats)
 //               pass 2  foreground labels (MU:321-322), compared in the log2 domain:
 //                       row max of (2 s/temp - log colsum_j) vs the background column,
-//                       column max of (2 s/temp - log rowsum_i) vs the background row;
+//                       column max of (2 s/temp - log rowsum_i) vs the background row (merged pass: as
+//                       "does any row beat the column's background entry", a sign-bit mask per column);
 //                       AND, per row, sum_j P_ij and sum_j P_ij pts2_j over EVERY column j
 //               pass 3  (ragged: one 256-column strip per instance) the same sums over the columns
 //                       that pass 2 found to be background, compacted into a spare operand, to be
@@ -24,7 +30,7 @@
 //             so a fixed shift replaces the running max of a streaming softmax.
 //   then the weighted Procrustes + pose score kernels of fine.cu.
 //
-// Kernel anatomy (persistent, one CTA per SM, 320 threads, CTAs grouped in PAIRS = clusters of 2
+// Kernel anatomy (persistent, one CTA per SM, 320 threads [fp16 mode: 576], CTAs grouped in PAIRS = clusters of 2
 // driving tcgen05 cta_group::2).  A task = (instance, 256-COLUMN strip, a few 256-row steps) and
 // belongs to a pair, which issues one M=256 x N=256 x K=16 MMA per K step:
 //   - each CTA keeps ITS 128 columns of the strip of B' (hi+lo, 128 KB) resident in shared memory
@@ -43,7 +49,7 @@
 //               issuer.  tcgen05.commit multicasts slot-free / accumulator-ready / chunk-free
 //               to both CTAs.
 //   warps 2-9   epilogue: tcgen05.ld 32x32b (one TMEM lane = one output row per thread, two
-//               warps per lane quadrant, 128 columns each).  Reductions along the columns of
+//   (2-17)      warps per lane quadrant, 128 columns each; fp16 mode: four per quadrant, 64 columns each).  Reductions along the columns of
 //               a tile are thread-local and leave as per-(row, strip-half) partials; reductions
 //               along the rows accumulate in 128 registers per thread ACROSS the steps of the
 //               task and are folded across lanes once per task (31-shuffle transpose reduce per

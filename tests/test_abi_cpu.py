@@ -29,6 +29,15 @@ def test_no_torch_types_in_the_abi():
     assert 'extern "C"' in src and "at::Tensor" not in src
 
 
+def test_precision_constants_match_the_header(pkg):
+    """The Python mirrors pass PEM_PREC_* by value: they must be the header's numbers."""
+    src = open(os.path.join(ROOT, "include", "pem_b200.h")).read()
+    defs = dict(re.findall(r"#define\s+(PEM_PREC_[A-Z0-9_]+)\s+(\d+)", src))
+    want = {"split_bf16": int(defs["PEM_PREC_SPLIT_BF16"]), "fp16": int(defs["PEM_PREC_FP16"])}
+    assert pkg.model_utils.FINE_PRECISIONS == want
+    assert pkg.stage.FINE_PRECISIONS == want
+
+
 def test_identification(pkg):
     lib = pkg._lib.lib()
     assert lib.pem_abi_version() == 1

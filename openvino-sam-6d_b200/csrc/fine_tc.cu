@@ -663,18 +663,9 @@ tc_prep_kernel(const float *__restrict__ fa, int rows_a, int rows_pa, __nv_bfloa
             const int i = i0 + r;
             uint2 *hi = reinterpret_cast<uint2 *>(out + (size_t)(gr + r) * C),
                   *lo = reinterpret_cast<uint2 *>(out + ((size_t)B * rows_p + gr + r) * C);
-            if (i >= rows) {  // padding rows
-#pragma unroll
-                for (int it = 0; it < NQ; ++it) {
-                    const int q = it * 32 + lane;
-                    if (q < nq) {
-                        hi[q] = make_uint2(0u, 0u);
-                        if (!single) lo[q] = make_uint2(0u, 0u);
-                    }
-                }
-                if (skip && lane == 0) bg[(size_t)b * rows_p + i] = 0.f;
-                continue;
-            }
+            // (padding rows, i >= rows, were fetched as zeros and come out as zeros below -- operand planes
+            // and background cosine alike -- so the row loop stays free of divergent branches around its
+            // warp reductions)
             // x * (1/norm) instead of the reference's x / norm: at most 1 ulp apart, far below the
             // 2^-12 / 2^-17 of the rounding that follows, and 8 IEEE divisions per lane cheaper
             const float rinv = normalize ? 1.0f / inv_of(sumsq(x[r])) : 1.f;

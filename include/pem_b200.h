@@ -55,7 +55,8 @@ const char *pem_status_string(int status);
  * PEM_FPS_SKIP_NEAR_ORIGIN points with |p|^2 <= 1e-3 (compared in double) are
  * never selected.  flags = 0 drops the near-origin rule (the reference's CUDA variant,
  * sampling_gpu.cu:106) but keeps lowest-index tie breaking.
- * workspace: pem_fps_workspace_bytes(B,N) bytes (0 for N <= 16384; may then be NULL).
+ * workspace: pem_fps_workspace_bytes(B,N) bytes (0 for N <= 262144 = 16 CTAs x 16384 points, the
+ * largest cloud the cluster kernel keeps on chip; may then be NULL).
  */
 size_t pem_fps_workspace_bytes(int B, int N);
 int pem_fps(const float *xyz, int B, int N, int M, int flags, int32_t *idx, void *workspace,
@@ -311,6 +312,29 @@ int pem_fine_fused_pass_ex(const float *f1, const float *f2, int B, int N1, int 
 int pem_weighted_procrustes(const float *src, const float *ref, const float *weights, int Bp,
                             int n, float weight_thresh, float eps, float *R, float *t,
                             pem_stream_t stream);
+
+/*
+ * The reference's operator seam (utils/model_utils.py:457-526): the three autograd `Function` shells whose
+ * forward is torch.svd / torch.det / torch.searchsorted and whose `symbolic` emits the custom ONNX ops the
+ * OpenVINO plugin fills (ov_pointnet2_op/custom_svd.cpp:103-180 Eigen BDCSVD, custom_det.cpp:52-74,
+ * custom_searchsorted.cpp:90-109).  Standalone batched entry points at the shapes of the reference's op
+ * scripts (ov_op_test/ov_test_custom_svd.py:31-33: 42000 x 3 x 3); the fused kernels of the hot path carry
+ * the same arithmetic inline.
+ *   pem_svd3_batched   H (n,3,3) row-major -> U (n,3,3), S (n,3) descending, V (n,3,3) with
+ *                      H = U diag(S) V^T (torch.svd's convention: V, not V^T); any of U, S, V may be NULL.
+ *                      fp64 one-sided Jacobi per matrix; U, V orthonormal for every input (rank-deficient
+ *                      H: missing vectors completed; H = 0 -> U = V = I like LAPACK).  Singular VECTORS are
+ *                      unique only up to sign (and rotation inside equal singular values), so parity with
+ *                      LAPACK is on S, on U diag(S) V^T, and on R = V diag(1,1,det(V U^T)) U^T.
+ *   pem_det3_batched   H (n,3,3) -> det (n): cofactor expansion in fp64, rounded once.
+ *   pem_searchsorted   sorted_seq (B,N) non-decreasing, values (B,S) -> out (B,S) int64 = the first e with
+ *                      sorted_seq[b,e] >= values[b,s], N when there is none (torch.searchsorted right=False;
+ *                      the lower-bound `>=` rule of custom_searchsorted.cpp:95-104).  Bit exact.
+ */
+int pem_svd3_batched(const float *H, long long n, float *U, float *S, float *V, pem_stream_t stream);
+int pem_det3_batched(const float *H, long long n, float *det, pem_stream_t stream);
+int pem_searchsorted(const float *sorted_seq, const float *values, int B, int N, int S, int64_t *out,
+                     pem_stream_t stream);
 
 /*
  * PositionalEncoding front end (model/fine_point_matching.py:102-144) without the

@@ -66,6 +66,9 @@ SIGNATURES = {
                                   c_i, c_i, c_p, c_p, c_p, c_p]),
     "pem_pack_records": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
     "pem_weighted_procrustes": (c_i, [c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    "pem_svd3_batched": (c_i, [c_p, c_ll, c_p, c_p, c_p, c_p]),
+    "pem_det3_batched": (c_i, [c_p, c_ll, c_p, c_p]),
+    "pem_searchsorted": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
 }
 
 

@@ -725,10 +725,12 @@ extern "C" int pem_coarse_assign(const float *atten, int B, int N1, int N2, floa
     PEM_REQUIRE_PTR(w2);
     PEM_REQUIRE_PTR(cdf);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0, PEM_E_SHAPE);
-    if (N1 + 1 >= 8 * kAsgCl && (long long)((N1 + kAsgCl) / kAsgCl) * (N2 + 1) <= 40000) {
-        // thread-block cluster: kAsgCl SMs per instance
+    if (N1 + 1 >= 8 * kAsgCl && (long long)((N1 + kAsgCl) / kAsgCl) * (N2 + 1) <= 40000 &&
+        coarse_assign_cluster_smem(N1, N2) <= (size_t)227 * 1024) {
+        // thread-block cluster: kAsgCl SMs per instance (shapes whose per-CTA slice plus the 2*kAsgCl
+        // exchange rows exceed 227 KB fall through to the single-CTA kernel or PEM_E_UNSUPPORTED)
         const size_t smem = coarse_assign_cluster_smem(N1, N2);
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         if (int rc = pem_ensure_dyn_smem(coarse_assign_cluster_kernel, smem, &cached)) return rc;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(B * kAsgCl);
@@ -746,9 +748,10 @@ extern "C" int pem_coarse_assign(const float *atten, int B, int N1, int N2, floa
         if (e != cudaSuccess) return (int)e;
         return pem_launch_status();
     }
-    PEM_REQUIRE((long long)(N1 + 1) * (N2 + 1) <= 50176, PEM_E_UNSUPPORTED);
+    PEM_REQUIRE((long long)(N1 + 1) * (N2 + 1) <= 50176 && coarse_assign_smem(N1, N2) <= (size_t)227 * 1024,
+                PEM_E_UNSUPPORTED);
     const size_t smem = coarse_assign_smem(N1, N2);
-    static size_t cached = 0;
+    static PemSmemCache cached(0);
     if (int rc = pem_ensure_dyn_smem(coarse_assign_kernel, smem, &cached)) return rc;
     coarse_assign_kernel<<<B, 1024, smem, pem_cu_stream(stream)>>>(atten, N1, N2, w1, w2, cdf);
     return pem_launch_status();
@@ -810,12 +813,12 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     const size_t smem = score_smem(N1, Nm, big ? 8 : 4);
     PEM_REQUIRE(smem <= 227 * 1024, PEM_E_UNSUPPORTED);
     if (big) {
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<8, 256>, smem, &cached)) return rc;
         score_hypotheses_kernel<8, 256><<<dim3((H + 7) / 8, B), 256, smem, pem_cu_stream(stream)>>>(
             R, t, sel, P, H, pts1, w1, N1, model, Nm, scores);
     } else {
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         // 4 hypotheses x <=196 points over 128 threads: up to 7 register-held queries per thread
         if (int rc = pem_ensure_dyn_smem(score_hypotheses_kernel<4, 128>, smem, &cached)) return rc;
         score_hypotheses_kernel<4, 128><<<dim3((H + 3) / 4, B), 128, smem, pem_cu_stream(stream)>>>(

@@ -425,7 +425,7 @@ int fine_tail_launch(const float *pred, const float *pts1, const float *rowsumA,
     pem_launch_pdl(weighted_procrustes_kernel, dim3(B), dim3(256), 0, st, pred, pts1, rowsumA, N1, 0.0f, 1e-5f, R, t,
                    counters);
     const size_t smem = (size_t)Nm * sizeof(float4);
-    static size_t cached = 40 * 1024;
+    static PemSmemCache cached(40 * 1024);
     if (int rc = pem_ensure_dyn_smem(fine_pose_score_kernel, smem, &cached)) return rc;
     pem_launch_pdl(fine_pose_score_kernel, dim3((N1 + kPsPoints - 1) / kPsPoints, B), dim3(kPsThreads), smem, st, pts1,
                    w1, R, t, model, N1, Nm, dis_thres, counters, score);

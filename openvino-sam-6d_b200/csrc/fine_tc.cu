@@ -1040,16 +1040,7 @@ static Ws carve(void *base, int B, int rows1, int rows2, int C) {
     return w;
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = PEM_NUM_SMS;
-    }
-    return n;
-}
+static int num_sms() { return pem_num_sms(); }
 
 static int g_steps_per_task = 0;  // development knob: 0 = choose automatically
 static int g_fine_passes = 2;     // development knob: 3 = the original three full GEMM passes
@@ -1110,7 +1101,7 @@ template <int MODE, int EPW>
 static int launch_pass_w(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
     constexpr int kThreads = 64 + 32 * EPW;
     const size_t smem = sizeof(Smem) + 1024;
-    static size_t cached = 0;
+    static PemSmemCache cached(0);
     if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE, EPW>, smem, &cached)) return rc;
     const int n_tasks = p.B * p.n_strips * p.n_splits;
     const int pairs = min(max(1, num_sms() / 2), n_tasks);  // one cluster of two CTAs per SM pair

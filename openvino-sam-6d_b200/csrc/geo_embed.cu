@@ -107,7 +107,7 @@ extern "C" int pem_geo_embedding_indices(const float *points, int B, int N, int 
     PEM_REQUIRE(B > 0 && N > 0 && angle_k > 0 && sigma_d > 0.f && sigma_a > 0.f && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(angle_k <= kGeoMaxK && angle_k < N && N <= 8192, PEM_E_UNSUPPORTED);  // 4 floats of smem per point
     const size_t smem = (size_t)4 * N * sizeof(float);
-    static size_t cached = 40 * 1024;
+    static PemSmemCache cached(40 * 1024);
     if (int rc = pem_ensure_dyn_smem(geo_embedding_kernel, smem, &cached)) return rc;
     const float factor_a = (float)(180.0 / ((double)sigma_a * 3.14159265358979323846));  // transformer.py:294, a Python float
     geo_embedding_kernel<<<dim3(N, B), kGeoThreads, smem, pem_cu_stream(stream)>>>(points, N, angle_k, sigma_d,

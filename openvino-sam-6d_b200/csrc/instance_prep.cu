@@ -229,15 +229,16 @@ instance_sample_kernel(const float *__restrict__ depth, int H, int W, Camera cam
                        const int32_t *__restrict__ scratch, const int32_t *__restrict__ det_ids,
                        const long long *__restrict__ pick, int n_sample, int img_size,
                        float *__restrict__ pts, long long *__restrict__ rgb_choose,
-                       long long *__restrict__ choose_out) {
+                       long long *__restrict__ choose_out, int D) {
     const int slot = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
     if (j >= n_sample) return;
     const int d = det_ids[slot];
-    const int32_t *inf = info + (size_t)d * kInfoInts;
+    const bool det_ok = d >= 0 && d < D;  // a detection id outside [0,D): flagged like a bad draw, never read
+    const int32_t *inf = info + (size_t)(det_ok ? d : 0) * kInfoInts;
     const int m = inf[2], y1 = inf[3], y2 = inf[4], x1 = inf[5], x2 = inf[6];
     const size_t o = (size_t)slot * n_sample + j;
     long long p = pick[o];
-    if (p < 0 || p >= m) {  // a draw outside the candidate list: flagged, never read
+    if (!det_ok || p < 0 || p >= m) {  // a draw outside the candidate list: flagged, never read
         pts[3 * o] = pts[3 * o + 1] = pts[3 * o + 2] = 0.f;
         rgb_choose[o] = -1;
         if (choose_out) choose_out[o] = -1;
@@ -334,10 +335,10 @@ extern "C" int pem_instance_sample(const float *depth_m, int H, int W, double fx
     if (precision == 0)
         instance_sample_kernel<float><<<grid, 256, 0, st>>>(depth_m, H, W, k, info, (const int32_t *)scratch, det_ids,
                                                             (const long long *)pick, n_sample, img_size, pts,
-                                                            (long long *)rgb_choose, (long long *)choose);
+                                                            (long long *)rgb_choose, (long long *)choose, D);
     else
         instance_sample_kernel<double><<<grid, 256, 0, st>>>(depth_m, H, W, k, info, (const int32_t *)scratch, det_ids,
                                                              (const long long *)pick, n_sample, img_size, pts,
-                                                             (long long *)rgb_choose, (long long *)choose);
+                                                             (long long *)rgb_choose, (long long *)choose, D);
     return pem_launch_status();
 }

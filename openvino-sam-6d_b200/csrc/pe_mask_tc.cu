@@ -264,16 +264,14 @@ pe_mask_tc_kernel(const float *__restrict__ xyz, int N, float eps, float thr, fl
 int pe_mask_tc_launch(const float *xyz, int B, int N, float eps, float thr, float rel_slack, int max_ctas,
                       uint32_t *masks, cudaStream_t st) {
     using namespace tc;
-    int dev = 0, sms = PEM_NUM_SMS;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = pem_num_sms();
     const int W = (N + 31) / 32;
     const int n_colblocks = (N + kMCols - 1) / kMCols, n_tiles = (N + kMRows - 1) / kMRows;
     const int n_units = B * n_colblocks * n_tiles;
     int grid = min(n_units, sms);  // one CTA per SM (all of TMEM, 160 KB of shared memory)
     if (max_ctas > 0) grid = min(grid, max_ctas);
     const size_t smem = sizeof(MaskSmem) + 1024;
-    static size_t cached = 0;
+    static PemSmemCache cached(0);
     if (int rc = pem_ensure_dyn_smem(pe_mask_tc_kernel, smem, &cached)) return rc;
     pe_mask_tc_kernel<<<grid, kMThreads, smem, st>>>(xyz, N, eps, thr, rel_slack, W, n_colblocks, n_units, masks);
     return pem_launch_status();

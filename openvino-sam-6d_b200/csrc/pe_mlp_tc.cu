@@ -299,20 +299,18 @@ extern "C" int pem_pe_mlp(const float *xyz, const int32_t *idx, int B, int N, in
     PEM_REQUIRE_PTR(out);
     PEM_REQUIRE(B > 0 && N > 0 && ldo >= ch_off + kPmC3 && ch_off >= 0, PEM_E_SHAPE);
     PEM_REQUIRE(N <= kPmMaxN && (nsample == 32 || nsample == 64 || nsample == 128), PEM_E_UNSUPPORTED);
-    int dev = 0, sms = PEM_NUM_SMS;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = pem_num_sms();
     const long long tpc = ((long long)N * nsample + kPmRows - 1) / kPmRows;
     const bool two = N <= kPmMaxN / 2 && tpc % 2 == 0;  // two row groups per CTA on alternate tiles
     const long long n_slots = (long long)B * tpc / (two ? 2 : 1);
     const int grid = (int)(n_slots < sms ? n_slots : sms);
     cudaStream_t st = pem_cu_stream(stream);
-    auto go = [&](auto kern, size_t smem, int threads, size_t *cached) -> int {
+    auto go = [&](auto kern, size_t smem, int threads, PemSmemCache *cached) -> int {
         if (int rc = pem_ensure_dyn_smem(kern, smem, cached)) return rc;
         kern<<<grid, threads, smem, st>>>(xyz, idx, B, N, centre_eps, w1, w2, w3, shift, out, ldo, ch_off);
         return pem_launch_status();
     };
-    static size_t cached[6] = {0, 0, 0, 0, 0, 0};
+    static PemSmemCache cached[6];
     const size_t s1 = sizeof(PmSmem<1>) + 1024, s2 = sizeof(PmSmem<2>) + 1024;
     const int t1 = 32 + kPmRows, t2 = 32 + 2 * kPmRows;
     if (two) {

@@ -4,6 +4,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "pem_b200.h"
 
 #define PEM_NUM_SMS 148  // B200: 2 dies x 74 SMs
@@ -23,18 +25,44 @@ static inline int pem_launch_status() {
     return e == cudaSuccess ? PEM_OK : (int)e;
 }
 
-// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is raised only when a
-// larger size than ever before is requested (cached per call site), so steady-state calls --
-// including calls made while the stream is being captured into a CUDA graph -- issue no
-// runtime API call here.
+// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per DEVICE, so the sizes already
+// granted are cached per call site AND per device (relaxed atomics: host threads may race to raise it, the
+// worst case is one redundant cudaFuncSetAttribute).  Steady-state calls -- including calls made while the
+// stream is being captured into a CUDA graph -- issue no runtime API call beyond cudaGetDevice.
+#define PEM_MAX_DEVICES 64
+struct PemSmemCache {
+    std::atomic<size_t> granted[PEM_MAX_DEVICES];
+    explicit PemSmemCache(size_t initial = 0) {
+        for (auto &g : granted) g.store(initial, std::memory_order_relaxed);
+    }
+};
+static inline int pem_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
 template <typename Kern>
-static inline int pem_ensure_dyn_smem(Kern kern, size_t bytes, size_t *cached) {
-    if (bytes <= *cached) return PEM_OK;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bytes);
+static inline int pem_ensure_dyn_smem(Kern kern, size_t bytes, PemSmemCache *cache) {
+    const int dev = pem_current_device();
+    const bool tracked = dev >= 0 && dev < PEM_MAX_DEVICES;
+    if (tracked && bytes <= cache->granted[dev].load(std::memory_order_relaxed)) return PEM_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    *cached = bytes;
+    if (tracked) cache->granted[dev].store(bytes, std::memory_order_relaxed);
     return PEM_OK;
+}
+// Number of SMs of the current device (cached per device).
+static inline int pem_num_sms() {
+    static std::atomic<int> sms[PEM_MAX_DEVICES];
+    const int dev = pem_current_device();
+    const bool tracked = dev >= 0 && dev < PEM_MAX_DEVICES;
+    int n = tracked ? sms[dev].load(std::memory_order_relaxed) : 0;
+    if (n <= 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = PEM_NUM_SMS;
+        if (tracked) sms[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
 }
 
 static inline cudaStream_t pem_cu_stream(pem_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

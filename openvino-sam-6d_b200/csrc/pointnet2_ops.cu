@@ -270,7 +270,7 @@ static int launch_fps_cta(const float *xyz, int B, int N, int M, int skip, int32
                           cudaStream_t st, float *new_xyz = nullptr) {
     const size_t smem = (size_t)3 * N * sizeof(float);
     auto kern = fps_cta_kernel<THREADS, PPT, IN_REGS>;
-    static size_t cached = 40 * 1024;  // static shared memory counts against the 48 KB default too
+    static PemSmemCache cached(40 * 1024);  // static shared memory counts against the 48 KB default too
     if (int rc = pem_ensure_dyn_smem(kern, smem, &cached)) return rc;
     kern<<<B, THREADS, smem, st>>>(xyz, N, M, skip, idx, new_xyz);
     return pem_launch_status();
@@ -282,13 +282,17 @@ static int launch_fps_cluster(const float *xyz, int B, int N, int M, int skip, i
     const int per = (N + C - 1) / C;
     const size_t smem = (size_t)3 * per * sizeof(float);
     auto kern = fps_cluster_kernel<THREADS, PPT, IN_REGS>;
-    static size_t cached = 40 * 1024;
+    static PemSmemCache cached(40 * 1024);
     if (int rc = pem_ensure_dyn_smem(kern, smem, &cached)) return rc;
-    static bool nonportable = false;
-    if (C > 8 && !nonportable) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return (int)e;
-        nonportable = true;
+    static PemSmemCache nonportable(0);  // per device, like the shared-memory opt-in (1 = attribute set)
+    if (C > 8) {
+        const int dev = pem_current_device();
+        const bool tracked = dev >= 0 && dev < PEM_MAX_DEVICES;
+        if (!tracked || nonportable.granted[dev].load(std::memory_order_relaxed) == 0) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return (int)e;
+            if (tracked) nonportable.granted[dev].store(1, std::memory_order_relaxed);
+        }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * C);
@@ -851,7 +855,7 @@ extern "C" int pem_ball_query(const float *new_xyz, const float *xyz, int B, int
     PEM_REQUIRE(B > 0 && M > 0 && N > 0 && nsample > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(nsample <= 128, PEM_E_UNSUPPORTED);
     const size_t smem = bq_smem_bytes(nsample);
-    static size_t cached = 0;
+    static PemSmemCache cached(0);
     if (int rc = pem_ensure_dyn_smem(ball_query_kernel, smem, &cached)) return rc;
     const float r2 = radius * radius;  // fp32 product, as ball_query.cpp:20
     ball_query_kernel<<<dim3((M + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
@@ -869,7 +873,7 @@ extern "C" int pem_query_and_group(const float *xyz, const float *new_xyz, const
     PEM_REQUIRE(C == 0 || feat != nullptr, PEM_E_NULL);
     PEM_REQUIRE(nsample <= 128, PEM_E_UNSUPPORTED);
     const size_t smem = bq_smem_bytes(nsample);
-    static size_t cached = 0;
+    static PemSmemCache cached(0);
     if (int rc = pem_ensure_dyn_smem(query_and_group_kernel, smem, &cached)) return rc;
     const float r2 = radius * radius;
     query_and_group_kernel<<<dim3((M + kBqCentres - 1) / kBqCentres, B), kBqCentres, smem,
@@ -903,13 +907,13 @@ extern "C" int pem_pe_group2(const float *xyz, int B, int N, float centre_eps, f
                         (size_t)kPeCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
     const dim3 grid((N + kPeCentres - 1) / kPeCentres, B);
     if (in_smem) {
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true, false>, smem, &cached)) return rc;
         pe_group2_kernel<true, false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
             xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
             nullptr, 0, nullptr, nullptr);
     } else {
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<false, false>, smem, &cached)) return rc;
         pe_group2_kernel<false, false><<<grid, kPeThreads, smem, pem_cu_stream(stream)>>>(
             xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
@@ -950,7 +954,7 @@ static int pe_masked_launch(const float *xyz, int B, int N, float centre_eps, fl
     const size_t n_pts = (size_t)(N + kPeTile - 1) / kPeTile * kPeTile;
     const size_t smem = n_pts * sizeof(float4) +
                         (size_t)kPeCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
-    static size_t cached = 0;
+    static PemSmemCache cached(0);
     if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true, true>, smem, &cached)) return rc;
     pe_group2_kernel<true, true><<<dim3((N + kPeCentres - 1) / kPeCentres, B), kPeThreads, smem,
                                   pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,

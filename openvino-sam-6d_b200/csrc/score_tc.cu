@@ -324,18 +324,16 @@ int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, i
                     float *scores, cudaStream_t st) {
     using namespace tc;
     if (Nm > 4 * kSMaxNm || N1 > kSMaxN1) return PEM_E_UNSUPPORTED;
-    int dev = 0, sms = PEM_NUM_SMS;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = pem_num_sms();
     const int cpi = max(1, min(sms / B, (H + 7) / 8));  // CTAs per instance
     if (g_score_parts == 2) {
         const size_t smem = sizeof(ScoreSmem<2>) + 1024;
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         if (int rc = pem_ensure_dyn_smem(score_tc_kernel<2>, smem, &cached)) return rc;
         score_tc_kernel<2><<<B * cpi, 64 + 256, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
     } else {
         const size_t smem = sizeof(ScoreSmem<4>) + 1024;
-        static size_t cached = 0;
+        static PemSmemCache cached(0);
         if (int rc = pem_ensure_dyn_smem(score_tc_kernel<4>, smem, &cached)) return rc;
         score_tc_kernel<4><<<B * cpi, 64 + 512, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
     }

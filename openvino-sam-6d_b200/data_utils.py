@@ -39,10 +39,18 @@ def _camera(K):
 def depth_to_metres(raw_depth, depth_scale, device="cuda"):
     """`load_im(depth_path).astype(np.float32) * cam_info['depth_scale'] / 1000.0` (:295) for a uint16
     sensor image: (H,W) uint16 (numpy or tensor) -> (H,W) float32 CUDA tensor in metres."""
-    raw = torch.as_tensor(np.ascontiguousarray(raw_depth).view(np.int16) if isinstance(raw_depth, np.ndarray)
-                          else raw_depth)
+    if isinstance(raw_depth, np.ndarray):
+        # check BEFORE the reinterpreting view: an int32 / float32 / uint8 image (imageio and cv2 can return
+        # those) must raise, not be read as a 16-bit image of another width
+        if raw_depth.dtype.kind not in "iu" or raw_depth.dtype.itemsize != 2:
+            raise TypeError("raw depth must be a 16-bit integer image, got %s" % raw_depth.dtype)
+        raw = torch.as_tensor(np.ascontiguousarray(raw_depth).view(np.int16))
+    else:
+        raw = torch.as_tensor(raw_depth)
     if raw.dtype not in (torch.int16, torch.uint16):
-        raise TypeError("raw depth must be 16-bit")
+        raise TypeError("raw depth must be a 16-bit integer image, got %s" % raw.dtype)
+    if raw.ndim != 2:
+        raise ValueError("raw depth must be (H,W)")
     raw = raw.to(device).contiguous()
     H, W = raw.shape
     out = torch.empty((H, W), dtype=torch.float32, device=raw.device)

@@ -3,7 +3,7 @@
 ``install_pointnet2_ext()`` registers this package's ``pointnet2_ext`` module as
 ``pointnet2._ext`` in ``sys.modules``: the reference's ``pointnet2_utils.py`` does
 ``import pointnet2._ext as _ext`` (pointnet2_utils.py:25-33) and then runs unmodified.
-``patch_model_utils(mu)`` swaps the four geometric functions of an already imported reference
+``patch_model_utils(mu)`` swaps the geometric functions and the operator-seam shells of an already imported reference
 ``utils/model_utils.py`` module for the accelerated ones (same signatures).
 """
 import sys
@@ -25,6 +25,7 @@ def install_pointnet2_ext():
 def patch_model_utils(mu):
     from . import model_utils as fast
     for name in ("sample_pts_feats", "compute_feature_similarity", "compute_coarse_Rt",
-                 "compute_fine_Rt", "weighted_procrustes", "WeightedProcrustes"):
+                 "compute_fine_Rt", "weighted_procrustes", "WeightedProcrustes", "CustomSearchSorted",
+                 "CustomSVD", "CustomSVDu", "CustomSVDv", "CustomDet"):
         setattr(mu, name, getattr(fast, name))
     return mu

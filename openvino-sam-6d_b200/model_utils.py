@@ -38,6 +38,8 @@ def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
     """FPS + point/feature gather.  pts (B,N,3), feats (B,N,C) -> (B,npoint,3), (B,npoint,C)
     [, idx (B,npoint) i32].  The gathers read the point-major tensors directly."""
     pts = _f32c(pts, "pts")
+    if feats.dtype != torch.float32 or not feats.is_cuda or feats.device != pts.device:
+        raise RuntimeError("feats must be a float CUDA tensor on the device of pts")
     B, N, _ = pts.shape
     M = int(npoint)
     if B == 0 or M == 0:
@@ -114,8 +116,9 @@ def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_pro
     scores = torch.empty((B, P2), **f32)
     R, t = torch.empty((B, 3, 3), **f32), torch.empty((B, 3), **f32)
     pid = torch.empty((B,), **i32)
-    L, st = _lib.lib(), _ext._stream()
+    L = _lib.lib()
     with torch.cuda.device(dev):
+        st = _ext._stream()  # the current stream of the tensors' device (taken inside the device context)
         _lib.check(L.pem_coarse_assign(atten.data_ptr(), B, N1, N2, w1.data_ptr(), w2.data_ptr(),
                                        cdf.data_ptr(), st), "pem_coarse_assign")
         _lib.check(L.pem_coarse_hypotheses(cdf.data_ptr(), rand.data_ptr(), pts1.data_ptr(),
@@ -255,3 +258,126 @@ class WeightedProcrustes(nn.Module):
     def forward(self, src_points, tgt_points, weights=None):
         return weighted_procrustes(src_points, tgt_points, weights, self.weight_thresh, self.eps,
                                    self.return_transform)
+
+
+# ---------------------------------------------------------------------------------------------
+# The operator seam (MU:457-526): CustomSearchSorted / CustomSVD(u,v) / CustomDet.  Same class names,
+# `apply` signatures, return values and ONNX `symbolic` names as the reference's shells; forward runs the
+# batched libpem_b200 kernels instead of torch.searchsorted / torch.svd / torch.det.
+# ---------------------------------------------------------------------------------------------
+def searchsorted(cumsum_weights, random_values):
+    """torch.searchsorted(cumsum_weights, random_values) (right=False) for (B,N) / (B,S) fp32 CUDA tensors
+    -> (B,S) int64; also accepts 1-D inputs.  MU:462-463, custom_searchsorted.cpp:90-109."""
+    one_d = cumsum_weights.ndim == 1
+    seq = _f32c(cumsum_weights, "cumsum_weights")
+    val = _f32c(random_values, "random_values")
+    if one_d:
+        seq, val = seq.unsqueeze(0), val.reshape(1, -1)
+    if seq.ndim != 2 or val.ndim != 2 or seq.shape[0] != val.shape[0]:
+        raise RuntimeError("searchsorted expects (B,N) and (B,S) tensors")
+    B, N = seq.shape
+    S = val.shape[1]
+    out = torch.empty((B, S), dtype=torch.int64, device=seq.device)
+    if out.numel():
+        if N == 0:
+            out.zero_()
+        else:
+            with torch.cuda.device(seq.device):
+                _lib.check(_lib.lib().pem_searchsorted(seq.data_ptr(), val.data_ptr(), B, N, S, out.data_ptr(),
+                                                       _ext._stream()), "pem_searchsorted")
+    return out.reshape(random_values.shape) if one_d else out
+
+
+def svd3(H, want=("U", "S", "V")):
+    """Batched SVD of (...,3,3) fp32 CUDA matrices: H = U diag(S) V^T like torch.svd (MU:475)."""
+    H = _f32c(H, "H")
+    if H.shape[-2:] != (3, 3):
+        raise RuntimeError("svd3 expects (...,3,3) matrices (the PEM pose solvers' shape)")
+    n = H.numel() // 9
+    mk = lambda *shape: torch.empty(H.shape[:-2] + shape, dtype=torch.float32, device=H.device)
+    U = mk(3, 3) if "U" in want else None
+    S = mk(3) if "S" in want else None
+    V = mk(3, 3) if "V" in want else None
+    if n:
+        p = lambda x: None if x is None else x.data_ptr()
+        with torch.cuda.device(H.device):
+            _lib.check(_lib.lib().pem_svd3_batched(H.data_ptr(), n, p(U), p(S), p(V), _ext._stream()),
+                       "pem_svd3_batched")
+    return U, S, V
+
+
+def det3(H):
+    """Batched determinant of (...,3,3) fp32 CUDA matrices (MU:520)."""
+    H = _f32c(H, "H")
+    if H.shape[-2:] != (3, 3):
+        raise RuntimeError("det3 expects (...,3,3) matrices")
+    out = torch.empty(H.shape[:-2], dtype=torch.float32, device=H.device)
+    if out.numel():
+        with torch.cuda.device(H.device):
+            _lib.check(_lib.lib().pem_det3_batched(H.data_ptr(), out.numel(), out.data_ptr(), _ext._stream()),
+                       "pem_det3_batched")
+    return out
+
+
+class CustomSearchSorted(torch.autograd.Function):
+    """MU:457-467."""
+
+    @staticmethod
+    def forward(ctx, cumsum_weights, random_values):
+        return searchsorted(cumsum_weights, random_values)
+
+    @staticmethod
+    def symbolic(g, cumsum_weights, random_values):
+        return g.op("CustomSearchSorted", cumsum_weights, random_values, outputs=1)
+
+
+class CustomSVD(torch.autograd.Function):
+    """MU:469-481: returns (U, S, V)."""
+
+    @staticmethod
+    def forward(ctx, H):
+        U, S, V = svd3(H)
+        ctx.save_for_backward(U, S, V)
+        return U, S, V
+
+    @staticmethod
+    def symbolic(g, H):
+        return g.op("CustomSVD", H, outputs=3)
+
+
+class CustomSVDu(torch.autograd.Function):
+    """MU:483-496."""
+
+    @staticmethod
+    def forward(ctx, H):
+        return svd3(H, want=("U",))[0]
+
+    @staticmethod
+    def symbolic(g, H):
+        return g.op("CustomSVDu", H, outputs=1)
+
+
+class CustomSVDv(torch.autograd.Function):
+    """MU:498-510."""
+
+    @staticmethod
+    def forward(ctx, H):
+        return svd3(H, want=("V",))[2]
+
+    @staticmethod
+    def symbolic(g, H):
+        return g.op("CustomSVDv", H, outputs=1)
+
+
+class CustomDet(torch.autograd.Function):
+    """MU:512-526."""
+
+    @staticmethod
+    def forward(ctx, H):
+        det = det3(H)
+        ctx.save_for_backward(det)
+        return det
+
+    @staticmethod
+    def symbolic(g, H):
+        return g.op("CustomDet", H, outputs=1)

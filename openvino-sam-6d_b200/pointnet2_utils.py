@@ -42,9 +42,17 @@ def gather_rows(feats, idx):
     idx (B,M) i32 -> (B,M,C).  Equals
     ``gather_operation(feats.transpose(1,2).contiguous(), idx).transpose(1,2)``
     (model_utils.py:77-80, transformer.py:667-671) without materialising the transposes."""
+    if not isinstance(feats, torch.Tensor) or feats.dtype != torch.float32:
+        raise RuntimeError("feats must be a float tensor")
+    if not feats.is_cuda:
+        raise RuntimeError("feats must be a CUDA tensor (libpem_b200 has no CPU path)")
+    if feats.ndim != 3:
+        raise RuntimeError("feats must be (B,N,C)")
     if feats.stride(2) != 1:
         feats = feats.contiguous()
     _ext._check(idx, "idx", torch.int32, "an int")
+    if idx.device != feats.device or idx.shape[0] != feats.shape[0]:
+        raise RuntimeError("idx must be (B,M) on the device of feats")
     B, N, C = feats.shape
     M = idx.shape[1]
     out = torch.empty((B, M, C), dtype=torch.float32, device=feats.device)

@@ -85,6 +85,13 @@ def test_argument_validation_without_gpu(pkg):
     assert lib.pem_instance_candidates(p, p, 1, 4, 4, 1.0, 1.0, 0.0, 0.0, 0, 0.2, p, p, 8, None) == -4
     assert lib.pem_instance_sample(p, 4, 4, 1.0, 1.0, 0.0, 0.0, 0, p, p, 64, 1, p, 0, p, 8, 224, p, p, None,
                                    None) == -2                                           # no kept detection
+    # operator seam
+    assert lib.pem_svd3_batched(None, 4, p, p, p, None) == -1
+    assert lib.pem_svd3_batched(p, 4, None, None, None, None) == -1      # at least one output
+    assert lib.pem_svd3_batched(p, 0, p, p, p, None) == -2
+    assert lib.pem_det3_batched(p, 4, None, None) == -1
+    assert lib.pem_searchsorted(p, p, 1, 0, 4, p, None) == -2
+    assert lib.pem_searchsorted(p, None, 1, 8, 4, p, None) == -1
     assert lib.pem_fps_workspace_bytes(4, 2048) == 0
     assert lib.pem_fps_workspace_bytes(2, 210000) == 0 and lib.pem_fps_workspace_bytes(2, 300000) == 2 * 300000 * 4
     assert lib.pem_fine_workspace_bytes(16, 2048, 2048) > 16 * 2049 * 4 * 6

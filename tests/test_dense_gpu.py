@@ -84,6 +84,52 @@ def test_coarse_hypotheses_S2_S3(pkg, oracle, dev):
     assert (torch.det(Rg) - 1).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("N1,N2", [(20, 20), (196, 196), (300, 300)])
+def test_sampler_edge_cases_on_device(pkg, oracle, dev, N1, N2):
+    """weighted_sampling_onnx_compatible (MU:277-305) = argmax(cumsum >= rand): the FIRST element >= the draw,
+    and 0 when none qualifies (argmax of an all-false row).  Cases: draws above the last cdf value (the cdf
+    ends at S/(S+1e-8) < 1), draws equal to a cdf entry, runs of equal entries, a draw of 0, and an
+    all-zero cdf (no foreground pair at all).  E = 90000 exceeds the kernel's shared-memory index
+    (64 x 1024 entries), so the direct search of the tail is covered too.  Bit exact against the
+    reference's compare/argmax form (faithful=True) and the lower-bound form."""
+    g = torch.Generator().manual_seed(N1)
+    E, P1 = N1 * N2, 512
+    inc = torch.rand(3, E, generator=g)
+    inc[:, torch.rand(E, generator=g) < 0.3] = 0.0     # runs of equal cdf entries (masked-out pairs)
+    cdf = torch.cumsum(inc.double(), 1)
+    cdf = (cdf / cdf[:, -1:] * 0.9).float()            # ends at 0.9: draws above it find nothing
+    cdf[2] = 0.0                                       # no foreground pair: everything maps to 0
+    rand = torch.rand(3, 3 * P1, generator=g)
+    rand[:, 0] = 1.0
+    rand[:, 1] = 0.95
+    rand[:, 2] = 0.0
+    rand[:, 3] = 0.9
+    pick = torch.randint(0, E, (3, 200), generator=g)
+    rand[:, 4:204] = torch.gather(cdf, 1, pick)        # draws that hit a cdf entry exactly
+    rand[:, 204:300] = torch.nextafter(rand[:, 4:100], torch.tensor(2.0))
+    want = oracle.inverse_cdf(cdf, rand, faithful=True)
+    assert torch.equal(want, oracle.inverse_cdf(cdf, rand, faithful=False))
+    assert (want[:, :2] == 0).all() and (want[2, 3:] == 0).all() and (want[0, 4:204] <= pick[0]).all()
+    L, ext = pkg._lib.lib(), pkg.pointnet2_ext
+    p1 = torch.randn(3, N1, 3, generator=g).to(dev)
+    p2 = torch.randn(3, N2, 3, generator=g).to(dev)
+    R, t = torch.empty(3, P1, 3, 3, device=dev), torch.empty(3, P1, 3, device=dev)
+    resid = torch.empty(3, P1, device=dev)
+    corr = torch.empty(3, P1 * 3, dtype=torch.int32, device=dev)
+    cd, rd = cdf.to(dev), rand.to(dev)
+    pkg._lib.check(L.pem_coarse_hypotheses(cd.data_ptr(), rd.data_ptr(), p1.data_ptr(), p2.data_ptr(), 3, N1, N2,
+                                           P1, R.data_ptr(), t.data_ptr(), resid.data_ptr(), corr.data_ptr(),
+                                           ext._stream()), "hyp")
+    assert torch.equal(corr.cpu().long(), want)
+    # instance 2 draws correspondence (0,0) three times: H = 0 -> R = I like LAPACK, t = p1[0] - p2[0]
+    assert torch.equal(R[2].cpu(), torch.eye(3).expand(P1, 3, 3))
+    assert torch.isfinite(R).all() and torch.isfinite(t).all() and torch.isfinite(resid).all()
+    # the standalone operator (CustomSearchSorted seam) agrees where an element qualifies
+    ss = pkg.model_utils.searchsorted(cd, rd).cpu()
+    assert torch.equal(ss, torch.searchsorted(cdf, rand))
+    assert torch.equal(torch.where(ss >= E, torch.zeros_like(ss), ss), want)
+
+
 @pytest.mark.parametrize("P1,P2", [(6000, 300), (1000, 1000), (777, 1), (60000, 300)])
 def test_select_smallest(pkg, dev, P1, P2):
     g = torch.Generator().manual_seed(P1)
@@ -182,7 +228,15 @@ def test_coarse_end_to_end_S5(pkg, oracle, dev):
     check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, b["model"], 6000, 300, b["rand"])
 
 
-def check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, model, P1, P2, rand, min_common=20):
+def check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, model, P1, P2, rand, min_common=20, stats=None):
+    """Staged comparison of compute_coarse_Rt with the oracle on the same atten / points / draw.
+
+    Bars: S3 on hypotheses whose H has sigma2/sigma1 > 1e-2 and whose three correspondences were
+    drawn identically: R, t 1e-4 abs.  S4: OUR scores against the oracle's scorer applied to OUR hypotheses
+    (identical hypotheses): rel 1e-4; end to end against the oracle's own score of the same proposal id
+    (hypotheses differ by the S3 error, |dR| ~ 1e-5 against point-to-model distances of ~ 0.03): rel 1e-3.
+    The best well-posed hypothesis is the same proposal id unless the oracle's top-2 gap is below 1e-3.
+    `stats` (dict) collects the winner-id match counts for the report under profiles/."""
     atten, sp, tp, model, rand = (torch.as_tensor(x) for x in (atten, sp, tp, model, rand))
     n_inst = sp.shape[0]
     oR, ot, ost = oracle.coarse_Rt(atten, sp, tp, model, P1, P2, rand)
@@ -190,8 +244,10 @@ def check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, model, P1, P2, 
                                                  P2, rand=rand.to(dev), return_stages=True)
     st = {k: v.cpu() for k, v in st.items()}
     S = torch.linalg.svdvals(ost["H"].double())
-    posed = (S[..., 1] / S[..., 0].clamp_min(1e-30)) > 1e-3
-    n_same_winner = 0
+    ratio = S[..., 1] / S[..., 0].clamp_min(1e-30)
+    posed = ratio > 1e-2
+    worst = {"dR": 0.0, "dt": 0.0, "score_staged": 0.0, "score_e2e": 0.0}
+    n_same_winner = n_winner_posed = n_same_posed_winner = 0
     for i in range(n_inst):
         ours, theirs = st["sel"][i].long(), ost["top"][i]
         assert len(set(ours.tolist()) ^ set(theirs.tolist())) <= 8
@@ -200,21 +256,41 @@ def check_coarse_against_oracle(pkg, oracle, dev, atten, sp, tp, model, P1, P2, 
         same_draw = (st["corr"][i].long() == ost["idx"][i]).view(-1, 3).all(1)
         common = [h for h in ours.tolist() if h in o_score and posed[i, h] and same_draw[h]]
         assert len(common) >= min_common
-        for h in common:
-            assert (st["R"][i, h].view(3, 3) - ost["R"][i, h]).abs().max().item() < 2e-3   # cond <= 1e3
-            assert abs(g_score[h] - o_score[h]) / o_score[h] < 2e-2
+        ci = torch.tensor(common)
+        # S4 staged: the oracle's scorer on OUR hypotheses
+        staged = oracle.score_hypotheses(st["R"][i, ci].view(1, -1, 3, 3), st["t"][i, ci].view(1, -1, 3), sp[i:i + 1],
+                                         ost["w1"][i:i + 1], model[i:i + 1])[0]
+        for k, h in enumerate(common):
+            worst["dR"] = max(worst["dR"], (st["R"][i, h].view(3, 3) - ost["R"][i, h]).abs().max().item())
+            worst["dt"] = max(worst["dt"], (st["t"][i, h] - ost["t"][i, h]).abs().max().item())
+            worst["score_staged"] = max(worst["score_staged"], abs(g_score[h] - staged[k].item()) / staged[k].item())
+            worst["score_e2e"] = max(worst["score_e2e"], abs(g_score[h] - o_score[h]) / o_score[h])
         best_o = max(common, key=lambda h: o_score[h])
         best_g = max(common, key=lambda h: g_score[h])
         second = sorted((o_score[h] for h in common), reverse=True)[1]
-        assert best_o == best_g or (o_score[best_o] - second) / o_score[best_o] < 2e-2, (i, best_o, best_g)
+        assert best_o == best_g or (o_score[best_o] - second) / o_score[best_o] < 1e-3, (i, best_o, best_g)
         same = st["proposal_id"][i].item() == ost["proposal_id"][i].item()
         n_same_winner += int(same)
-        if same and posed[i, ost["proposal_id"][i]]:  # identical well-posed winner -> pose within tolerance
+        w_posed = bool(posed[i, ost["proposal_id"][i]])
+        n_winner_posed += int(w_posed)
+        n_same_posed_winner += int(same and w_posed)
+        if same and w_posed:  # identical well-posed winner -> pose within tolerance
             assert oracle.rotation_angle_deg(R[i].cpu(), oR[i]).item() < 0.1
             assert (t[i].cpu() - ot[i]).abs().max().item() < 1e-4
         # (no assertion on the overall best score: when a degenerate triplet wins, its score is a
         #  function of LAPACK's rounding noise on one side and of ours on the other)
-    print("coarse winner identical on %d of %d instances (the rest: degenerate-triplet lottery)" % (n_same_winner, n_inst))
+    print("coarse winner identical on %d of %d instances; the oracle's winner is well-posed on %d, identical on %d "
+          "of those; worst well-posed errors %s" % (n_same_winner, n_inst, n_winner_posed, n_same_posed_winner, worst))
+    if stats is not None:
+        stats["instances"] = stats.get("instances", 0) + n_inst
+        stats["winner_id_match"] = stats.get("winner_id_match", 0) + n_same_winner
+        stats["oracle_winner_well_posed"] = stats.get("oracle_winner_well_posed", 0) + n_winner_posed
+        stats["winner_id_match_given_well_posed"] = stats.get("winner_id_match_given_well_posed", 0) + n_same_posed_winner
+        for k, v in worst.items():
+            stats["worst_" + k] = max(stats.get("worst_" + k, 0.0), v)
+    assert worst["dR"] < 1e-4 and worst["dt"] < 1e-4, worst          # S3
+    assert worst["score_staged"] < 1e-4, worst                          # S4, identical hypotheses
+    assert worst["score_e2e"] < 1e-3, worst                             # end to end (S3 error propagated)
     # correspondences drawn from OUR cdf differ from the oracle's only for draws that land
     # within rounding distance of a bin edge
     assert (st["corr"].long() != ost["idx"]).float().mean().item() < 0.005

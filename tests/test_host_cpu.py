@@ -113,3 +113,29 @@ def test_dropin_registers_pointnet2_ext(pkg):
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_depth_dtype_is_checked_before_the_reinterpreting_view(pkg):
+    """A non-16-bit depth image must raise instead of being read as a 16-bit image of another width."""
+    import numpy as np
+    import pytest
+    for bad in (np.zeros((4, 6), np.int32), np.zeros((4, 6), np.float32), np.zeros((4, 6), np.uint8),
+                np.zeros((4, 6), np.float16)):
+        with pytest.raises(TypeError):
+            pkg.data_utils.depth_to_metres(bad, 1.0)
+    with pytest.raises(TypeError):
+        pkg.data_utils.depth_to_metres(torch.zeros(4, 6, dtype=torch.int32), 1.0)
+    with pytest.raises(ValueError):
+        pkg.data_utils.depth_to_metres(np.zeros((2, 4, 6), np.uint16), 1.0)
+
+
+def test_gather_rows_validates_its_tensors(pkg):
+    """float16 / float64 / CPU feats must raise instead of being reinterpreted through a raw pointer."""
+    import pytest
+    idx = torch.zeros(1, 2, dtype=torch.int32)
+    for feats in (torch.zeros(1, 4, 8, dtype=torch.float16), torch.zeros(1, 4, 8, dtype=torch.float64),
+                  torch.zeros(1, 4, 8)):
+        with pytest.raises(RuntimeError):
+            pkg.pointnet2_utils.gather_rows(feats, idx)
+        with pytest.raises(RuntimeError):
+            pkg.model_utils.sample_pts_feats(torch.zeros(1, 4, 3), feats, 2)

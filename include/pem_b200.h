@@ -292,8 +292,8 @@ int pem_fine_fused_ex(const float *f1, const float *f2, const float *pts1, const
  * Profiling hook (no reference counterpart): re-run ONE reducing GEMM pass of pem_fine_fused on the
  * operands and constants a previous pem_fine_fused call with the same shapes left in `workspace`:
  * pass 1 softmax statistics, 4 foreground labels + weighted sums over all columns (the two full
- * passes of the default path), 2 labels only, 3 weighted sums only (the original three-pass
- * path).  Outputs go to workspace scratch only.  bench.py times the dominant kernel with it.
+ * passes of the default path), 5 the ragged background-column correction launch that follows them,
+ * 2 labels only, 3 weighted sums only (the original three-pass path).  Outputs go to workspace scratch only.  bench.py times the dominant kernel with it.
  */
 int pem_fine_fused_pass(const float *f1, const float *f2, int B, int N1, int N2, int C, float temp,
                         int pass, void *workspace, size_t workspace_bytes, pem_stream_t stream);
@@ -421,6 +421,40 @@ int pem_instance_sample(const float *depth_m, int H, int W, double fx, double fy
  */
 int pem_pack_records(const float *R, const float *t, const float *score, const int32_t *proposal_id,
                      const float *instance_id, int B, float *records, pem_stream_t stream);
+
+/*
+ * Multi-GPU pose-record gather without a collective call ("fused variant"; no reference
+ * counterpart): pem_gather_poses packs this rank's n_per_rank 64-byte records (as pem_pack_records) and
+ * stores them into the record tables of ALL `world` ranks over NVLink, then raises a per-rank flag;
+ * pem_gather_poses_wait waits for every rank's flag of the step and copies the complete
+ * (world * n_per_rank, 16) table to `out`.  Both are plain stream work (capturable into the step's CUDA
+ * graph).  Tables are double buffered by step parity; every rank must run the same sequence of steps.
+ *   setup (once; these call the allocator / CUDA IPC): pem_peer_table_bytes, pem_peer_alloc (cudaMalloc +
+ *   zero + IPC handle, 64 bytes), pem_peer_open (a peer's handle -> device pointer valid in this process),
+ *   pem_peer_release(ptr, opened).  peer_tables: HOST array of `world` device pointers, peer_tables[rank] =
+ *   the own table.
+ * A peer that does not deliver within timeout_ms sets word 1 of the own table's header instead of hanging.
+ */
+size_t pem_peer_table_bytes(int world, int n_per_rank);
+int pem_peer_alloc(size_t bytes, void **ptr, unsigned char *ipc_handle);
+int pem_peer_open(const unsigned char *ipc_handle, void **ptr);
+int pem_peer_release(void *ptr, int opened);
+int pem_gather_poses(const float *R, const float *t, const float *score, const int32_t *proposal_id,
+                     const float *instance_id, int n_per_rank, int rank, int world, void *const *peer_tables,
+                     float *records_local, pem_stream_t stream);
+int pem_gather_poses_wait(void *own_table, int world, int n_per_rank, float *out, int timeout_ms,
+                          pem_stream_t stream);
+
+/* fp16 -> fp32 widening of an uploaded tensor (host-facing path with half-precision features); n % 8 == 0. */
+int pem_half_to_float(const void *src, float *dst, size_t n, pem_stream_t stream);
+
+/*
+ * Measurement aid (no reference counterpart; SURVEY 8d asks for it): an FP32 issue-peak probe.  `ctas` CTAs of
+ * 512 threads each run `iters` x 64 dependent-chain instructions per lane over 8 independent chains: mode 0 =
+ * fused multiply-adds (2 flop each), mode 1 = unfused FMUL / FADD (the instruction mix bit-exactness with the
+ * reference's CPU loops mandates for FPS / ball query), mode 2 = packed fma.rn.f32x2 (4 flop each).  sink: one float, never written in practice.
+ */
+int pem_bench_fp32_peak(int mode, int ctas, int iters, float *sink, pem_stream_t stream);
 
 #ifdef __cplusplus
 }

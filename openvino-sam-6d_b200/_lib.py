@@ -69,6 +69,14 @@ SIGNATURES = {
     "pem_svd3_batched": (c_i, [c_p, c_ll, c_p, c_p, c_p, c_p]),
     "pem_det3_batched": (c_i, [c_p, c_ll, c_p, c_p]),
     "pem_searchsorted": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "pem_bench_fp32_peak": (c_i, [c_i, c_i, c_i, c_p, c_p]),
+    "pem_peer_table_bytes": (c_sz, [c_i, c_i]),
+    "pem_peer_alloc": (c_i, [c_sz, ctypes.POINTER(c_p), c_p]),
+    "pem_peer_open": (c_i, [c_p, ctypes.POINTER(c_p)]),
+    "pem_peer_release": (c_i, [c_p, c_i]),
+    "pem_gather_poses": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, ctypes.POINTER(c_p), c_p, c_p]),
+    "pem_gather_poses_wait": (c_i, [c_p, c_i, c_i, c_p, c_i, c_p]),
+    "pem_half_to_float": (c_i, [c_p, c_p, c_sz, c_p]),
 }
 
 

@@ -1084,6 +1084,25 @@ static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp
     return PEM_OK;
 }
 
+// Parameters of the ragged background-column correction launch.  Only the first strip_count[b] strips of an
+// instance are live there (one, as a rule): short tasks, so that the few live (instance, strip) pairs spread
+// over the CTA pairs instead of 8 steps in a row on 16 of them.
+static Params ragged_params(const Params &p, int B) {
+    Params pc = p;
+    const int pairs = max(1, num_sms() / 2);
+    int best = 1;
+    double best_cost = 1e30;
+    for (int spt = p.n_msteps; spt >= 1; --spt) {
+        const int splits = (p.n_msteps + spt - 1) / spt;
+        const long rounds = ((long)B * splits + pairs - 1) / pairs;
+        const double cost = (double)rounds * (spt + (p.single ? 0.75 : 0.25));
+        if (cost <= best_cost) { best_cost = cost; best = spt; }
+    }
+    pc.spt = g_steps_per_task > 0 ? p.spt : best;
+    pc.n_splits = (p.n_msteps + pc.spt - 1) / pc.spt;
+    return pc;
+}
+
 // normalise + split both operands (and the background dots when skip = 1)
 static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const float *f1, __nv_bfloat16 *A,
                         const float *f2, __nv_bfloat16 *Bm, int normalize, int skip, float *bg_a, float *bg_b,
@@ -1227,23 +1246,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
                                                 w.strip_count, p.single ? 1 : 2);
         CUtensorMap tmC;
         if (int rc = make_operand_map(&tmC, w.Bc, (size_t)2 * B * p.Np, C)) return rc;
-        Params pc = p;
-        // Only the first strip_count[b] strips of an instance are live here (one, as a rule): short tasks,
-        // so that the few live (instance, strip) pairs spread over the CTA pairs instead of 8 steps in a row
-        // on 16 of them.
-        {
-            const int pairs = max(1, num_sms() / 2);
-            int best = 1;
-            double best_cost = 1e30;
-            for (int spt = p.n_msteps; spt >= 1; --spt) {
-                const int splits = (p.n_msteps + spt - 1) / spt;
-                const long rounds = ((long)B * splits + pairs - 1) / pairs;
-                const double cost = (double)rounds * (spt + (p.single ? 0.75 : 0.25));
-                if (cost <= best_cost) { best_cost = cost; best = spt; }
-            }
-            pc.spt = g_steps_per_task > 0 ? p.spt : best;
-            pc.n_splits = (p.n_msteps + pc.spt - 1) / pc.spt;
-        }
+        Params pc = ragged_params(p, B);
         pc.G = w.Gc;
         pc.rowpart4 = w.rowpart_c;
         pc.strip_count = w.strip_count;
@@ -1308,6 +1311,16 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
         p.lbg = w.lbg;
         return launch_pass<kLabelW>(tmA, tmB, p, st);
     }
+    if (mode == 5) {  // the ragged background-column correction launch of the two-pass path
+        CUtensorMap tmC;
+        if (int rc = make_operand_map(&tmC, w.Bc, (size_t)2 * B * p.Np, C)) return rc;
+        Params pc = ragged_params(p, B);
+        pc.G = w.Gc;
+        pc.rowpart4 = w.rowpart_c;
+        pc.strip_count = w.strip_count;
+        pc.strip_major = 1;
+        return launch_pass<kWsum>(tmA, tmC, pc, st);
+    }
     return mode == 3 ? launch_pass<kWsum>(tmA, tmB, p, st)
                      : mode == 2 ? launch_pass<kLabel>(tmA, tmB, p, st) : launch_pass<kStats>(tmA, tmB, p, st);
 }
@@ -1320,7 +1333,7 @@ extern "C" int pem_fine_fused_pass_ex(const float *f1, const float *f2, int B, i
     PEM_REQUIRE_PTR(f1);
     PEM_REQUIRE_PTR(f2);
     PEM_REQUIRE(B > 0 && N1 > 0 && N2 > 0 && C > 0, PEM_E_SHAPE);
-    PEM_REQUIRE(pass >= 0 && pass <= 4, PEM_E_UNSUPPORTED);
+    PEM_REQUIRE(pass >= 0 && pass <= 5, PEM_E_UNSUPPORTED);
     PEM_REQUIRE(workspace != nullptr && workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
     // pass 0: the operand preparation alone (what precedes the passes in a step and leaves the

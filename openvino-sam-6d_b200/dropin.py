@@ -29,3 +29,17 @@ def patch_model_utils(mu):
                  "CustomSVD", "CustomSVDu", "CustomSVDv", "CustomDet"):
         setattr(mu, name, getattr(fast, name))
     return mu
+
+
+def patch_call_sites(*modules):
+    """The reference's matching modules bind the functions by name (`from model_utils import compute_coarse_Rt`,
+    coarse_point_matching.py:5-9, fine_point_matching.py:9), so patching `model_utils` alone does not reach them:
+    swap every accelerated name that a module holds."""
+    from . import model_utils as fast
+    names = ("sample_pts_feats", "compute_feature_similarity", "compute_coarse_Rt", "compute_fine_Rt",
+             "weighted_procrustes", "WeightedProcrustes")
+    for mod in modules:
+        for name in names:
+            if hasattr(mod, name):
+                setattr(mod, name, getattr(fast, name))
+    return modules

@@ -89,6 +89,9 @@ class GeometricStage:
         self.stream = torch.cuda.Stream(device=self.dev, priority=-1)
         self.side = torch.cuda.Stream(device=self.dev, priority=0)  # pose-independent work, forked inside a step
         self.graph = None
+        self.plan = None
+        self.feats_half = None  # PipelinedStage(upload="fp16") allocates it
+        self.gather = None  # parallel.RecordGather (mode "peer") attaches itself here
         self.use_graph = use_graph
         self.kernels_per_step = 0
 
@@ -109,13 +112,23 @@ class GeometricStage:
         self.stream.synchronize()
 
     # ---------------------------------------------------------------------------------
-    def _enqueue(self):
-        """The fixed launch sequence of one step on self.stream (also what gets captured)."""
-        L, st = self.L, self.stream.cuda_stream
+    def _plan(self):
+        """The fixed launch sequence of one step as a list of entries, built once (every buffer is
+        preallocated, so the pointers are fixed): ("launch", name, stream tag, fn(stream handle) -> status,
+        kernels launched) or ("fork" | "side_waits_main" | "main_waits_side",).  _enqueue() walks it (that is
+        also what gets captured into the CUDA graph); bench.py walks the "launch" entries to time every kernel
+        alone on one stream."""
+        L = self.L
         B, N, M, C, Nm, P1, P2 = self.B, self.N, self.M, self.C, self.Nm, self.P1, self.P2
-        ck = _lib.check
         p = lambda t: t.data_ptr()
-        n = 0
+        (r1, ns1), (r2, ns2) = PE_SCALES
+        half = self.pe_mask_bytes // 2
+        plan = []
+        add = lambda name, tag, fn, k=1: plan.append(("launch", name, tag, fn, k))
+        if self.feats_half is not None:
+            # host-facing path with half-precision features: widen the uploaded tensor into the fp32 slots
+            add("half_to_float(uploaded feats)", "main", lambda st: L.pem_half_to_float(
+                p(self.feats_half), p(self.feats), self.feats.numel(), st))
         # fork: pose-independent work runs on a side stream, concurrently with the (latency-bound,
         # few-CTA) FPS at the head of the coarse chain:
         #  * tensor-core candidate masks of the ball query for BOTH clouds in one launch.  One cloud is
@@ -123,87 +136,110 @@ class GeometricStage:
         #    survives a rigid motion, so its N^2 filter also runs here, ahead of the pose, and step 3
         #    only re-tests the candidates exactly on the moved points;
         #  * the PE grouping of the cloud that is not moved.
-        (r1, ns1), (r2, ns2) = PE_SCALES
-        half = self.pe_mask_bytes // 2
-        self.side.wait_stream(self.stream)
+        plan.append(("fork",))
         # (grid capped so that the filter's CTAs -- one whole SM each -- are resident TOGETHER with the
         # 2B CTAs of the FPS kernel instead of waiting for them in a second round)
-        ck(L.pem_pe_masks(p(self.pts), 2 * B, N, 1e-8, max(r1, r2), 1e-3, max(1, self.n_sms - 2 * B),
-                          p(self.pe_masks), self.pe_mask_bytes, self.side.cuda_stream), "pe_masks"); n += 1
+        add("pe_masks", "side", lambda st: L.pem_pe_masks(
+            p(self.pts), 2 * B, N, 1e-8, max(r1, r2), 1e-3, max(1, self.n_sms - 2 * B), p(self.pe_masks),
+            self.pe_mask_bytes, st))
         # 1. FPS on both clouds in one launch (2B clouds), then row gathers
         # (the sampled points are stored by the sampling kernel itself: no separate gather launch)
-        ck(L.pem_fps_gather(p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), p(self.sparse_pts), None, 0, st),
-           "fps + point gather"); n += 1
+        add("fps+point_gather", "main", lambda st: L.pem_fps_gather(
+            p(self.pts), 2 * B, N, M, 1, p(self.fps_idx), p(self.sparse_pts), None, 0, st))
         # dense features live in rows 1.. of `feats`; gather into rows 1.. of `sparse_feats`
-        ck(L.pem_gather_rows(p(self.feats) + 4 * C, p(self.fps_idx), 2 * B, N, C, M, (N + 1) * C, C,
-                             p(self.sparse_feats) + 4 * C, (M + 1) * C, st), "gather feats"); n += 1
+        add("gather_rows(sparse feats)", "main", lambda st: L.pem_gather_rows(
+            p(self.feats) + 4 * C, p(self.fps_idx), 2 * B, N, C, M, (N + 1) * C, C, p(self.sparse_feats) + 4 * C,
+            (M + 1) * C, st))
         # 2. coarse
-        ck(L.pem_feature_similarity(p(self.sparse_feats[0]), p(self.sparse_feats[1]), B, M + 1, M + 1,
-                                    C, self.temp, 1, p(self.atten_c), p(self.ws), self.ws_bytes, st),
-           "coarse similarity"); n += 2
+        add("coarse_similarity", "main", lambda st: L.pem_feature_similarity(
+            p(self.sparse_feats[0]), p(self.sparse_feats[1]), B, M + 1, M + 1, C, self.temp, 1, p(self.atten_c),
+            p(self.ws), self.ws_bytes, st), 2)
         # The grouping of the unmoved cloud (bulk work, every SM) is held back until here: under the FPS it
         # would spill over the feature gather and the similarity GEMM of the critical chain (both slowed by
         # a third), while coarse_assign (64 CTAs) and the hypothesis kernel that follow are latency bound
         # and leave most of the chip idle.
         if self.side_after_similarity:
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-            self.side.wait_event(ev)
-        ck(L.pem_pe_group2_masked(p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2,
-                                  p(self.pe_out[1][B:]), p(self.pe_masks) + half, half,
-                                  self.side.cuda_stream), "pe_group2 unmoved cloud"); n += 1
-        ck(L.pem_coarse_assign(p(self.atten_c), B, M, M, p(self.w1c), p(self.w2c), p(self.cdf), st),
-           "coarse_assign"); n += 1
-        ck(L.pem_coarse_hypotheses(p(self.cdf), p(self.rand), p(self.sparse_pts[0]),
-                                   p(self.sparse_pts[1]), B, M, M, P1, p(self.hyp_R), p(self.hyp_t),
-                                   p(self.resid), None, st), "coarse_hypotheses"); n += 1
-        ck(L.pem_select_smallest(p(self.resid), B, P1, P2, p(self.sel), st), "select_smallest"); n += 1
-        ck(L.pem_score_hypotheses(p(self.hyp_R), p(self.hyp_t), p(self.sel), B, P1, P2,
-                                  p(self.sparse_pts[0]), p(self.w1c), M, p(self.model), Nm,
-                                  p(self.scores), st), "score_hypotheses"); n += 1
-        ck(L.pem_select_best(p(self.scores), p(self.sel), p(self.hyp_R), p(self.hyp_t), B, P1, P2,
-                             p(self.init_R), p(self.init_t), p(self.proposal_id), st),
-           "select_best"); n += 1
+            plan.append(("side_waits_main",))
+        add("pe_group2_masked(template cloud)", "side", lambda st: L.pem_pe_group2_masked(
+            p(self.pts[1]), B, N, 1e-8, r1, ns1, p(self.pe_out[0][B:]), r2, ns2, p(self.pe_out[1][B:]),
+            p(self.pe_masks) + half, half, st))
+        add("coarse_assign", "main", lambda st: L.pem_coarse_assign(
+            p(self.atten_c), B, M, M, p(self.w1c), p(self.w2c), p(self.cdf), st))
+        add("coarse_hypotheses", "main", lambda st: L.pem_coarse_hypotheses(
+            p(self.cdf), p(self.rand), p(self.sparse_pts[0]), p(self.sparse_pts[1]), B, M, M, P1, p(self.hyp_R),
+            p(self.hyp_t), p(self.resid), None, st))
+        add("select_smallest", "main", lambda st: L.pem_select_smallest(p(self.resid), B, P1, P2, p(self.sel), st))
+        add("score_hypotheses", "main", lambda st: L.pem_score_hypotheses(
+            p(self.hyp_R), p(self.hyp_t), p(self.sel), B, P1, P2, p(self.sparse_pts[0]), p(self.w1c), M,
+            p(self.model), Nm, p(self.scores), st))
+        add("select_best", "main", lambda st: L.pem_select_best(
+            p(self.scores), p(self.sel), p(self.hyp_R), p(self.hyp_t), B, P1, P2, p(self.init_R), p(self.init_t),
+            p(self.proposal_id), st))
         # 3. fine front end: p1_ = (p1 - t) @ R ; PE grouping of p1_ and of the template
-        ck(L.pem_transform_points(p(self.pts[0]), p(self.init_R), p(self.init_t), B, N, 0.0,
-                                  p(self.pe_xyz[0]), st), "transform"); n += 1
+        add("transform_points", "main", lambda st: L.pem_transform_points(
+            p(self.pts[0]), p(self.init_R), p(self.init_t), B, N, 0.0, p(self.pe_xyz[0]), st))
         # both PE scales of the moved cloud: exact test of the candidates only (bit-identical to
         # pem_pe_group2 on the moved cloud); needs the side stream's masks
-        self.stream.wait_stream(self.side)
-        ck(L.pem_pe_group2_masked(p(self.pe_xyz[0]), B, N, 1e-8, r1, ns1, p(self.pe_out[0]), r2, ns2,
-                                  p(self.pe_out[1]), p(self.pe_masks), half, st),
-           "pe_group2 moved cloud"); n += 1
+        plan.append(("main_waits_side",))
+        add("pe_group2_masked(moved cloud)", "main", lambda st: L.pem_pe_group2_masked(
+            p(self.pe_xyz[0]), B, N, 1e-8, r1, ns1, p(self.pe_out[0]), r2, ns2, p(self.pe_out[1]), p(self.pe_masks),
+            half, st))
         # 3 transformer blocks x (observed, template): gather 196 rows of the bg-prepended
         # (B,2049,C) features with the FPS indices (reference quirk kept: index 0 fetches the
         # background row, transformer.py:667-671)
         for blk in range(3):
-            ck(L.pem_gather_rows(p(self.feats), p(self.fps_idx), 2 * B, N + 1, C, M, (N + 1) * C, C,
-                                 p(self.sparse_fine[blk]), 0, st), "gather fine"); n += 1
+            add("gather_rows(fine block %d)" % blk, "main", lambda st, blk=blk: L.pem_gather_rows(
+                p(self.feats), p(self.fps_idx), 2 * B, N + 1, C, M, (N + 1) * C, C, p(self.sparse_fine[blk]), 0, st))
         # 4. fine
         if self.fine_mode == "fused":
-            ck(L.pem_fine_fused_ex(p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]),
-                                   p(self.model), B, N, N, C, Nm, self.temp, self.dis_thres,
-                                   self.fine_precision, p(self.R), p(self.t), p(self.score), None, None,
-                                   None, None, p(self.ws), self.ws_bytes, st), "fine_fused"); n += 10
+            add("fine_fused", "main", lambda st: L.pem_fine_fused_ex(
+                p(self.feats[0]), p(self.feats[1]), p(self.pts[0]), p(self.pts[1]), p(self.model), B, N, N, C, Nm,
+                self.temp, self.dis_thres, self.fine_precision, p(self.R), p(self.t), p(self.score), None, None,
+                None, None, p(self.ws), self.ws_bytes, st), 10)
         else:
-            self._enqueue_fine_materialised(); n += 12
-        self.stream.wait_stream(self.side)  # join
-        # 64-byte records
-        ck(L.pem_pack_records(p(self.R), p(self.t), p(self.score), p(self.proposal_id),
-                              p(self.instance_ids), B, p(self.records), st), "pack_records"); n += 1
-        self.kernels_per_step = n
+            add("fine_similarity", "main", lambda st: L.pem_feature_similarity(
+                p(self.feats[0]), p(self.feats[1]), B, N + 1, N + 1, C, self.temp, 1, p(self.atten_f), p(self.ws),
+                self.ws_bytes, st), 2)
+            add("fine_Rt", "main", lambda st: L.pem_fine_Rt(
+                p(self.atten_f), p(self.pts[0]), p(self.pts[1]), p(self.model), B, N, N, Nm, self.dis_thres,
+                p(self.R), p(self.t), p(self.score), None, None, None, None, p(self.ws), self.ws_bytes, st), 10)
+        plan.append(("main_waits_side",))  # join
+        # 64-byte records; at N > 1 GPUs (parallel.RecordGather, mode "peer") the packing kernel also stores them
+        # into every rank's table over NVLink and a wait kernel completes the step, both inside the graph
+        if self.gather is not None:
+            add("gather_poses (pack + peer stores)", "main", self.gather.launch_push)
+            add("gather_poses_wait", "main", self.gather.launch_wait)
+        else:
+            add("pack_records", "main", lambda st: L.pem_pack_records(
+                p(self.R), p(self.t), p(self.score), p(self.proposal_id), p(self.instance_ids), B, p(self.records),
+                st))
+        return plan
 
-    def _enqueue_fine_materialised(self):
-        L, st = self.L, self.stream.cuda_stream
-        B, N, C, Nm = self.B, self.N, self.C, self.Nm
-        ck = _lib.check
-        p = lambda t: t.data_ptr()
-        ck(L.pem_feature_similarity(p(self.feats[0]), p(self.feats[1]), B, N + 1, N + 1, C, self.temp,
-                                    1, p(self.atten_f), p(self.ws), self.ws_bytes, st),
-           "fine similarity")
-        ck(L.pem_fine_Rt(p(self.atten_f), p(self.pts[0]), p(self.pts[1]), p(self.model), B, N, N, Nm,
-                         self.dis_thres, p(self.R), p(self.t), p(self.score), None, None, None, None,
-                         p(self.ws), self.ws_bytes, st), "fine_Rt")
+    def launches(self):
+        """[(name, fn(stream handle) -> status, kernels)] of one step, in order (bench.py's per-kernel table)."""
+        if self.plan is None:
+            self.plan = self._plan()
+        return [(e[1], e[3], e[4]) for e in self.plan if e[0] == "launch"]
+
+    def _enqueue(self):
+        """Walk the plan on self.stream / self.side (also what gets captured)."""
+        if self.plan is None:
+            self.plan = self._plan()
+        handles = {"main": self.stream.cuda_stream, "side": self.side.cuda_stream}
+        n = 0
+        for e in self.plan:
+            if e[0] == "launch":
+                _lib.check(e[3](handles[e[2]]), e[1])
+                n += e[4]
+            elif e[0] == "fork":
+                self.side.wait_stream(self.stream)
+            elif e[0] == "side_waits_main":
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.side.wait_event(ev)
+            elif e[0] == "main_waits_side":
+                self.stream.wait_stream(self.side)
+        self.kernels_per_step = n
 
     def run(self):
         """Enqueue one step on self.stream (no synchronisation)."""
@@ -230,30 +266,57 @@ class PipelinedStage:
     slots, stream and CUDA graph.  submit() enqueues H2D copies of one pinned host batch, the
     stage and the D2H copy of its pose records on the next replica's stream and returns
     immediately, so the copies of batch k+1 overlap the kernels of batch k (the copy engines and
-    the SMs run concurrently); collect() waits for the oldest batch in flight."""
+    the SMs run concurrently); collect() waits for the oldest batch in flight.
 
-    def __init__(self, batch, device, depth=2, **kw):
+    upload: "fp32" -- features cross the link as the fp32 tensors the reference's functions take;
+            "fp16" -- the caller hands over HALF-precision features (what a ViT under autocast produces, and all the
+                      fp16 fine GEMM consumes): half the bytes on the link, widened on the device by the first
+                      kernel of the step.  Parity is then defined against the reference fed the same
+                      (fp16-representable) features."""
+
+    def __init__(self, batch, device, depth=2, upload="fp32", **kw):
+        if upload not in ("fp32", "fp16"):
+            raise ValueError("upload must be 'fp32' or 'fp16'")
+        self.upload = upload
         self.stages = [GeometricStage(batch, device, **kw) for _ in range(depth)]
+        if upload == "fp16":
+            for s in self.stages:
+                s.feats_half = torch.empty(s.feats.shape, dtype=torch.float16, device=s.dev)
         self.host_records = [torch.empty((batch, 16), dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.inflight = []
         self.k = 0
 
-    def load_constants(self, host_batch):
-        for s in self.stages:
-            s.load(host_batch)
+    def upload_note(self):
+        return ("features uploaded as fp16 (the caller's features are half precision), widened on the device"
+                if self.upload == "fp16" else "features uploaded as fp32")
 
     @staticmethod
-    def pin_inputs(host_batch):
+    def as_uploaded(host_batch, upload):
+        """The batch as the device sees it: with upload="fp16" the features (and the background token) are the
+        caller's half-precision values."""
+        if upload != "fp16":
+            return host_batch
+        out = dict(host_batch)
+        for k in ("dense_fm", "dense_fo", "bg"):
+            out[k] = host_batch[k].half().float()
+        return out
+
+    def load_constants(self, host_batch):
+        for s in self.stages:
+            s.load(self.as_uploaded(host_batch, self.upload))
+
+    def pin_inputs(self, host_batch):
         """Pinned host buffers laid out exactly like the device input slots, so that each step's
         upload is four contiguous cudaMemcpyAsync calls: pts (2,B,N,3), feats (2,B,N+1,C) with
-        the background token in row 0, model (B,Nm,3), rand (B,3*P1)."""
+        the background token in row 0 (fp16 when upload="fp16"), model (B,Nm,3), rand (B,3*P1)."""
         pm, fm = host_batch["dense_pm"], host_batch["dense_fm"]
         B, N, C = fm.shape
         pts = torch.stack([pm, host_batch["dense_po"]]).contiguous().pin_memory()
-        feats = torch.empty((2, B, N + 1, C), dtype=torch.float32).pin_memory()
-        feats[:, :, 0] = host_batch["bg"].unsqueeze(0)
-        feats[0, :, 1:] = fm
-        feats[1, :, 1:] = host_batch["dense_fo"]
+        fdt = torch.float16 if self.upload == "fp16" else torch.float32
+        feats = torch.empty((2, B, N + 1, C), dtype=fdt).pin_memory()
+        feats[:, :, 0] = host_batch["bg"].unsqueeze(0).to(fdt)
+        feats[0, :, 1:] = fm.to(fdt)
+        feats[1, :, 1:] = host_batch["dense_fo"].to(fdt)
         return {"pts": pts, "feats": feats, "model": host_batch["model"].contiguous().pin_memory(),
                 "rand": host_batch["rand"].contiguous().pin_memory()}
 
@@ -263,9 +326,11 @@ class PipelinedStage:
         s = self.stages[i]
         if len(self.inflight) == len(self.stages):
             self.collect()
+        if pinned["feats"].dtype != (torch.float16 if self.upload == "fp16" else torch.float32):
+            raise RuntimeError("pinned features do not match upload=%r" % self.upload)
         with torch.cuda.stream(s.stream):
             s.pts.copy_(pinned["pts"], non_blocking=True)
-            s.feats.copy_(pinned["feats"], non_blocking=True)
+            (s.feats_half if self.upload == "fp16" else s.feats).copy_(pinned["feats"], non_blocking=True)
             s.model.copy_(pinned["model"], non_blocking=True)
             s.rand.copy_(pinned["rand"], non_blocking=True)
         s.run()

@@ -84,12 +84,18 @@ def run_stage_cpu(batch, n_sparse=196, n_proposal1=6000, n_proposal2=300, temp=0
     sp, sf, idx_m = sample(pm, fm)
     tp, tf, idx_o = sample(po, fo)
     atten_c = O.feature_similarity(torch.cat([bg, sf], 1), torch.cat([bg, tf], 1), temp)
-    R0s, t0s, pids = [], [], []
+    R0s, t0s, pids, tops, scs, posed, w1s = [], [], [], [], [], [], []
     for s in range(0, B, chunk):  # ~3.5 GB of temporaries per instance in faithful mode
         e = slice(s, s + chunk)
         R0, t0, st = O.coarse_Rt(atten_c[e], sp[e], tp[e], batch["model"][e], n_proposal1,
                                  n_proposal2, batch["rand"][e], faithful=faithful)
         R0s.append(R0); t0s.append(t0); pids.append(st["proposal_id"])
+        # for the parity tests: the scored hypotheses, and which of them are well posed (sigma2/sigma1 of
+        # their 3x3 H above 1e-2; the rest are the degenerate triplets whose rotation LAPACK takes from noise)
+        Htop = torch.gather(st["H"], 1, st["top"].reshape(st["top"].shape[0], -1, 1, 1).expand(-1, -1, 3, 3))
+        sv = torch.linalg.svdvals(Htop.double())
+        tops.append(st["top"]); scs.append(st["scores"]); w1s.append(st["w1"])
+        posed.append(sv[..., 1] / sv[..., 0].clamp_min(1e-30) > 1e-2)
     R0, t0, pid = torch.cat(R0s), torch.cat(t0s), torch.cat(pids)
     p1_ = (pm - t0.unsqueeze(1)) @ R0
     pe = []
@@ -104,5 +110,7 @@ def run_stage_cpu(batch, n_sparse=196, n_proposal1=6000, n_proposal2=300, temp=0
         fine_sparse.append(ops.gather(ff2.transpose(1, 2).contiguous(), idx_o).transpose(1, 2).contiguous())
     atten_f = O.feature_similarity(ff1, ff2, temp)
     R, t, score, _ = O.fine_Rt(atten_f, pm, po, batch["model"])
-    return R, t, score, {"init_R": R0, "init_t": t0, "proposal_id": pid, "idx_m": idx_m,
+    return R, t, score, {"init_R": R0, "init_t": t0, "proposal_id": pid, "coarse_top": torch.cat(tops),
+                         "coarse_scores": torch.cat(scs), "coarse_posed": torch.cat(posed),
+                         "coarse_w1": torch.cat(w1s), "sparse_pm": sp, "idx_m": idx_m,
                          "idx_o": idx_o, "pe": pe, "fine_sparse": fine_sparse, "ops": ops.kind}

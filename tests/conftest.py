@@ -35,3 +35,16 @@ def dev():
 
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def write_report(name, obj):
+    """Measured parity figures of a GPU test run, written to gpurun_out/ (scratch on the GPU box; the
+    ones that are evidence are copied to profiles/ and committed)."""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, name), "w") as f:
+            json.dump(obj, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

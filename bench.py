@@ -362,8 +362,10 @@ def _peaks():
             "fallback (B200_PROFILING.md)"
 
 
-def _timed(stream, fn, iters=10, pre=None, flush=None):
-    """mean ms of fn on `stream`: [flush,] [pre (untimed),] event, fn, event"""
+def _timed(stream, fn, iters=10, pre=None, flush=None, inner=1):
+    """mean ms of fn on `stream`: [flush,] [pre (untimed),] event, fn x inner, event.  inner > 1: back-to-back
+    launches of an idempotent kernel inside one event pair (an event pair around ONE short launch reads 5-8 us
+    whatever the kernel does)."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = 0.0
     with torch.cuda.stream(stream):
@@ -375,11 +377,12 @@ def _timed(stream, fn, iters=10, pre=None, flush=None):
             if pre is not None:
                 pre()
             e0.record(stream)
-            fn()
+            for _ in range(inner):
+                fn()
             e1.record(stream)
             stream.synchronize()
             ms += e0.elapsed_time(e1)
-    return ms / iters
+    return ms / (iters * inner)
 
 
 def fp32_peak(pkg, stage, dev):
@@ -476,8 +479,9 @@ def dominant_kernel_roofline(pkg, stage, flush):
 
 # ------------------------------------------------------------------------------- per-kernel table
 def kernel_table(pkg, stage, fp32, roof):
-    """Every launch of the step timed ALONE with CUDA events on the stage's stream (inputs as the step left
-    them, L2-warm like inside the step), with the bound and algorithmic work of SURVEY 8d.  The fused fine
+    """Every launch of the step timed ALONE with CUDA events on the stage's stream (10 back-to-back launches per
+    event pair, inputs as the step left them, L2-warm like inside the step), with the bound and algorithmic work
+    of SURVEY 8d.  The fused fine
     call is split into its kernels through the pass hook.  The step itself is shorter than the sum: the
     side-stream kernels overlap the coarse chain."""
     B, N, M, C, Nm, P1, P2 = stage.B, stage.N, stage.M, stage.C, stage.Nm, stage.P1, stage.P2
@@ -502,7 +506,7 @@ def kernel_table(pkg, stage, fp32, roof):
     for name, fn, k in stage.launches():
         if name == "fine_fused":
             continue
-        us = 1e3 * _timed(stage.stream, lambda fn=fn, name=name: pkg._lib.check(fn(st), name), iters=20)
+        us = 1e3 * _timed(stage.stream, lambda fn=fn, name=name: pkg._lib.check(fn(st), name), iters=5, inner=10)
         if name.startswith("fps"):
             row(name, us, "fp32 (unfused, latency: M-1 dependent steps)", 2 * B * (M - 1) * N * 10.0, "Top/s", unf,
                 "streaming-equivalent %.0f GB/s" % (2 * B * (M - 1) * N * 20.0 / (us * 1e-6) / 1e9))

@@ -314,20 +314,61 @@ static int launch_fps_cluster(const float *xyz, int B, int N, int M, int skip, i
 // ------------------------------------------------------------------------------------
 // gather / group
 // ------------------------------------------------------------------------------------
-// One warp per (b,c) channel row; lanes sweep the M samples (coalesced idx reads and
-// output writes, random 4-byte reads inside one N-float row that stays in L1/L2).
+// gather_points: the index list of a cloud is shared by its C channel rows, and every gathered float costs a
+// 32-byte sector of the (b,c) row, so the kernel is bound by memory-level parallelism, not bytes.  A thread owns
+// four consecutive samples (index quad read once, as int4 when aligned) and walks kGaCh channel rows with all
+// 4 x kGaUnroll gathers of an unrolled step in flight before the first 16-byte store.
+constexpr int kGaCh = 16;      // channel rows per CTA (grid.y = ceil(C / kGaCh))
+constexpr int kGaUnroll = 4;   // rows per unrolled step: 16 independent gathers per thread
 __global__ void __launch_bounds__(256)
-gather_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int BC, int C, int N,
-              int M, float *__restrict__ out) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (row >= BC) return;
-    const int b = row / C;
-    const float *src = feat + (size_t)row * N;
-    const int32_t *ib = idx + (size_t)b * M;
-    float *dst = out + (size_t)row * M;
-    for (int j = lane_id(); j < M; j += 32) {
-        const int a = __ldg(ib + j);
-        dst[j] = (a >= 0 && a < N) ? __ldg(src + a) : 0.0f;
+gather_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int C, int N, int M,
+              float *__restrict__ out, int vec) {
+    const int b = blockIdx.z, c0 = blockIdx.y * kGaCh, c1 = min(C, c0 + kGaCh);
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= M) return;
+    const int32_t *ib = idx + (size_t)b * M + j0;
+    int a[4];
+    if (vec) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(ib));
+        a[0] = q.x, a[1] = q.y, a[2] = q.z, a[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = j0 + k < M ? __ldg(ib + k) : -1;
+    }
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ok[k] = a[k] >= 0 && a[k] < N;   // out-of-range index -> 0.0f (sampling.cpp:23-44)
+        if (!ok[k]) a[k] = 0;
+    }
+    const float *src = feat + ((size_t)b * C + c0) * N;
+    float *dst = out + ((size_t)b * C + c0) * M + j0;
+    int c = c0;
+    for (; c + kGaUnroll <= c1; c += kGaUnroll, src += (size_t)kGaUnroll * N, dst += (size_t)kGaUnroll * M) {
+        float v[kGaUnroll][4];
+#pragma unroll
+        for (int u = 0; u < kGaUnroll; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = __ldg(src + (size_t)u * N + a[k]);
+#pragma unroll
+        for (int u = 0; u < kGaUnroll; ++u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (!ok[k]) v[u][k] = 0.f;
+            float *d = dst + (size_t)u * M;
+            if (vec) {
+                __stcs(reinterpret_cast<float4 *>(d), make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (j0 + k < M) d[k] = v[u][k];
+            }
+        }
+    }
+    for (; c < c1; ++c, src += N, dst += M) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (j0 + k < M) dst[k] = ok[k] ? __ldg(src + a[k]) : 0.f;
     }
 }
 
@@ -354,6 +395,58 @@ gather_rows_kernel(const float *__restrict__ feat, const int32_t *__restrict__ i
 }
 
 // out[b,c,e] = feat[b,c,idx[b,e]] over the flattened e = j*ns + k.
+// Every gathered float would cost a 32-byte sector on the L2 -> SM path (8x the useful bytes; at C = 256 that
+// path, not HBM, set the pace), so the R channel rows a CTA owns are first copied into shared memory (coalesced),
+// the gathers become 4-byte LDS, and the index quad a thread reads (int4) serves all R rows; outputs leave as
+// streaming 16-byte stores.  grid = (chunks of the E outputs, groups of R channels, B).
+template <int R>
+__global__ void __launch_bounds__(512)
+group_smem_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int C, int N,
+                  long long E, long long chunk, float *__restrict__ out, int vec) {
+    extern __shared__ float rows[];   // R x N
+    const int b = blockIdx.z, c0 = blockIdx.y * R;
+    const int nr = min(R, C - c0);
+    const float *src = feat + ((size_t)b * C + c0) * N;
+    for (int i = threadIdx.x; i < nr * N; i += blockDim.x) rows[i] = __ldg(src + i);
+    __syncthreads();
+    const long long e_lo = (long long)blockIdx.x * chunk, e_hi = min(E, e_lo + chunk);
+    const int32_t *ib = idx + (size_t)b * E;
+    float *dst = out + ((size_t)b * C + c0) * E;
+    for (long long e = e_lo + (long long)threadIdx.x * 4; e < e_hi; e += (long long)blockDim.x * 4) {
+        int a[4];
+        if (vec) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(ib + e));
+            a[0] = q.x, a[1] = q.y, a[2] = q.z, a[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = e + k < e_hi ? __ldg(ib + e + k) : -1;
+        }
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ok[k] = a[k] >= 0 && a[k] < N;   // invalid index -> 0.0f (group_points.cpp:20-45)
+            if (!ok[k]) a[k] = 0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < nr) {
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = ok[k] ? rows[r * N + a[k]] : 0.f;
+                float *d = dst + (size_t)r * E + e;
+                if (vec) {
+                    __stcs(reinterpret_cast<float4 *>(d), make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (e + k < e_hi) d[k] = v[k];
+                }
+            }
+        }
+    }
+}
+
+// rows too long for shared memory: direct gathers
 __global__ void __launch_bounds__(256)
 group_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int C, int N,
              long long E, float *__restrict__ out) {
@@ -366,6 +459,21 @@ group_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, in
         const int a = __ldg(ib + e);
         dst[e] = (a >= 0 && a < N) ? __ldg(src + a) : 0.0f;
     }
+}
+
+template <int R>
+static int launch_group_smem(const float *feat, const int32_t *idx, int B, int C, int N, long long E, float *out,
+                             cudaStream_t st) {
+    const size_t smem = (size_t)R * N * sizeof(float);
+    static PemSmemCache cached(48 * 1024);
+    if (int rc = pem_ensure_dyn_smem(group_smem_kernel<R>, smem, &cached)) return rc;
+    // outputs per CTA: at least 16 x the staged bytes (staging stays a small share), whole E when rows are long
+    long long chunk = max((long long)R * N * 16 / R, 16384LL);
+    chunk = min(E, (chunk + 2047) / 2048 * 2048);
+    const int gx = (int)((E + chunk - 1) / chunk);
+    const int vec = (E % 4 == 0) && (chunk % 4 == 0) && ((uintptr_t)idx % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    group_smem_kernel<R><<<dim3(gx, (C + R - 1) / R, B), 512, smem, st>>>(feat, idx, C, N, E, chunk, out, vec);
+    return pem_launch_status();
 }
 
 // ------------------------------------------------------------------------------------
@@ -811,8 +919,11 @@ extern "C" int pem_gather(const float *feat, const int32_t *idx, int B, int C, i
     PEM_REQUIRE_PTR(idx);
     PEM_REQUIRE_PTR(out);
     PEM_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0, PEM_E_SHAPE);
-    const int rows = B * C;
-    gather_kernel<<<(rows + 7) / 8, 256, 0, pem_cu_stream(stream)>>>(feat, idx, rows, C, N, M, out);
+    PEM_REQUIRE(B <= 65535 && (C + kGaCh - 1) / kGaCh <= 65535, PEM_E_SHAPE);
+    const int quads = (M + 3) / 4, threads = quads >= 256 ? 256 : (quads + 31) / 32 * 32;
+    const int vec = (M % 4 == 0) && ((uintptr_t)idx % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    gather_kernel<<<dim3((quads + threads - 1) / threads, (C + kGaCh - 1) / kGaCh, B), threads, 0,
+                    pem_cu_stream(stream)>>>(feat, idx, C, N, M, out, vec);
     return pem_launch_status();
 }
 
@@ -842,8 +953,13 @@ extern "C" int pem_group(const float *feat, const int32_t *idx, int B, int C, in
     PEM_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && ns > 0 && C <= 65535 && B <= 65535,
                 PEM_E_SHAPE);
     const long long E = (long long)M * ns;
+    cudaStream_t st = pem_cu_stream(stream);
+    const size_t row = (size_t)N * sizeof(float);
+    if (row * 4 <= 64 * 1024 && C >= 4) return launch_group_smem<4>(feat, idx, B, C, N, E, out, st);
+    if (row * 3 <= 200 * 1024 && C >= 3) return launch_group_smem<3>(feat, idx, B, C, N, E, out, st);
+    if (row <= 200 * 1024) return launch_group_smem<1>(feat, idx, B, C, N, E, out, st);
     const int gx = (int)((E + 1023) / 1024);  // 4 elements per thread
-    group_kernel<<<dim3(gx, C, B), 256, 0, pem_cu_stream(stream)>>>(feat, idx, C, N, E, out);
+    group_kernel<<<dim3(gx, C, B), 256, 0, st>>>(feat, idx, C, N, E, out);
     return pem_launch_status();
 }
 

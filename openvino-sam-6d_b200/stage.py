@@ -59,6 +59,7 @@ class GeometricStage:
         self.fps_idx = e((2, B, M), **i32)
         self.sparse_pts = e((2, B, M, 3), **f32)
         self.sparse_feats = e((2, B, M + 1, C), **f32)  # row 0 = background token
+        self.row0 = torch.zeros((2 * B, 1), **i32)       # "row 0" index list: copies the token per step
         # step 2
         self.atten_c = e((B, M + 1, M + 1), **f32)
         self.w1c, self.w2c = e((B, M), **f32), e((B, M), **f32)
@@ -115,7 +116,7 @@ class GeometricStage:
     def _plan(self):
         """The fixed launch sequence of one step as a list of entries, built once (every buffer is
         preallocated, so the pointers are fixed): ("launch", name, stream tag, fn(stream handle) -> status,
-        kernels launched) or ("fork" | "side_waits_main" | "main_waits_side",).  _enqueue() walks it (that is
+        kernels launched) or ("fork" | "side_waits_main" | "main_waits_side" | "side_mark" | "main_waits_mark",).  _enqueue() walks it (that is
         also what gets captured into the CUDA graph); bench.py walks the "launch" entries to time every kernel
         alone on one stream."""
         L = self.L
@@ -137,6 +138,11 @@ class GeometricStage:
         #    only re-tests the candidates exactly on the moved points;
         #  * the PE grouping of the cloud that is not moved.
         plan.append(("fork",))
+        # the background token of the coarse features = row 0 of this step's dense features (the caller may hand
+        # over a different token with every batch): one strided row copy, off the critical chain
+        add("gather_rows(bg token)", "side", lambda st: L.pem_gather_rows(
+            p(self.feats), p(self.row0), 2 * B, N + 1, C, 1, (N + 1) * C, C, p(self.sparse_feats), (M + 1) * C, st))
+        plan.append(("side_mark",))  # the coarse similarity waits for exactly this much of the side stream
         # (grid capped so that the filter's CTAs -- one whole SM each -- are resident TOGETHER with the
         # 2B CTAs of the FPS kernel instead of waiting for them in a second round)
         add("pe_masks", "side", lambda st: L.pem_pe_masks(
@@ -151,6 +157,7 @@ class GeometricStage:
             p(self.feats) + 4 * C, p(self.fps_idx), 2 * B, N, C, M, (N + 1) * C, C, p(self.sparse_feats) + 4 * C,
             (M + 1) * C, st))
         # 2. coarse
+        plan.append(("main_waits_mark",))
         add("coarse_similarity", "main", lambda st: L.pem_feature_similarity(
             p(self.sparse_feats[0]), p(self.sparse_feats[1]), B, M + 1, M + 1, C, self.temp, 1, p(self.atten_c),
             p(self.ws), self.ws_bytes, st), 2)
@@ -239,6 +246,11 @@ class GeometricStage:
                 self.side.wait_event(ev)
             elif e[0] == "main_waits_side":
                 self.stream.wait_stream(self.side)
+            elif e[0] == "side_mark":
+                mark = torch.cuda.Event()
+                mark.record(self.side)
+            elif e[0] == "main_waits_mark":
+                self.stream.wait_event(mark)
         self.kernels_per_step = n
 
     def run(self):

@@ -57,10 +57,13 @@ def cuda_so_path():
 
 
 def build_cuda(verbose=False):
-    """The reference's CUDA build of the same extension (setup.py:25-43: all .cpp + .cu,
-    -DCUDA_AVAILABLE=1 and its nvcc defines) compiled for sm_100 -- the same-box GPU baseline the
-    pointnet2 kernels are timed beside and, where the tie / skip rules allow, checked
-    against.  Output: oracle/_ref_cuda/ (git-ignored, travels to the GPU box)."""
+    """The reference's CUDA kernels (the four *_gpu.cu files of _ext_src/src, compiled UNMODIFIED from where
+    they lie, with the nvcc defines of setup.py:36-42) for sm_100 -- the same-box GPU baseline the pointnet2
+    kernels are timed beside and, where the tie / skip rules allow, checked against.  The host
+    side is oracle/ref_cuda_shim.cpp, not the reference's .cpp files: in the reference's own CUDA build those
+    re-define CUDA_AVAILABLE to 0 under g++ (utils.h:9-14) and raise "CUDA not available" for every CUDA
+    tensor, so its kernels cannot be reached through its bindings.  Output: oracle/_ref_cuda/ (git-ignored,
+    travels to the GPU box)."""
     if os.path.exists(cuda_so_path()):
         return cuda_so_path()
     if not os.path.isdir(EXT_SRC):
@@ -70,9 +73,9 @@ def build_cuda(verbose=False):
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     load(
         name=CUDA_NAME,
-        sources=sorted(glob.glob(os.path.join(EXT_SRC, "src", "*.cpp")) + glob.glob(os.path.join(EXT_SRC, "src", "*.cu"))),
+        sources=[os.path.join(HERE, "ref_cuda_shim.cpp")] + sorted(glob.glob(os.path.join(EXT_SRC, "src", "*.cu"))),
         extra_include_paths=[os.path.join(EXT_SRC, "include")],
-        extra_cflags=["-O3", "-DCUDA_AVAILABLE=1"],
+        extra_cflags=["-O3"],
         extra_cuda_cflags=["-O3", "-DCUDA_HAS_FP16=1", "-D__CUDA_NO_HALF_OPERATORS__",
                            "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__",
                            "-DCUDA_AVAILABLE=1"],

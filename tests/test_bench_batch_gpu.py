@@ -110,7 +110,7 @@ def test_bench_batch_through_stage_and_pipeline(pkg, oracle, dev, cpu_ref, fine_
         stats["winner_differs_fine_pose_ok"] += int((~same).sum())   # _check_group asserted the fine pose on all
     # ---- the host-facing path: three distinct pinned batches in flight over two replicas -------------
     pipe = pkg.stage.PipelinedStage(GROUP, dev, depth=2, fine_precision=fine_precision)
-    pins = [pkg.stage.PipelinedStage.pin_inputs(ref[0]) for ref in cpu_ref[:3]]
+    pins = [pipe.pin_inputs(ref[0]) for ref in cpu_ref[:3]]
     got = []
     for rnd in range(2):                      # second round: every replica re-used with different inputs
         for gi in range(3):

@@ -56,7 +56,8 @@ def test_reference_pointnet2_utils_runs_on_the_dropin(pkg, oracle, dev, ref):
     xyz = b["dense_po"].to(dev)
     feat = b["dense_fo"].transpose(1, 2).contiguous().to(dev)
     # FurthestPointSampling / GatherOperation through the reference's autograd Functions
-    idx = pu.furthest_point_sample(xyz, 196)
+    # (the reference passes the count as the LENGTH of a tensor: utils/model_utils.py:75, pointnet2_utils.py:77)
+    idx = pu.furthest_point_sample(xyz, torch.ones(196, dtype=torch.int32))
     want = oracle.fps(b["dense_po"].numpy(), 196)
     assert np.array_equal(idx.cpu().numpy(), want)
     g = pu.gather_operation(feat, idx)
@@ -70,7 +71,7 @@ def test_reference_pointnet2_utils_runs_on_the_dropin(pkg, oracle, dev, ref):
         assert np.array_equal(out.cpu().numpy(), wq)
     # the reference's errors for bad tensors still surface as RuntimeError (utils.h:20-35)
     with pytest.raises(RuntimeError):
-        pu.furthest_point_sample(xyz.double(), 8)
+        pu.furthest_point_sample(xyz.double(), torch.ones(8, dtype=torch.int32))
 
 
 def test_reference_sample_pts_feats_unpatched_on_config1(pkg, dev, ref):

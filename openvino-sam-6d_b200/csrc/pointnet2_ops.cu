@@ -461,18 +461,22 @@ group_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, in
     }
 }
 
+// returns PEM_E_UNSUPPORTED when staging would not pay (few outputs per staged row): the caller gathers directly
 template <int R>
 static int launch_group_smem(const float *feat, const int32_t *idx, int B, int C, int N, long long E, float *out,
                              cudaStream_t st) {
     const size_t smem = (size_t)R * N * sizeof(float);
+    const int groups = (C + R - 1) / R;
+    // enough CTAs to fill the chip four times over, in whole 2048-output blocks
+    long long gx = max(1LL, (4LL * pem_num_sms() + (long long)B * groups - 1) / ((long long)B * groups));
+    long long chunk = ((E + gx - 1) / gx + 2047) / 2048 * 2048;
+    chunk = min(E, chunk);
+    if (chunk < 2LL * N) return PEM_E_UNSUPPORTED;  // a staged row must serve at least two outputs per element
+    gx = (E + chunk - 1) / chunk;
     static PemSmemCache cached(48 * 1024);
     if (int rc = pem_ensure_dyn_smem(group_smem_kernel<R>, smem, &cached)) return rc;
-    // outputs per CTA: at least 16 x the staged bytes (staging stays a small share), whole E when rows are long
-    long long chunk = max((long long)R * N * 16 / R, 16384LL);
-    chunk = min(E, (chunk + 2047) / 2048 * 2048);
-    const int gx = (int)((E + chunk - 1) / chunk);
     const int vec = (E % 4 == 0) && (chunk % 4 == 0) && ((uintptr_t)idx % 16 == 0) && ((uintptr_t)out % 16 == 0);
-    group_smem_kernel<R><<<dim3(gx, (C + R - 1) / R, B), 512, smem, st>>>(feat, idx, C, N, E, chunk, out, vec);
+    group_smem_kernel<R><<<dim3((unsigned)gx, groups, B), 512, smem, st>>>(feat, idx, C, N, E, chunk, out, vec);
     return pem_launch_status();
 }
 
@@ -954,10 +958,14 @@ extern "C" int pem_group(const float *feat, const int32_t *idx, int B, int C, in
                 PEM_E_SHAPE);
     const long long E = (long long)M * ns;
     cudaStream_t st = pem_cu_stream(stream);
+    // rows staged in shared memory, three CTAs per SM (<= 72 KB each) so that one CTA's staging hides under the
+    // others' gathers; as many rows per CTA as fit (the index quads are read once per CTA)
     const size_t row = (size_t)N * sizeof(float);
-    if (row * 4 <= 64 * 1024 && C >= 4) return launch_group_smem<4>(feat, idx, B, C, N, E, out, st);
-    if (row * 3 <= 200 * 1024 && C >= 3) return launch_group_smem<3>(feat, idx, B, C, N, E, out, st);
-    if (row <= 200 * 1024) return launch_group_smem<1>(feat, idx, B, C, N, E, out, st);
+    int rc = PEM_E_UNSUPPORTED;
+    if (row * 4 <= 72 * 1024 && C >= 4) rc = launch_group_smem<4>(feat, idx, B, C, N, E, out, st);
+    else if (row * 3 <= 72 * 1024 && C >= 3) rc = launch_group_smem<3>(feat, idx, B, C, N, E, out, st);
+    else if (row <= 200 * 1024) rc = launch_group_smem<1>(feat, idx, B, C, N, E, out, st);
+    if (rc != PEM_E_UNSUPPORTED) return rc;
     const int gx = (int)((E + 1023) / 1024);  // 4 elements per thread
     group_kernel<<<dim3(gx, C, B), 256, 0, st>>>(feat, idx, C, N, E, out);
     return pem_launch_status();

@@ -15,22 +15,31 @@
 //   A  row: qh.x qh.y qh.z | qh.x qh.y qh.z | ql.x ql.y ql.z | ql.x ql.y ql.z | 1    1    0 0
 //   Bm row: -2mh.x ..      | -2ml.x ..      | -2mh.x ..      | -2ml.x ..      | s_hi s_lo 0 0     s = |m|^2
 //
-// One persistent CTA per (instance, slice of its hypotheses):
+// One persistent CTA per (instance, slice of its hypotheses), warp-specialised:
 //   * the model operand (1024 rows x 64 used bytes, SWIZZLE_128B K-major rows) is built once in
 //     shared memory; rows of all hypotheses of the slice are packed back to back into 128-row
 //     tiles, so no tensor work is wasted on padding 151 points to 256;
-//   * warps 2-9 ("row threads", two per TMEM lane = tile row, one per half of the columns)
-//     transform their point, write their half of the A row (generic stores + proxy fence), and
-//     later reduce their lane of the accumulator with 3-input minima straight out of TMEM
-//     (PARTS = 4 puts four threads on a row; measured 6 % slower, kept as a development knob);
-//   * warp 1 issues M128 x N256 x K8 MMAs: 2 per 256-model-point chunk, accumulator chunks double
-//     buffered in the 512 TMEM columns; A tiles double buffered so tile t+1 is built while tile t
-//     is reduced;
-//   * distances land in shared memory, and each hypothesis is summed in a fixed order.
-// Bound: every pair value crosses the TMEM read port once.  Measured here: 128 KB per chunk per SM in
-// ~980 cycles = 128 B/clk/SM (32 B/clk per scheduler quadrant), whatever the split of the columns over
-// warps (2 or 4 per row) and whether or not a warp keeps a second load in flight -- the port, not issue
-// or latency, sets the pace (ncu: issue slots 37 % busy, ALU pipe 43 %, tensor pipe 30 %).
+//   * warp 0 issues M128 x N128 x K8 MMAs, 2 per 128-model-point chunk, into FOUR accumulator buffers
+//     (all 512 TMEM columns), i.e. it runs up to three chunks ahead of the reduction;
+//   * warps 1-3 ("builders", 96 threads for the 128 tile rows) transform their points and write the A rows
+//     (generic stores + proxy fence) of the next tile, double buffered, and leave |q|^2 in a small ring;
+//   * warps 4-11 ("reducers", two per TMEM lane quadrant, each on 64 of a chunk's 128 columns) fold
+//     their lane of every accumulator chunk with 3-input minima; the tcgen05.ld of chunk g+1 is issued
+//     BEFORE chunk g is folded and the buffer is handed back as soon as its load has landed, so TMEM
+//     reads, minima and MMAs overlap;
+//   * per-part row minima (+ |q|^2) land in shared memory, and each hypothesis is summed in a fixed order.
+// What bounds it (tools/tmem_ld_rate.cu, tools/minmax_rate.cu on this GPU): tcgen05.ld 32x32b delivers
+// ~950 B/clk/SM with two warps per quadrant, so the accumulator read is NOT the limit (the round-1 form
+// of this kernel -- load, wait, fold in lock step, two buffers -- sat at 128 B/clk/SM and was misread as
+// port bound); FMNMX3 issues at 0.4 per clock per scheduler = 102 folded values per clock per SM, i.e.
+// ~1290 clocks per 128 x 1024 tile, next to 1024 clocks of MMAs.  What the round-1 form and a first
+// warp-specialised cut really spent their time on was the hand-shake itself: ~50 dependent integer
+// instructions per chunk (barrier slot and parity from running counters) at ~6 clocks each with two warps
+// per scheduler (ncu source page; with MMAs, loads and minima all switched off the kernel still took 3/4
+// of its time).  Hence the FIXED form: when every model block is exactly eight chunks (Nm = 1024, 2048,
+// ...) a tile's chunk loop is unrolled with every barrier slot, parity and TMEM column a compile-time
+// constant (8 uses of 4 buffers per tile = an even number of phases per buffer and tile).  Other shapes take the
+// generic loop.
 // More than 1024 model points are taken in blocks of 1024: the tiles of a batch of hypotheses run
 // once per block and the running minima wait in shared memory.  The SIMT kernel (coarse.cu) remains
 // for shapes this one does not take (more than 4096 model points or 256 query points).
@@ -40,50 +49,69 @@ namespace pem {
 namespace tc {
 
 constexpr int kSRows = 128;          // rows per tile = TMEM lanes
-constexpr int kSChunk = 256;         // model points per accumulator buffer
+constexpr int kSChunk = 128;         // model points per accumulator buffer
+constexpr int kSBufs = 4;            // accumulator buffers (4 x 128 = all 512 TMEM columns)
 constexpr int kSMaxNm = 1024;        // model points held in shared memory (128 B per row)
+constexpr int kSFixedChunks = kSMaxNm / kSChunk;  // chunks per tile of the unrolled form
 constexpr int kSMaxN1 = 256;         // query points per instance
-constexpr int kSBatchHyps = 40;      // hypotheses whose distances fit in shared memory at once
+constexpr int kSBatchHyps = 40;      // hypotheses per batch (their R | t staged in shared memory)
+constexpr int kSRowCap = 6144;       // rows (hypothesis, point) of a batch whose minima fit in shared memory
+constexpr int kSBuilders = 96, kSReducers = 256, kSThreads = 32 + kSBuilders + kSReducers;  // 12 warps: 168 registers
+constexpr int kSCols = kSChunk / 2;  // columns per reducer thread and chunk
 constexpr uint32_t kSIdesc = make_idesc_tf32(kSRows, kSChunk);
 
-// PARTS = row threads per tile row, each reducing 256 / PARTS columns of every chunk (2 or 4)
-template <int PARTS>
 struct ScoreSmem {
     uint8_t b[kSMaxNm * 128];        // model operand
     uint8_t a[2][kSRows * 128];      // query tiles
-    float dis[kSBatchHyps * kSMaxN1];
-    float comb[2][PARTS - 1][kSRows];  // best of column parts 1.., handed to the part-0 thread of the row
+    float dmin[2][kSRowCap];         // per column half: running minimum (+ |q|^2 after the last model block)
+    float q2[8][kSRows];             // |q|^2 of the rows of the tiles in flight
     float px[kSMaxN1], py[kSMaxN1], pz[kSMaxN1];  // compacted foreground points
     float Rt[kSBatchHyps][12];       // R (row-major) | t of the hypotheses of the batch
     int nfg;
-    uint64_t a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
+    uint64_t a_full[2], a_empty[2], tmem_full[kSBufs], tmem_empty[kSBufs];
     uint32_t tmem_base;
 };
 
-template <int N>
-__device__ __forceinline__ void row_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void builder_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kSBuilders) : "memory"); }
+__device__ __forceinline__ void reducer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kSReducers) : "memory"); }
+
+// 64 accumulator values into 8 running minima (8 independent chains of 3-input minima)
+__device__ __forceinline__ void fold64(const uint32_t (&r)[64], float (&m)[8]) {
+#pragma unroll
+    for (int q = 0; q < 64; q += 16) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            m[k] = fminf(fminf(m[k], __uint_as_float(r[q + 2 * k])), __uint_as_float(r[q + 2 * k + 1]));
+    }
+}
+__device__ __forceinline__ float min8(const float (&m)[8]) {
+    return fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
 }
 
-template <int PARTS>
-__global__ void __launch_bounds__(64 + 128 * PARTS, 1)
+// FIXED: every model block has exactly kSFixedChunks chunks (Nm a multiple of 1024 after padding the last
+// chunk: 896 < Nm - 1024 k <= 1024 for every block), so chunk_seq == 8 * tile_seq throughout and the
+// barrier slot (c & 3) and parity (c >> 2) of chunk c of a tile are compile-time constants.
+template <bool FIXED>
+__global__ void __launch_bounds__(kSThreads, 1)
 score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const int32_t *__restrict__ sel,
                 int P, int H, const float *__restrict__ pts1, const float *__restrict__ w1, int N1,
                 const float *__restrict__ model, int Nm, int cpi, float *__restrict__ scores) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int kSRowThreads = 128 * PARTS, kSThreads = 64 + kSRowThreads, kSCols = kSChunk / PARTS;
-    ScoreSmem<PARTS> &sm = *reinterpret_cast<ScoreSmem<PARTS> *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id(), tid = threadIdx.x;
     const int b = blockIdx.x / cpi, slice = blockIdx.x - b * cpi;
     const int hpc = (H + cpi - 1) / cpi;                       // hypotheses per CTA
     const int h_begin = slice * hpc, h_end = min(H, h_begin + hpc);
+    const bool is_mma = warp == 0, is_builder = warp >= 1 && warp <= 3, is_reducer = warp >= 4;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&sm.a_full[i]), kSRowThreads);
+            mbar_init(smem_u32(&sm.a_full[i]), kSBuilders);
             mbar_init(smem_u32(&sm.a_empty[i]), 1);
+        }
+        for (int i = 0; i < kSBufs; ++i) {
             mbar_init(smem_u32(&sm.tmem_full[i]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[i]), kSRowThreads / 32);
+            mbar_init(smem_u32(&sm.tmem_empty[i]), kSReducers / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -119,7 +147,7 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
     const int nfg = sm.nfg;
     const int n_blocks = (Nm + kSMaxNm - 1) / kSMaxNm;  // model blocks of <= 1024 points
 
-    // the model operand: block `mblk` of the model points as B rows
+    // the model operand: block `mblk` of the model points as B rows (all threads)
     auto build_model = [&](int mblk) {
         const float *mb = model + (size_t)b * Nm * 3;
         const int m_lo = mblk * kSMaxNm, cnt = min(kSMaxNm, Nm - m_lo);
@@ -146,35 +174,40 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
             *reinterpret_cast<float4 *>(sm.b + sw128_offset(m, 3)) = c3;
         }
         fence_proxy_async_smem();
-        return padded / kSChunk;
     };
 
     if (nfg > 0 && h_begin < h_end) {
         // Every warp walks the same (batch of hypotheses, model block) sequence; with more than 1024
         // model points the tiles of a batch are run once per model block and the running minimum of
-        // each row waits in `dis` in between.  Barrier phases (tile_seq, chunk_seq) run on throughout.
+        // each row waits in `dmin` in between.  Barrier phases (tile_seq, chunk_seq) run on throughout.
         uint32_t tile_seq = 0, chunk_seq = 0;
         int loaded = -1;  // model block currently in shared memory
-        for (int hb = h_begin; hb < h_end; hb += kSBatchHyps) {
-            const int nb = min(h_end, hb + kSBatchHyps) - hb, rows = nb * nfg;
+        const int batch = max(1, min(kSBatchHyps, kSRowCap / nfg));
+        const uint32_t full0 = smem_u32(&sm.tmem_full[0]), empty0 = smem_u32(&sm.tmem_empty[0]);
+        for (int hb = h_begin; hb < h_end; hb += batch) {
+            const int nb = min(h_end, hb + batch) - hb, rows = nb * nfg;
             const int n_tiles = (rows + kSRows - 1) / kSRows;
-            if (warp >= 2)
-                for (int k = tid - 64; k < nb * 12; k += kSRowThreads) {  // stage R | t of the batch
+            if (is_builder) {
+                builder_barrier();  // every builder is done with the previous batch's R | t
+                for (int k = tid - 32; k < nb * 12; k += kSBuilders) {  // stage R | t of the batch
                     const int hh = k / 12, e = k - hh * 12, h = hb + hh;
                     const size_t src = (size_t)b * P + (sel ? __ldg(sel + (size_t)b * H + h) : h);
                     sm.Rt[hh][e] = e < 9 ? __ldg(R + src * 9 + e) : __ldg(t + src * 3 + (e - 9));
                 }
+                builder_barrier();
+            }
             for (int mblk = 0; mblk < n_blocks; ++mblk) {
-                int n_chunks = (min(kSMaxNm, Nm - mblk * kSMaxNm) + kSChunk - 1) / kSChunk;
+                const int n_chunks = FIXED ? kSFixedChunks
+                                           : (min(kSMaxNm, Nm - mblk * kSMaxNm) + kSChunk - 1) / kSChunk;
                 if (loaded != mblk) {  // (every MMA that read the previous block has retired: its
                     __syncthreads();   //  accumulators were all consumed before this barrier)
-                    n_chunks = build_model(mblk);
+                    build_model(mblk);
                     loaded = mblk;
+                    __syncthreads();
                 }
-                __syncthreads();
                 const bool first = mblk == 0, last = mblk == n_blocks - 1;
 
-                if (warp == 1) {
+                if (is_mma) {
                     // ================================ MMA issuer ==================================
                     const uint64_t b0 = umma_desc_sw128(smem_u32(sm.b));
                     for (int tl = 0; tl < n_tiles; ++tl, ++tile_seq) {
@@ -182,126 +215,179 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                         mbar_wait(smem_u32(&sm.a_full[buf]), (tile_seq >> 1) & 1);
                         tc_fence_after();
                         const uint64_t ad = umma_desc_sw128(smem_u32(sm.a[buf]));
-                        for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
-                            const int cb = chunk_seq & 1;
-                            mbar_wait(smem_u32(&sm.tmem_empty[cb]), ((chunk_seq >> 1) & 1) ^ 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint32_t d = tmem_base + (uint32_t)(cb * kSChunk);
-                                const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
-                                tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
-                                tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
-                                tc_commit(smem_u32(&sm.tmem_full[cb]));
-                                if (c == n_chunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                        if constexpr (FIXED) {
+#pragma unroll
+                            for (int c = 0; c < kSFixedChunks; ++c) {
+                                mbar_wait(empty0 + 8u * (uint32_t)(c & 3), (uint32_t)(((c >> 2) & 1) ^ 1));
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint32_t d = tmem_base + (uint32_t)((c & 3) * kSChunk);
+                                    const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
+                                    tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
+                                    tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
+                                    tc_commit(full0 + 8u * (uint32_t)(c & 3));
+                                    if (c == kSFixedChunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                                }
+                                __syncwarp();
                             }
-                            __syncwarp();
+                        } else {
+                            for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                                const int cb = chunk_seq & (kSBufs - 1);
+                                mbar_wait(smem_u32(&sm.tmem_empty[cb]), ((chunk_seq / kSBufs) & 1) ^ 1);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint32_t d = tmem_base + (uint32_t)(cb * kSChunk);
+                                    const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
+                                    tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
+                                    tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
+                                    tc_commit(smem_u32(&sm.tmem_full[cb]));
+                                    if (c == n_chunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                                }
+                                __syncwarp();
+                            }
                         }
                     }
-                } else if (warp >= 2) {
-                    // ================================ row threads =================================
-                    const int quad = warp & 3, part = (warp - 2) >> 2;
-                    const int et = quad * 32 + lane;  // tile row = TMEM lane
-
-                    // transform the point of tile row `et` and write this thread's share of the A row
-                    auto build = [&](int r0, uint32_t seq) {
-                        const int buf = seq & 1;
-                        mbar_wait(smem_u32(&sm.a_empty[buf]), ((seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
-                        const int row = r0 + et;
-                        float4 c[4];
-                        c[0] = c[1] = c[2] = c[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float q2 = 0.f;
-                        if (row < rows) {
-                            const int hh = row / nfg, i = row - hh * nfg;
-                            const float *Rm = sm.Rt[hh];
-                            const float v0 = sm.px[i] - Rm[9], v1 = sm.py[i] - Rm[10], v2 = sm.pz[i] - Rm[11];
-                            // (p1 - t) @ R : row vector times R (MU:267)
-                            const float qx = v0 * Rm[0] + v1 * Rm[3] + v2 * Rm[6];
-                            const float qy = v0 * Rm[1] + v1 * Rm[4] + v2 * Rm[7];
-                            const float qz = v0 * Rm[2] + v1 * Rm[5] + v2 * Rm[8];
-                            q2 = qx * qx + qy * qy + qz * qz;
-                            const float xh = to_tf32(qx), yh = to_tf32(qy), zh = to_tf32(qz);
-                            const float xl = to_tf32(qx - xh), yl = to_tf32(qy - yh), zl = to_tf32(qz - zh);
-                            c[0] = make_float4(xh, yh, zh, xh);
-                            c[1] = make_float4(yh, zh, xl, yl);
-                            c[2] = make_float4(zl, xl, yl, zl);
-                            c[3] = make_float4(1.f, 1.f, 0.f, 0.f);
+                } else if (is_builder) {
+                    // ================================ A-tile builders ==============================
+                    for (int tl = 0; tl < n_tiles; ++tl, ++tile_seq) {
+                        const int buf = tile_seq & 1;
+                        mbar_wait(smem_u32(&sm.a_empty[buf]), ((tile_seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
+                        for (int et = tid - 32; et < kSRows; et += kSBuilders) {  // tile rows of this thread
+                            const int row = tl * kSRows + et;
+                            float4 c0, c1, c2, c3;
+                            c0 = c1 = c2 = c3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float q2 = 0.f;
+                            if (row < rows) {
+                                const int hh = row / nfg, i = row - hh * nfg;
+                                const float *Rm = sm.Rt[hh];
+                                const float v0 = sm.px[i] - Rm[9], v1 = sm.py[i] - Rm[10], v2 = sm.pz[i] - Rm[11];
+                                // (p1 - t) @ R : row vector times R (MU:267)
+                                const float qx = v0 * Rm[0] + v1 * Rm[3] + v2 * Rm[6];
+                                const float qy = v0 * Rm[1] + v1 * Rm[4] + v2 * Rm[7];
+                                const float qz = v0 * Rm[2] + v1 * Rm[5] + v2 * Rm[8];
+                                q2 = qx * qx + qy * qy + qz * qz;
+                                const float xh = to_tf32(qx), yh = to_tf32(qy), zh = to_tf32(qz);
+                                const float xl = to_tf32(qx - xh), yl = to_tf32(qy - yh), zl = to_tf32(qz - zh);
+                                c0 = make_float4(xh, yh, zh, xh);
+                                c1 = make_float4(yh, zh, xl, yl);
+                                c2 = make_float4(zl, xl, yl, zl);
+                                c3 = make_float4(1.f, 1.f, 0.f, 0.f);
+                            }
+                            *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 0)) = c0;
+                            *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 1)) = c1;
+                            *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 2)) = c2;
+                            *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, 3)) = c3;
+                            // (the reducers read this slot when they finish the tile.  The builders run at most two
+                            // tiles ahead of the MMAs, the MMAs at most four chunks -- four tiles when a tile is
+                            // one chunk -- ahead of the reducers: 8 slots never collide)
+                            sm.q2[tile_seq & 7][et] = q2;
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)  // 16 K slots = 4 float4, shared out between the parts
-                            if (k * PARTS / 4 == part)
-                                *reinterpret_cast<float4 *>(sm.a[buf] + sw128_offset(et, k)) = c[k];
                         fence_proxy_async_smem();
                         mbar_arrive(smem_u32(&sm.a_full[buf]));
-                        return q2;
+                    }
+                    chunk_seq += (uint32_t)(n_tiles * n_chunks);
+                } else {
+                    // ================================ reducers ====================================
+                    const int quad = warp & 3, part = (warp - 4) >> 2;
+                    const int et = quad * 32 + lane;  // tile row = TMEM lane
+                    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * kSCols);
+                    float *dm = sm.dmin[part];
+                    uint32_t ra[64], rb[64];
+                    float m[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) m[k] = INFINITY;
+                    int r0 = 0;
+                    auto finish_tile = [&]() {
+                        float d = min8(m);
+                        if (r0 + et < rows) {
+                            if (!first) d = fminf(d, dm[r0 + et]);  // minimum over the earlier model blocks
+                            dm[r0 + et] = last ? d + sm.q2[tile_seq & 7][et] : d;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) m[k] = INFINITY;
+                        r0 += kSRows;
+                        ++tile_seq;
                     };
-
-                    float q2_next = build(0, tile_seq);
-                    for (int tl = 0; tl < n_tiles; ++tl, ++tile_seq) {
-                        const int r0 = tl * kSRows;
-                        const float q2 = q2_next;
-                        if (tl + 1 < n_tiles) q2_next = build(r0 + kSRows, tile_seq + 1);
-                        // reduce this thread's lane over its half of every chunk
-                        float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
-                        for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
-                            const int cb = chunk_seq & 1;
-                            mbar_wait(smem_u32(&sm.tmem_full[cb]), (chunk_seq >> 1) & 1);
-                            tc_fence_after();
-                            {
-                                float v[kSCols];
-                                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                                    (uint32_t)(cb * kSChunk + part * kSCols);
-                                if constexpr (kSCols == 128) {
-                                    tmem_ld128(ta, v);
-                                } else {
-                                    uint32_t r[64];
-                                    tmem_ld64_issue(ta, r);
-                                    tmem_ld64_wait(r);
+                    if constexpr (FIXED) {
+                        // chunk c of a tile: buffer c & 3, parity c >> 2; chunk c + 1 is loading while chunk c is folded
+                        mbar_wait(full0, 0u);
+                        tc_fence_after();
+                        tmem_ld64_issue(lane_base, ra);
+                        for (int tl = 0; tl < n_tiles; ++tl) {
+                            const bool more = tl + 1 < n_tiles;
 #pragma unroll
-                                    for (int q = 0; q < 64; ++q) v[q] = __uint_as_float(r[q]);
+                            for (int c = 0; c < kSFixedChunks; ++c) {
+                                uint32_t(&cur)[64] = (c & 1) ? rb : ra;
+                                uint32_t(&nxt)[64] = (c & 1) ? ra : rb;
+                                tmem_ld64_wait(cur);           // chunk c has landed: hand its buffer back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)(c & 3));
+                                if (c + 1 < kSFixedChunks || more) {
+                                    const int n = (c + 1) & (kSFixedChunks - 1);  // constant after unrolling
+                                    mbar_wait(full0 + 8u * (uint32_t)(n & 3), (uint32_t)((n >> 2) & 1));
+                                    tc_fence_after();
+                                    tmem_ld64_issue(lane_base + (uint32_t)((n & 3) * kSChunk), nxt);
                                 }
-#pragma unroll
-                                for (int q = 0; q < kSCols; q += 8) {
-                                    m0 = fminf(fminf(m0, v[q]), v[q + 1]);
-                                    m1 = fminf(fminf(m1, v[q + 2]), v[q + 3]);
-                                    m2 = fminf(fminf(m2, v[q + 4]), v[q + 5]);
-                                    m3 = fminf(fminf(m3, v[q + 6]), v[q + 7]);
-                                }
+                                fold64(cur, m);
                             }
+                            finish_tile();
+                        }
+                    } else {
+                        const int G = n_tiles * n_chunks;
+                        int c_in_tile = 0;
+                        auto issue = [&](uint32_t (&r)[64], uint32_t seq) {  // chunk `seq`: wait for its MMAs, start the load
+                            const int cb = seq & (kSBufs - 1);
+                            mbar_wait(smem_u32(&sm.tmem_full[cb]), (seq / kSBufs) & 1);
+                            tc_fence_after();
+                            tmem_ld64_issue(lane_base + (uint32_t)(cb * kSChunk), r);
+                        };
+                        auto landed = [&](uint32_t (&r)[64], uint32_t seq) {  // the load has landed: hand the buffer back
+                            tmem_ld64_wait(r);
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[cb]));
+                            if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[seq & (kSBufs - 1)]));
+                        };
+                        auto chunk_done = [&]() {
+                            if (++c_in_tile < n_chunks) return;
+                            c_in_tile = 0;
+                            finish_tile();
+                        };
+                        issue(ra, chunk_seq);
+                        for (int g = 0; g < G; g += 2) {
+                            landed(ra, chunk_seq + g);
+                            if (g + 1 < G) issue(rb, chunk_seq + g + 1);
+                            fold64(ra, m);
+                            chunk_done();
+                            if (g + 1 < G) {
+                                landed(rb, chunk_seq + g + 1);
+                                if (g + 2 < G) issue(ra, chunk_seq + g + 2);
+                                fold64(rb, m);
+                                chunk_done();
+                            }
                         }
-                        const float best = fminf(fminf(m0, m1), fminf(m2, m3));
-                        const int par = tile_seq & 1;
-                        if (part > 0) sm.comb[par][part - 1][et] = best;
-                        row_barrier<kSRowThreads>();
-                        if (part == 0 && r0 + et < rows) {
-                            float d = best;
-#pragma unroll
-                            for (int k = 0; k < PARTS - 1; ++k) d = fminf(d, sm.comb[par][k][et]);
-                            if (!first) d = fminf(d, sm.dis[r0 + et]);  // minimum over the earlier model blocks
-                            sm.dis[r0 + et] = last ? sqrtf(fmaxf(q2 + d, 0.f)) : d;  // clamp, then sqrt
-                        }
+                        chunk_seq += (uint32_t)G;
                     }
-                } else {  // warp 0 keeps the sequence numbers in step
-                    tile_seq += (uint32_t)n_tiles;
-                    chunk_seq += (uint32_t)(n_tiles * n_chunks);
                 }
             }
-            // deterministic per-hypothesis sums: one warp per hypothesis, fixed order
-            __syncthreads();
-            if (warp >= 2)
-                for (int hh = warp - 2; hh < nb; hh += kSRowThreads / 32) {
+            // deterministic per-hypothesis sums: one reducer warp per hypothesis, fixed order
+            if (is_reducer) {
+                reducer_barrier();
+                for (int hh = warp - 4; hh < nb; hh += kSReducers / 32) {
                     float s = 0.f;
-                    for (int i = lane; i < nfg; i += 32) s += sm.dis[hh * nfg + i];
+                    for (int i = lane; i < nfg; i += 32) {
+                        const int r = hh * nfg + i;
+                        s += sqrtf(fmaxf(fminf(sm.dmin[0][r], sm.dmin[1][r]), 0.f));  // clamp, then sqrt (MU:267)
+                    }
                     s = warp_sum(s);
                     if (lane == 0) scores[(size_t)b * H + hb + hh] = __fdiv_rn((float)nfg, s + 1e-8f);  // MU:271
                 }
-            __syncthreads();  // dis and Rt are rewritten by the next batch
+                reducer_barrier();  // dmin is rewritten by the next batch
+            }
         }
-    } else if (warp >= 2) {
+    } else if (is_reducer) {
         // no foreground point: sum = 0 -> score = 0 / 1e-8 = 0 (MU:271)
-        for (int h = h_begin + (tid - 64); h < h_end; h += kSRowThreads) scores[(size_t)b * H + h] = 0.f;
+        for (int h = h_begin + (tid - 32 - kSBuilders); h < h_end; h += kSReducers) scores[(size_t)b * H + h] = 0.f;
     }
 
     tc_fence_before();
@@ -315,8 +401,6 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
 
 }  // namespace tc
 
-static int g_score_parts = 2;  // row threads per tile row (development knob: 2 or 4; 4 measured 6 % slower)
-
 // returns PEM_E_UNSUPPORTED for shapes the tensor-core kernel does not take (the caller falls back
 // to the SIMT kernel)
 int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
@@ -326,20 +410,19 @@ int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, i
     if (Nm > 4 * kSMaxNm || N1 > kSMaxN1) return PEM_E_UNSUPPORTED;
     const int sms = pem_num_sms();
     const int cpi = max(1, min(sms / B, (H + 7) / 8));  // CTAs per instance
-    if (g_score_parts == 2) {
-        const size_t smem = sizeof(ScoreSmem<2>) + 1024;
+    const size_t smem = sizeof(ScoreSmem) + 1024;
+    const int tail = Nm % kSMaxNm;  // every model block eight chunks?
+    const bool fixed = tail == 0 || tail > kSMaxNm - kSChunk;
+    if (fixed) {
         static PemSmemCache cached(0);
-        if (int rc = pem_ensure_dyn_smem(score_tc_kernel<2>, smem, &cached)) return rc;
-        score_tc_kernel<2><<<B * cpi, 64 + 256, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
+        if (int rc = pem_ensure_dyn_smem(score_tc_kernel<true>, smem, &cached)) return rc;
+        score_tc_kernel<true><<<B * cpi, kSThreads, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
     } else {
-        const size_t smem = sizeof(ScoreSmem<4>) + 1024;
         static PemSmemCache cached(0);
-        if (int rc = pem_ensure_dyn_smem(score_tc_kernel<4>, smem, &cached)) return rc;
-        score_tc_kernel<4><<<B * cpi, 64 + 512, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
+        if (int rc = pem_ensure_dyn_smem(score_tc_kernel<false>, smem, &cached)) return rc;
+        score_tc_kernel<false><<<B * cpi, kSThreads, smem, st>>>(R, t, sel, P, H, pts1, w1, N1, model, Nm, cpi, scores);
     }
     return pem_launch_status();
 }
 
 }  // namespace pem
-
-extern "C" void pem_dev_set_score_parts(int parts) { pem::g_score_parts = parts == 4 ? 4 : 2; }

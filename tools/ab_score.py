@@ -1,4 +1,4 @@
-"""A/B of the scoring kernel's row-thread split (2 or 4 parts per tile row) at the stage's shape."""
+"""Times the tensor-core scoring kernel at the stage's shape (NM=... for other model sizes)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,8 +15,7 @@ w1 = torch.zeros(B, n1)
 w1[:, :152] = 1.0
 w1 = w1.to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for parts in (2, 4, 2, 4):
-    L.pem_dev_set_score_parts(parts)
+for parts in (2, 2):
     for _ in range(3):
         pkg.model_utils.score_hypotheses(R, t, pts, w1, model)
     ms = []

@@ -218,6 +218,14 @@ int pem_select_smallest(const float *resid, int B, int P1, int P2, int32_t *sel,
 int pem_score_hypotheses(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
                          const float *pts1, const float *w1, int N1, const float *model, int Nm,
                          float *scores, pem_stream_t stream);
+/* ... with the kernel named by the caller (parity tests compare the two): AUTO = the tensor-core kernel for every
+ * shape it takes (<= 4096 model points), else the SIMT kernel; TENSOR returns PEM_E_UNSUPPORTED for other shapes. */
+#define PEM_SCORE_AUTO 0
+#define PEM_SCORE_SIMT 1
+#define PEM_SCORE_TENSOR 2
+int pem_score_hypotheses_ex(const float *R, const float *t, const int32_t *sel, int B, int P, int H,
+                            const float *pts1, const float *w1, int N1, const float *model, int Nm,
+                            float *scores, int kernel, pem_stream_t stream);
 
 /*
  * argmax over scores (MU:272-274), first maximum wins; copies the winner.
@@ -282,6 +290,13 @@ int pem_fine_fused(const float *f1, const float *f2, const float *pts1, const fl
  */
 #define PEM_PREC_SPLIT_BF16 0
 #define PEM_PREC_FP16 1
+/* Options OR-ed into `precision` (same results; the parity tests hold the forms against each other):
+ *   PEM_FINE_THREE_PASS         the original three full GEMM passes (statistics, labels, weighted sums) instead of
+ *                               two full passes + the ragged background-column correction;
+ *   PEM_FINE_STEPS_PER_TASK(n)  n row steps of 256 rows per (instance, strip) task instead of the automatic choice
+ *                               (n = 0). */
+#define PEM_FINE_THREE_PASS 0x100
+#define PEM_FINE_STEPS_PER_TASK(n) (((n) & 0xff) << 16)
 int pem_fine_fused_ex(const float *f1, const float *f2, const float *pts1, const float *pts2,
                       const float *model, int B, int N1, int N2, int C, int Nm, float temp,
                       float dis_thres, int precision, float *R, float *t, float *score, float *w1,

@@ -40,6 +40,7 @@ SIGNATURES = {
     "pem_coarse_hypotheses": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "pem_select_smallest": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "pem_score_hypotheses": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p]),
+    "pem_score_hypotheses_ex": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p]),
     "pem_select_best": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "pem_fine_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "pem_fine_Rt": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p,

@@ -787,13 +787,17 @@ int score_tc_launch(const float *R, const float *t, const int32_t *sel, int B, i
                     const float *pts1, const float *w1, int N1, const float *model, int Nm,
                     float *scores, cudaStream_t st);  // score_tc.cu
 }
-static int g_score_simt = 0;  // development knob: 1 = always the SIMT kernel
-extern "C" void pem_dev_set_score_simt(int v) { g_score_simt = v; }
-
 extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_t *sel, int B, int P,
                                     int H, const float *pts1, const float *w1, int N1,
                                     const float *model, int Nm, float *scores,
                                     pem_stream_t stream) {
+    return pem_score_hypotheses_ex(R, t, sel, B, P, H, pts1, w1, N1, model, Nm, scores, PEM_SCORE_AUTO, stream);
+}
+
+extern "C" int pem_score_hypotheses_ex(const float *R, const float *t, const int32_t *sel, int B, int P,
+                                       int H, const float *pts1, const float *w1, int N1,
+                                       const float *model, int Nm, float *scores, int kernel,
+                                       pem_stream_t stream) {
     PEM_REQUIRE_PTR(R);
     PEM_REQUIRE_PTR(t);
     PEM_REQUIRE_PTR(pts1);
@@ -803,9 +807,10 @@ extern "C" int pem_score_hypotheses(const float *R, const float *t, const int32_
     PEM_REQUIRE(B > 0 && P > 0 && H > 0 && N1 > 0 && Nm > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(sel != nullptr || H <= P, PEM_E_SHAPE);
     PEM_REQUIRE(N1 <= 256, PEM_E_UNSUPPORTED);  // hyps*N1 <= kScQMax*threads in both shapes
-    if (!g_score_simt) {  // tensor-core kernel (score_tc.cu) for every shape it takes
+    PEM_REQUIRE(kernel == PEM_SCORE_AUTO || kernel == PEM_SCORE_SIMT || kernel == PEM_SCORE_TENSOR, PEM_E_SHAPE);
+    if (kernel != PEM_SCORE_SIMT) {  // tensor-core kernel (score_tc.cu) for every shape it takes
         const int rc = score_tc_launch(R, t, sel, B, P, H, pts1, w1, N1, model, Nm, scores, pem_cu_stream(stream));
-        if (rc != PEM_E_UNSUPPORTED) return rc;
+        if (rc != PEM_E_UNSUPPORTED || kernel == PEM_SCORE_TENSOR) return rc;
     }
     // 8 hypotheses per CTA amortise the model-point staging best; small problems use 4 so the
     // grid still covers every SM several times

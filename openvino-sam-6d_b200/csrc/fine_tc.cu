@@ -78,6 +78,7 @@ struct Params {
     int Mp, Np;            // padded rows of A' / B' per instance (multiples of 256)
     int n_msteps, n_strips; // Mp / 256 row steps, Np / 256 column strips
     int spt, n_splits;     // row steps per task, tasks per (instance, strip)
+    int spt_fixed;         // 1: the caller fixed spt (PEM_FINE_STEPS_PER_TASK); the ragged launch keeps it
     int KC;                // C / 64
     int ring;              // single-product mode: ring slots (2..9)
     int single;            // 1: one fp16 product per element (operands = fp16 of the normalised rows); 0: split-bf16, three products
@@ -1042,16 +1043,25 @@ static Ws carve(void *base, int B, int rows1, int rows2, int C) {
 
 static int num_sms() { return pem_num_sms(); }
 
-static int g_steps_per_task = 0;  // development knob: 0 = choose automatically
-static int g_fine_passes = 2;     // development knob: 3 = the original three full GEMM passes
-static int g_epi_warps_single = kEpiWarpsSingle;  // development knob: epilogue warps of the single-product mode (8 or 16)
+// Tuning knobs of the single-product mode.  Constants in the shipped library; a -DPEM_DEV_KNOBS build (make DEV=1,
+// tools/pass_probe.py) makes them settable.
+#ifdef PEM_DEV_KNOBS
+static int g_epi_warps_single = kEpiWarpsSingle;  // epilogue warps of the single-product mode (8 or 16)
+static int g_ring_single = kMaxStages;            // ring slots of the single-product mode
+static int g_dev_steps_per_task = 0;              // row steps per task when the caller leaves the choice open
+#else
+static constexpr int g_epi_warps_single = kEpiWarpsSingle;
+static constexpr int g_ring_single = kMaxStages;
+#endif
 
 // epilogue warps per CTA / row partials per strip for these parameters
-static int g_ring_single = kMaxStages;            // development knob: ring slots of the single-product mode
 static int epw_of(const Params &p) { return p.single ? g_epi_warps_single : 8; }
 
 // rows1 x rows2 GEMM per instance
-static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp, int single = 0) {
+static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp, int single = 0, int steps_per_task = 0) {
+#ifdef PEM_DEV_KNOBS
+    if (steps_per_task == 0) steps_per_task = g_dev_steps_per_task;
+#endif
     if (C % BK != 0 || C > BK * kMaxKC) return PEM_E_UNSUPPORTED;
     if (!(temp > 0.f) || 2.0f / temp > 80.f) return PEM_E_UNSUPPORTED;  // fixed-shift softmax range
     p.B = B; p.R = rows1; p.Cn = rows2;
@@ -1075,7 +1085,8 @@ static int fill_common(Params &p, int B, int rows1, int rows2, int C, float temp
         const double cost = (double)rounds * (spt + reload);
         if (cost < best_cost) { best_cost = cost; best = spt; }
     }
-    p.spt = g_steps_per_task > 0 ? min(g_steps_per_task, p.n_msteps) : best;
+    p.spt = steps_per_task > 0 ? min(steps_per_task, p.n_msteps) : best;
+    p.spt_fixed = steps_per_task > 0;
     p.n_splits = (p.n_msteps + p.spt - 1) / p.spt;
     p.ring = g_ring_single;
     p.temp = temp;
@@ -1098,7 +1109,7 @@ static Params ragged_params(const Params &p, int B) {
         const double cost = (double)rounds * (spt + (p.single ? 0.75 : 0.25));
         if (cost <= best_cost) { best_cost = cost; best = spt; }
     }
-    pc.spt = g_steps_per_task > 0 ? p.spt : best;
+    pc.spt = p.spt_fixed ? p.spt : best;
     pc.n_splits = (p.n_msteps + pc.spt - 1) / pc.spt;
     return pc;
 }
@@ -1139,10 +1150,11 @@ static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Par
 using namespace pem;
 using namespace pem::tc;
 
-extern "C" void pem_dev_set_fine_steps_per_task(int v) { g_steps_per_task = v; }
-extern "C" void pem_dev_set_fine_passes(int v) { g_fine_passes = v == 3 ? 3 : 2; }
+#ifdef PEM_DEV_KNOBS
+extern "C" void pem_dev_set_fine_steps_per_task(int v) { g_dev_steps_per_task = v; }
 extern "C" void pem_dev_set_fine_epi_warps(int v) { g_epi_warps_single = v == 8 ? 8 : 16; }
 extern "C" void pem_dev_set_fine_ring(int v) { g_ring_single = v < 2 ? 2 : v > kMaxStages ? kMaxStages : v; }
+#endif
 
 // fine.cu
 namespace pem {
@@ -1187,6 +1199,10 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
                                  float dis_thres, int precision, float *R, float *t, float *score,
                                  float *w1_out, float *w2_out, float *rowsum_out, float *pred_out,
                                  void *workspace, size_t workspace_bytes, pem_stream_t stream) {
+    // option bits ride on the precision word (pem_b200.h): PEM_FINE_THREE_PASS, PEM_FINE_STEPS_PER_TASK(n)
+    const int options = precision & ~0xff;
+    precision &= 0xff;
+    PEM_REQUIRE((options & ~(PEM_FINE_THREE_PASS | PEM_FINE_STEPS_PER_TASK(0xff))) == 0, PEM_E_UNSUPPORTED);
     PEM_REQUIRE(precision == PEM_PREC_SPLIT_BF16 || precision == PEM_PREC_FP16, PEM_E_UNSUPPORTED);
     PEM_REQUIRE_PTR(f1);
     PEM_REQUIRE_PTR(f2);
@@ -1200,7 +1216,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
     PEM_REQUIRE((uintptr_t)f1 % 16 == 0 && (uintptr_t)f2 % 16 == 0, PEM_E_UNSUPPORTED);  // 16-byte row loads
     Params p{};
     // the background token stays out of the GEMM
-    if (int rc = fill_common(p, B, N1, N2, C, temp, precision == PEM_PREC_FP16)) return rc;
+    if (int rc = fill_common(p, B, N1, N2, C, temp, precision == PEM_PREC_FP16, (options >> 16) & 0xff)) return rc;
     PEM_REQUIRE(workspace != nullptr &&
                     workspace_bytes >= pem_fine_fused_workspace_bytes(B, N1, N2, C),
                 PEM_E_WORKSPACE);
@@ -1218,7 +1234,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
     const int mx = max(p.Mp, p.Np);
     const int pps = epw_of(p) / 4;  // row partials per strip: one per epilogue warp of a quadrant
     const int n_part = pps * p.n_strips, planes = 2 * p.n_splits;
-    const bool two_pass = g_fine_passes == 2 && p.Np <= 4096;
+    const bool two_pass = !(options & PEM_FINE_THREE_PASS) && p.Np <= 4096;
     // pass 1: softmax statistics
     p.rowpart = w.rowpart;
     p.colpart = w.colpart;

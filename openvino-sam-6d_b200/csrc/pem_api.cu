@@ -24,6 +24,7 @@ extern "C" const char *pem_status_string(int status) {
     return "unknown status";
 }
 
-// programmatic dependent launches on/off (development knob; default on)
+#ifdef PEM_DEV_KNOBS   // make DEV=1: programmatic dependent launches on/off for A/B runs (always on otherwise)
 int g_pem_pdl = 1;
 extern "C" void pem_dev_set_pdl(int on) { g_pem_pdl = on ? 1 : 0; }
+#endif

@@ -73,8 +73,12 @@ static inline cudaStream_t pem_cu_stream(pem_stream_t s) { return reinterpret_ca
 // completed and flushed, so launch latency and prologue hide under the predecessor's tail.  EVERY kernel
 // launched this way calls pem::pdl_enter() before its first global-memory access; a kernel that calls it
 // under a plain launch passes straight through.  Works across stream capture (the graph keeps the
-// programmatic edge).  pem_dev_set_pdl(0) turns all such launches back into plain ones.
+// programmatic edge).  In a -DPEM_DEV_KNOBS build pem_dev_set_pdl(0) turns such launches back into plain ones.
+#ifdef PEM_DEV_KNOBS
 extern int g_pem_pdl;  // pem_api.cu
+#else
+static constexpr int g_pem_pdl = 1;
+#endif
 template <typename... KArgs, typename... Args>
 static inline void pem_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                   Args... args) {

@@ -856,8 +856,12 @@ static size_t bq_smem_bytes(int ns) {
 // ------------------------------------------------------------------------------------
 using namespace pem;
 
+#ifdef PEM_DEV_KNOBS   // make DEV=1 (tools/fps_variants.py): alternative launch shapes of the sampling kernel
 static int g_fps_variant = 0;
 extern "C" void pem_dev_set_fps_variant(int v) { g_fps_variant = v; }
+#else
+static constexpr int g_fps_variant = 0;
+#endif
 
 extern "C" size_t pem_fps_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 16 * 16384) return 0;

@@ -19,15 +19,16 @@
 //   * the model operand (1024 rows x 64 used bytes, SWIZZLE_128B K-major rows) is built once in
 //     shared memory; rows of all hypotheses of the slice are packed back to back into 128-row
 //     tiles, so no tensor work is wasted on padding 151 points to 256;
-//   * warp 0 issues M128 x N128 x K8 MMAs, 2 per 128-model-point chunk, into FOUR accumulator buffers
-//     (all 512 TMEM columns), i.e. it runs up to three chunks ahead of the reduction;
-//   * warps 1-3 ("builders", 96 threads for the 128 tile rows) transform their points and write the A rows
+//   * warps 0-1 issue M128 x N128 x K8 MMAs, 2 per 128-model-point chunk (even chunks warp 0, odd chunks
+//     warp 1: one warp walking its ~40 dependent instructions per chunk could not keep the reducers fed), into
+//     FOUR accumulator buffers (all 512 TMEM columns), i.e. up to three chunks ahead of the reduction;
+//   * warps 2-3 ("builders", 64 threads for the 128 tile rows) transform their points and write the A rows
 //     (generic stores + proxy fence) of the next tile, double buffered, and leave |q|^2 in a small ring;
-//   * warps 4-11 ("reducers", two per TMEM lane quadrant, each on 64 of a chunk's 128 columns) fold
-//     their lane of every accumulator chunk with 3-input minima; the tcgen05.ld of chunk g+1 is issued
-//     BEFORE chunk g is folded and the buffer is handed back as soon as its load has landed, so TMEM
-//     reads, minima and MMAs overlap;
-//   * per-part row minima (+ |q|^2) land in shared memory, and each hypothesis is summed in a fixed order.
+//   * warps 4-11 ("reducers", two per TMEM lane quadrant: one takes the even chunks, the other the odd
+//     ones, all 128 columns) load their lane of an accumulator chunk, hand the buffer back the moment the
+//     load has landed and fold it with 3-input minima (8 independent chains); the two warps of a scheduler
+//     wait on different barriers, so one folds while the other's load is in flight;
+//   * per-warp row minima (+ |q|^2) land in shared memory, and each hypothesis is summed in a fixed order.
 // What bounds it (tools/tmem_ld_rate.cu, tools/minmax_rate.cu on this GPU): tcgen05.ld 32x32b delivers
 // ~950 B/clk/SM with two warps per quadrant, so the accumulator read is NOT the limit (the round-1 form
 // of this kernel -- load, wait, fold in lock step, two buffers -- sat at 128 B/clk/SM and was misread as
@@ -56,8 +57,8 @@ constexpr int kSFixedChunks = kSMaxNm / kSChunk;  // chunks per tile of the unro
 constexpr int kSMaxN1 = 256;         // query points per instance
 constexpr int kSBatchHyps = 40;      // hypotheses per batch (their R | t staged in shared memory)
 constexpr int kSRowCap = 6144;       // rows (hypothesis, point) of a batch whose minima fit in shared memory
-constexpr int kSBuilders = 96, kSReducers = 256, kSThreads = 32 + kSBuilders + kSReducers;  // 12 warps: 168 registers
-constexpr int kSCols = kSChunk / 2;  // columns per reducer thread and chunk
+constexpr int kSIssuers = 2;        // MMA-issuing warps: warp w takes the chunks whose running number has parity w
+constexpr int kSBuilders = 64, kSReducers = 256, kSThreads = 32 * kSIssuers + kSBuilders + kSReducers;  // 12 warps: 168 registers
 constexpr uint32_t kSIdesc = make_idesc_tf32(kSRows, kSChunk);
 
 struct ScoreSmem {
@@ -102,57 +103,33 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
     const int b = blockIdx.x / cpi, slice = blockIdx.x - b * cpi;
     const int hpc = (H + cpi - 1) / cpi;                       // hypotheses per CTA
     const int h_begin = slice * hpc, h_end = min(H, h_begin + hpc);
-    const bool is_mma = warp == 0, is_builder = warp >= 1 && warp <= 3, is_reducer = warp >= 4;
+    const bool is_mma = warp < kSIssuers, is_builder = warp >= kSIssuers && warp <= 3, is_reducer = warp >= 4;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&sm.a_full[i]), kSBuilders);
-            mbar_init(smem_u32(&sm.a_empty[i]), 1);
+            mbar_init(smem_u32(&sm.a_empty[i]), kSIssuers);
         }
         for (int i = 0; i < kSBufs; ++i) {
             mbar_init(smem_u32(&sm.tmem_full[i]), 1);
-            mbar_init(smem_u32(&sm.tmem_empty[i]), kSReducers / 32);
+            mbar_init(smem_u32(&sm.tmem_empty[i]), kSReducers / 64);   // one reducer warp per lane quadrant
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&sm.tmem_base)),
                      "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ---- per-CTA setup: foreground points (ordered compaction)
-    if (warp == 0) {
-        const float *wb = w1 + (size_t)b * N1, *pb = pts1 + (size_t)b * N1 * 3;
-        int n = 0;
-        for (int base = 0; base < N1; base += 32) {
-            const int i = base + lane;
-            const bool fg = i < N1 && __ldg(wb + i) != 0.f;
-            const unsigned bal = __ballot_sync(kFull, fg);
-            if (fg) {
-                const int o = n + __popc(bal & ((1u << lane) - 1u));
-                sm.px[o] = __ldg(pb + 3 * i);
-                sm.py[o] = __ldg(pb + 3 * i + 1);
-                sm.pz[o] = __ldg(pb + 3 * i + 2);
-            }
-            n += __popc(bal);
-        }
-        if (lane == 0) sm.nfg = n;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = sm.tmem_base;
-    const int nfg = sm.nfg;
     const int n_blocks = (Nm + kSMaxNm - 1) / kSMaxNm;  // model blocks of <= 1024 points
-
     // the model operand: block `mblk` of the model points as B rows (all threads)
-    auto build_model = [&](int mblk) {
+    auto build_model = [&](int mblk, int first_thread) {
         const float *mb = model + (size_t)b * Nm * 3;
         const int m_lo = mblk * kSMaxNm, cnt = min(kSMaxNm, Nm - m_lo);
         const int padded = (cnt + kSChunk - 1) / kSChunk * kSChunk;
-        for (int m = tid; m < padded; m += kSThreads) {
+        for (int m = tid - first_thread; m < padded; m += kSThreads - first_thread) {
             float4 c0, c1, c2, c3;
             if (m < cnt) {
                 const float *p = mb + 3 * (size_t)(m_lo + m);
@@ -176,12 +153,38 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
         fence_proxy_async_smem();
     };
 
+    // ---- per-CTA setup: foreground points (ordered compaction)
+    // (warp 0 compacts -- seven dependent rounds of global loads -- while the other warps build the first model block)
+    if (warp != 0) build_model(0, 32);
+    if (warp == 0) {
+        const float *wb = w1 + (size_t)b * N1, *pb = pts1 + (size_t)b * N1 * 3;
+        int n = 0;
+        for (int base = 0; base < N1; base += 32) {
+            const int i = base + lane;
+            const bool fg = i < N1 && __ldg(wb + i) != 0.f;
+            const unsigned bal = __ballot_sync(kFull, fg);
+            if (fg) {
+                const int o = n + __popc(bal & ((1u << lane) - 1u));
+                sm.px[o] = __ldg(pb + 3 * i);
+                sm.py[o] = __ldg(pb + 3 * i + 1);
+                sm.pz[o] = __ldg(pb + 3 * i + 2);
+            }
+            n += __popc(bal);
+        }
+        if (lane == 0) sm.nfg = n;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+    const int nfg = sm.nfg;
+
     if (nfg > 0 && h_begin < h_end) {
         // Every warp walks the same (batch of hypotheses, model block) sequence; with more than 1024
         // model points the tiles of a batch are run once per model block and the running minimum of
         // each row waits in `dmin` in between.  Barrier phases (tile_seq, chunk_seq) run on throughout.
         uint32_t tile_seq = 0, chunk_seq = 0;
-        int loaded = -1;  // model block currently in shared memory
+        int loaded = 0;  // model block currently in shared memory (block 0 was built during the setup)
         const int batch = max(1, min(kSBatchHyps, kSRowCap / nfg));
         const uint32_t full0 = smem_u32(&sm.tmem_full[0]), empty0 = smem_u32(&sm.tmem_empty[0]);
         for (int hb = h_begin; hb < h_end; hb += batch) {
@@ -189,7 +192,7 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
             const int n_tiles = (rows + kSRows - 1) / kSRows;
             if (is_builder) {
                 builder_barrier();  // every builder is done with the previous batch's R | t
-                for (int k = tid - 32; k < nb * 12; k += kSBuilders) {  // stage R | t of the batch
+                for (int k = tid - 32 * kSIssuers; k < nb * 12; k += kSBuilders) {  // stage R | t of the batch
                     const int hh = k / 12, e = k - hh * 12, h = hb + hh;
                     const size_t src = (size_t)b * P + (sel ? __ldg(sel + (size_t)b * H + h) : h);
                     sm.Rt[hh][e] = e < 9 ? __ldg(R + src * 9 + e) : __ldg(t + src * 3 + (e - 9));
@@ -201,7 +204,7 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                                            : (min(kSMaxNm, Nm - mblk * kSMaxNm) + kSChunk - 1) / kSChunk;
                 if (loaded != mblk) {  // (every MMA that read the previous block has retired: its
                     __syncthreads();   //  accumulators were all consumed before this barrier)
-                    build_model(mblk);
+                    build_model(mblk, 0);
                     loaded = mblk;
                     __syncthreads();
                 }
@@ -217,21 +220,27 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                         const uint64_t ad = umma_desc_sw128(smem_u32(sm.a[buf]));
                         if constexpr (FIXED) {
 #pragma unroll
-                            for (int c = 0; c < kSFixedChunks; ++c) {
-                                mbar_wait(empty0 + 8u * (uint32_t)(c & 3), (uint32_t)(((c >> 2) & 1) ^ 1));
+                            for (int c0 = 0; c0 < kSFixedChunks; c0 += kSIssuers) {
+                                const int c = c0 + warp;  // (kSFixedChunks is even: the parity of c is the warp's)
+                                const uint32_t slot = 8u * (uint32_t)(c & 3), par = (uint32_t)(((c0 >> 2) & 1) ^ 1);
+                                mbar_wait(empty0 + slot, par);
                                 tc_fence_after();
                                 if (elect_one()) {
                                     const uint32_t d = tmem_base + (uint32_t)((c & 3) * kSChunk);
                                     const uint64_t bd = b0 + (uint64_t)(c * (kSChunk * 128 / 16));
                                     tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
                                     tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
-                                    tc_commit(full0 + 8u * (uint32_t)(c & 3));
-                                    if (c == kSFixedChunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                                    tc_commit(full0 + slot);
+                                    if (c0 == kSFixedChunks - kSIssuers) tc_commit(smem_u32(&sm.a_empty[buf]));
                                 }
                                 __syncwarp();
                             }
                         } else {
+                            bool mine = false;
                             for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                                if ((int)(chunk_seq & (kSIssuers - 1)) != warp) continue;
+                                const bool last_of_mine = c + kSIssuers >= n_chunks;
+                                mine = true;
                                 const int cb = chunk_seq & (kSBufs - 1);
                                 mbar_wait(smem_u32(&sm.tmem_empty[cb]), ((chunk_seq / kSBufs) & 1) ^ 1);
                                 tc_fence_after();
@@ -241,10 +250,12 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                                     tc_mma_tf32(d, ad, bd, kSIdesc, 0);          // K slots 0..7
                                     tc_mma_tf32(d, ad + 2, bd + 2, kSIdesc, 1);  // K slots 8..15 (+32 bytes)
                                     tc_commit(smem_u32(&sm.tmem_full[cb]));
-                                    if (c == n_chunks - 1) tc_commit(smem_u32(&sm.a_empty[buf]));
+                                    if (last_of_mine) tc_commit(smem_u32(&sm.a_empty[buf]));
                                 }
                                 __syncwarp();
                             }
+                            // a warp without a chunk in this tile still owes the tile's a_empty arrival
+                            if (!mine && lane == 0) mbar_arrive(smem_u32(&sm.a_empty[buf]));
                         }
                     }
                 } else if (is_builder) {
@@ -252,7 +263,7 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                     for (int tl = 0; tl < n_tiles; ++tl, ++tile_seq) {
                         const int buf = tile_seq & 1;
                         mbar_wait(smem_u32(&sm.a_empty[buf]), ((tile_seq >> 1) & 1) ^ 1);  // MMAs of the tile two back retired
-                        for (int et = tid - 32; et < kSRows; et += kSBuilders) {  // tile rows of this thread
+                        for (int et = tid - 32 * kSIssuers; et < kSRows; et += kSBuilders) {  // tile rows of this thread
                             const int row = tl * kSRows + et;
                             float4 c0, c1, c2, c3;
                             c0 = c1 = c2 = c3 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,11 +299,14 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                     chunk_seq += (uint32_t)(n_tiles * n_chunks);
                 } else {
                     // ================================ reducers ====================================
+                    // Two warps per TMEM lane quadrant; warp `part` of a quadrant takes the chunks whose running
+                    // number has parity `part`, all 128 columns of them: load, hand the buffer back the moment
+                    // the load has landed, fold.  The two warps of a scheduler wait on different barriers, so
+                    // one folds while the other's load is in flight.
                     const int quad = warp & 3, part = (warp - 4) >> 2;
                     const int et = quad * 32 + lane;  // tile row = TMEM lane
-                    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * kSCols);
+                    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
                     float *dm = sm.dmin[part];
-                    uint32_t ra[64], rb[64];
                     float m[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) m[k] = INFINITY;
@@ -308,65 +322,38 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                         r0 += kSRows;
                         ++tile_seq;
                     };
-                    if constexpr (FIXED) {
-                        // chunk c of a tile: buffer c & 3, parity c >> 2; chunk c + 1 is loading while chunk c is folded
-                        mbar_wait(full0, 0u);
+                    auto take = [&](uint32_t full_bar, uint32_t parity, uint32_t empty_bar, uint32_t col) {
+                        float v[kSChunk];
+                        mbar_wait(full_bar, parity);
                         tc_fence_after();
-                        tmem_ld64_issue(lane_base, ra);
-                        for (int tl = 0; tl < n_tiles; ++tl) {
-                            const bool more = tl + 1 < n_tiles;
+                        tmem_ld128(lane_base + col, v);     // (waits for the load)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty_bar);
 #pragma unroll
-                            for (int c = 0; c < kSFixedChunks; ++c) {
-                                uint32_t(&cur)[64] = (c & 1) ? rb : ra;
-                                uint32_t(&nxt)[64] = (c & 1) ? ra : rb;
-                                tmem_ld64_wait(cur);           // chunk c has landed: hand its buffer back
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)(c & 3));
-                                if (c + 1 < kSFixedChunks || more) {
-                                    const int n = (c + 1) & (kSFixedChunks - 1);  // constant after unrolling
-                                    mbar_wait(full0 + 8u * (uint32_t)(n & 3), (uint32_t)((n >> 2) & 1));
-                                    tc_fence_after();
-                                    tmem_ld64_issue(lane_base + (uint32_t)((n & 3) * kSChunk), nxt);
-                                }
-                                fold64(cur, m);
+                        for (int q = 0; q < kSChunk; q += 16) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) m[k] = fminf(fminf(m[k], v[q + 2 * k]), v[q + 2 * k + 1]);
+                        }
+                    };
+                    if constexpr (FIXED) {
+                        for (int tl = 0; tl < n_tiles; ++tl) {
+#pragma unroll
+                            for (int j = 0; j < kSFixedChunks / 2; ++j) {
+                                const uint32_t slot = (uint32_t)((2 * j + part) & 3);   // chunk c = 2 j + part
+                                take(full0 + 8u * slot, (uint32_t)((j >> 1) & 1), empty0 + 8u * slot, slot * kSChunk);
                             }
                             finish_tile();
                         }
                     } else {
-                        const int G = n_tiles * n_chunks;
-                        int c_in_tile = 0;
-                        auto issue = [&](uint32_t (&r)[64], uint32_t seq) {  // chunk `seq`: wait for its MMAs, start the load
-                            const int cb = seq & (kSBufs - 1);
-                            mbar_wait(smem_u32(&sm.tmem_full[cb]), (seq / kSBufs) & 1);
-                            tc_fence_after();
-                            tmem_ld64_issue(lane_base + (uint32_t)(cb * kSChunk), r);
-                        };
-                        auto landed = [&](uint32_t (&r)[64], uint32_t seq) {  // the load has landed: hand the buffer back
-                            tmem_ld64_wait(r);
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&sm.tmem_empty[seq & (kSBufs - 1)]));
-                        };
-                        auto chunk_done = [&]() {
-                            if (++c_in_tile < n_chunks) return;
-                            c_in_tile = 0;
-                            finish_tile();
-                        };
-                        issue(ra, chunk_seq);
-                        for (int g = 0; g < G; g += 2) {
-                            landed(ra, chunk_seq + g);
-                            if (g + 1 < G) issue(rb, chunk_seq + g + 1);
-                            fold64(ra, m);
-                            chunk_done();
-                            if (g + 1 < G) {
-                                landed(rb, chunk_seq + g + 1);
-                                if (g + 2 < G) issue(ra, chunk_seq + g + 2);
-                                fold64(rb, m);
-                                chunk_done();
+                        for (int tl = 0; tl < n_tiles; ++tl) {
+                            for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
+                                if ((int)(chunk_seq & 1) != part) continue;
+                                const uint32_t slot = chunk_seq & (kSBufs - 1);
+                                take(full0 + 8u * slot, (chunk_seq / kSBufs) & 1, empty0 + 8u * slot, slot * kSChunk);
                             }
+                            finish_tile();
                         }
-                        chunk_seq += (uint32_t)G;
                     }
                 }
             }
@@ -387,12 +374,12 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
         }
     } else if (is_reducer) {
         // no foreground point: sum = 0 -> score = 0 / 1e-8 = 0 (MU:271)
-        for (int h = h_begin + (tid - 32 - kSBuilders); h < h_end; h += kSReducers) scores[(size_t)b * H + h] = 0.f;
+        for (int h = h_begin + (tid - 32 * kSIssuers - kSBuilders); h < h_end; h += kSReducers) scores[(size_t)b * H + h] = 0.f;
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
                      : "memory");

@@ -140,19 +140,23 @@ def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_pro
     return R, t
 
 
-def score_hypotheses(R, t, pts1, w1, model_pts, sel=None):
+SCORE_KERNELS = {"auto": 0, "simt": 1, "tensor": 2}  # PEM_SCORE_* of include/pem_b200.h
+
+
+def score_hypotheses(R, t, pts1, w1, model_pts, sel=None, kernel="auto"):
     """Standalone hypothesis scoring (MU:267-271) for the proposal sweep: R (B,P,3,3),
-    t (B,P,3) -> scores (B,H) with H = P (sel None) or sel.shape[1]."""
+    t (B,P,3) -> scores (B,H) with H = P (sel None) or sel.shape[1].  kernel: "auto" (the tensor-core
+    kernel for every shape it takes), "simt" or "tensor" (the parity tests compare the two)."""
     R, t = _f32c(R, "R"), _f32c(t, "t")
     pts1, w1, model_pts = _f32c(pts1, "pts1"), _f32c(w1, "w1"), _f32c(model_pts, "model_pts")
     B, P = R.shape[:2]
     H = P if sel is None else sel.shape[1]
     scores = torch.empty((B, H), dtype=torch.float32, device=R.device)
     with torch.cuda.device(R.device):
-        _lib.check(_lib.lib().pem_score_hypotheses(
+        _lib.check(_lib.lib().pem_score_hypotheses_ex(
             R.data_ptr(), t.data_ptr(), None if sel is None else sel.data_ptr(), B, P, H,
             pts1.data_ptr(), w1.data_ptr(), pts1.shape[1], model_pts.data_ptr(),
-            model_pts.shape[1], scores.data_ptr(), _ext._stream()), "pem_score_hypotheses")
+            model_pts.shape[1], scores.data_ptr(), SCORE_KERNELS[kernel], _ext._stream()), "pem_score_hypotheses")
     return scores
 
 
@@ -188,12 +192,14 @@ FINE_PRECISIONS = {"split_bf16": 0, "fp16": 1}  # PEM_PREC_* of include/pem_b200
 
 
 def compute_fine_Rt_fused(feat1, feat2, pts1, pts2, model_pts=None, temp=0.1, dis_thres=0.15,
-                          return_stages=False, precision="split_bf16"):
+                          return_stages=False, precision="split_bf16", three_pass=False, steps_per_task=0):
     """compute_feature_similarity(feat1, feat2, 'cosine', temp, True) followed by
     compute_fine_Rt(...), fused: the attention matrix never exists in memory.
     feat1 (B,N1+1,C), feat2 (B,N2+1,C) carry the background token in row 0
     (fine_point_matching.py:48-51).  precision: "split_bf16" (three bf16 products per element,
-    fp32-class logits) or "fp16" (one fp16 product, logits to ~1e-3 of +-1/temp)."""
+    fp32-class logits) or "fp16" (one fp16 product, logits to ~1e-3 of +-1/temp).  three_pass /
+    steps_per_task: PEM_FINE_THREE_PASS / PEM_FINE_STEPS_PER_TASK of include/pem_b200.h (same results by
+    another schedule; the parity tests hold the forms against each other)."""
     if precision not in FINE_PRECISIONS:
         raise ValueError("precision must be one of %s" % sorted(FINE_PRECISIONS))
     f1, f2 = _f32c(feat1, "feat1"), _f32c(feat2, "feat2")
@@ -216,7 +222,8 @@ def compute_fine_Rt_fused(feat1, feat2, pts1, pts2, model_pts=None, temp=0.1, di
     with torch.cuda.device(dev):
         _lib.check(L.pem_fine_fused_ex(f1.data_ptr(), f2.data_ptr(), pts1.data_ptr(), pts2.data_ptr(),
                                        model_pts.data_ptr(), B, N1, N2, C, Nm, float(temp),
-                                       float(dis_thres), FINE_PRECISIONS[precision], R.data_ptr(),
+                                       float(dis_thres), FINE_PRECISIONS[precision] | (0x100 if three_pass else 0) |
+                                       ((int(steps_per_task) & 0xff) << 16), R.data_ptr(),
                                        t.data_ptr(), score.data_ptr(), p(w1), p(w2), p(row), p(pred),
                                        ws.data_ptr(), nbytes, _ext._stream()), "pem_fine_fused_ex")
     if return_stages:

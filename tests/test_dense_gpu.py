@@ -199,12 +199,9 @@ def test_score_hypotheses_tensor_core_vs_simt_and_oracle(pkg, oracle, dev, Nm, H
     for b in range(Bn):
         w1[b, torch.randperm(n1, generator=g)[:nfg]] = 1.0
     want = oracle.score_hypotheses(R, t, pts, w1, model)
-    L = ctypes.CDLL(pkg._lib.LIB_PATH)
     args = (R.to(dev), t.to(dev), pts.to(dev), w1.to(dev), model.to(dev))
-    L.pem_dev_set_score_simt(1)
-    simt = pkg.model_utils.score_hypotheses(*args).cpu()
-    L.pem_dev_set_score_simt(0)
-    tc = pkg.model_utils.score_hypotheses(*args).cpu()
+    simt = pkg.model_utils.score_hypotheses(*args, kernel="simt").cpu()
+    tc = pkg.model_utils.score_hypotheses(*args, kernel="tensor").cpu()
     assert torch.equal(tc, pkg.model_utils.score_hypotheses(*args).cpu())   # deterministic sums
     if nfg == 0:
         assert (tc == 0).all() and (simt == 0).all()

@@ -61,14 +61,9 @@ def test_fine_fused_ragged_shapes_and_task_splits(pkg, oracle, dev, B, N1, N2, C
     model = (0.3 * torch.randn(B, 500, 3, generator=g)).contiguous()
     atten = oracle.feature_similarity(f1, f2, 0.1)
     oR, ot, os_, ost = oracle.fine_Rt(atten, p1, p2, model)
-    L = ctypes.CDLL(pkg._lib.LIB_PATH)
-    L.pem_dev_set_fine_steps_per_task(spt)
-    try:
-        R, t, s, st = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), p1.to(dev), p2.to(dev),
-                                                            model.to(dev), 0.1, 0.15, return_stages=True,
-                                                            precision=precision)
-    finally:
-        L.pem_dev_set_fine_steps_per_task(0)
+    R, t, s, st = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), p1.to(dev), p2.to(dev),
+                                                        model.to(dev), 0.1, 0.15, return_stages=True,
+                                                        precision=precision, steps_per_task=spt)
     for k in ("w1", "w2"):
         bad = (st[k].cpu() != ost[k]).float().sum().item()
         assert bad <= max(1.0, 2e-3 * ost[k].numel()), (k, bad)
@@ -99,16 +94,11 @@ def test_fine_fused_two_pass_equals_three_pass(pkg, oracle, dev, n_unrelated, pr
     p1 = (0.3 * torch.randn(B, N, 3, generator=g)).contiguous()
     p2 = (0.3 * torch.randn(B, N, 3, generator=g)).contiguous()
     model = (0.3 * torch.randn(B, 500, 3, generator=g)).contiguous()
-    L = ctypes.CDLL(pkg._lib.LIB_PATH)
     out = {}
-    try:
-        for passes in (3, 2):
-            L.pem_dev_set_fine_passes(passes)
-            out[passes] = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), p1.to(dev), p2.to(dev),
-                                                                model.to(dev), 0.1, 0.15, return_stages=True,
-                                                                precision=precision)
-    finally:
-        L.pem_dev_set_fine_passes(2)
+    for passes in (3, 2):
+        out[passes] = pkg.model_utils.compute_fine_Rt_fused(f1.to(dev), f2.to(dev), p1.to(dev), p2.to(dev),
+                                                            model.to(dev), 0.1, 0.15, return_stages=True,
+                                                            precision=precision, three_pass=passes == 3)
     (R3, t3, s3, st3), (R2, t2, s2, st2) = out[3], out[2]
     assert torch.equal(st3["w1"], st2["w1"]) and torch.equal(st3["w2"], st2["w2"])
     n_bg = int((st2["w2"] == 0).sum(1).max().item())

@@ -1,3 +1,5 @@
+# NOTE: uses pem_dev_* tuning knobs: build the library with `make -C openvino-sam-6d_b200/csrc clean all EXTRA=-DPEM_DEV_KNOBS`
+# (the shipped library keeps these as compile-time constants).
 """Fused fine kernel: parity vs the oracle + timing, for several row-steps-per-task settings (0 = automatic)."""
 import ctypes, os, sys
 import torch

@@ -1,3 +1,5 @@
+# NOTE: uses pem_dev_* tuning knobs: build the library with `make -C openvino-sam-6d_b200/csrc clean all EXTRA=-DPEM_DEV_KNOBS`
+# (the shipped library keeps these as compile-time constants).
 """Timing experiments on one fine GEMM pass: which role bounds it?
 flags: 1 no MMAs, 2 no streamed TMA loads, 4 no epilogue math.  mode: 1 stats, 4 label + wsum (the merged pass), 2 label, 3 wsum."""
 import ctypes, os, sys

@@ -1,3 +1,5 @@
+# NOTE: uses pem_dev_* tuning knobs: build the library with `make -C openvino-sam-6d_b200/csrc clean all EXTRA=-DPEM_DEV_KNOBS`
+# (the shipped library keeps these as compile-time constants).
 """Kernel timeline of graph-replayed steps (torch profiler / CUPTI): per-kernel warm durations and
 the idle gaps between consecutive kernels on the critical path."""
 import os, sys, json

@@ -7,9 +7,12 @@ A *step* is one pass of the geometric stage (openvino-sam-6d_b200/stage.py) over
 of B synthetic instances per GPU (default B = 16, BASELINE.json configs[1]: coarse 196 / fine
 2048 points, 6000 -> 300 hypotheses, 1024 model points).  Prints ONE JSON line on rank 0.
 
-  value        instances/s, whole job, inputs resident in HBM, CUDA-event time per step
-               (L2 flushed by a 256 MB memset between steps, outside the timed events),
-               max over ranks
+  value        instances/s, whole job, inputs resident in HBM: K steps round-robin over --in-flight (3) batches
+               in flight (one stage replica, streams and CUDA graph per batch; the latency-bound coarse chain
+               of one batch runs under the bulk kernels of the others), one CUDA-event pair around the K
+               steps, max over ranks.  No L2 flush inside that region: the batches in flight are distinct
+               and far larger than L2 (config.l2).  single_batch = the same step with ONE batch in flight
+               (the step's latency; L2 flushed between steps)
   e2e          the same through the host-facing call: pinned host inputs -> H2D -> stage ->
                D2H of the 64-byte pose records, all inside the timed region
   roofline     the dominant kernel (the fine-stage tcgen05 GEMM) timed with CUDA events on its launch
@@ -57,7 +60,10 @@ def workload_config(args, world):
         "instances_per_gpu": args.batch, "n_gpus": world, "n_dense": 2048, "n_sparse": 196,
         "feat_dim": 256, "n_model": 1024, "n_proposal1": 6000, "n_proposal2": 300,
         "parallelism": "instance-sharded dp%d, pose-record gather" % world,
-        "l2": "flushed between timed steps (256 MB memset outside the event pair)",
+        "l2": "no flush inside the timed region: %d batches in flight on distinct instances, each step reads 70 MB "
+              "of inputs and writes 150 MB of PE groups (working set %d x ~330 MB >> 126 MB L2); "
+              "single_batch: flushed between steps" % (getattr(args, "in_flight", 3), getattr(args, "in_flight", 3)),
+        "batches_in_flight": getattr(args, "in_flight", 3),
         "fine_gemm": getattr(args, "fine_precision", "fp16") + " tcgen05 (fp32 accumulation; pose parity bars "
                      "0.1 deg / 1e-4 asserted for this mode on the bench batch, tests/test_bench_batch_gpu.py)",
     }
@@ -164,13 +170,21 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     numa_cores = pkg.parallel.bind_to_gpu_numa(local_rank) if world > 1 else None
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    ids = [rank * B + i for i in range(B)]
+    B, K, W, D = args.batch, args.steps, max(args.warmup, 3), max(1, args.in_flight)
+    # D batches in flight: one stage replica (input slots, streams, CUDA graph) per batch, distinct instances.
+    # Replica 0 holds this rank's ids rank*B*D .. (+B): the instances the CPU leg and parity_in_bench look at.
+    stages, gathers, ids0 = [], [], None
+    for d in range(D):
+        ids = [(rank * D + d) * B + i for i in range(B)]
+        st_ = pkg.stage.GeometricStage(B, dev, fine_precision=args.fine_precision)
+        st_.instance_ids.copy_(torch.tensor(ids, dtype=torch.float32))
+        st_.load(pkg.synth.make_batch(ids))
+        stages.append(st_)
+        gathers.append(pkg.parallel.RecordGather(st_, rank, world, mode=args.record_gather))
+        if d == 0:
+            ids0 = ids
+    stage, gather, ids = stages[0], gathers[0], ids0
     host = pkg.synth.make_batch(ids)
-    stage = pkg.stage.GeometricStage(B, dev, fine_precision=args.fine_precision)
-    stage.instance_ids.copy_(torch.tensor(ids, dtype=torch.float32))
-    stage.load(host)
-    gather = pkg.parallel.RecordGather(stage, rank, world, mode=args.record_gather)
 
     def step_collective(s_=stage, g_=gather):
         # the only multi-GPU traffic: the 64-byte pose records of every rank into one table
@@ -179,22 +193,44 @@ def run_b200(args, rank, world, local_rank):
                 g_.run()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cur = torch.cuda.current_stream(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- value: inputs resident, per-step CUDA events on the launch stream -------------
+    def pipelined(n_steps):
+        """n_steps steps round-robin over the D replicas (each on its own streams); one event pair on the
+        current stream around all of them.  Returns device ms."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for s_ in stages:
+            s_.stream.wait_event(e0)
+        for k in range(n_steps):
+            s_ = stages[k % D]
+            s_.run()
+            step_collective(s_, gathers[k % D])
+        for s_ in stages:
+            cur.wait_stream(s_.stream)
+        e1.record(cur)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1)
+
+    # ---- value: inputs resident, D batches in flight, one CUDA-event pair around the K steps ------------
     clocks = ClockSampler(local_rank)
     clocks.start()
-    for _ in range(W):
-        stage.run()
-        step_collective()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    pipelined(W * D)
     barrier()
     wall0 = time.perf_counter()
+    dev_ms = pipelined(K)
+    barrier()
+    wall = time.perf_counter() - wall0
+    records_dev = stage.records.clone()
+
+    # ---- the same step with ONE batch in flight (its latency): L2 flushed between steps, per-step events ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
     for k in range(K):
         with torch.cuda.stream(stage.stream):
             flush.zero_()
@@ -203,9 +239,7 @@ def run_b200(args, rank, world, local_rank):
         step_collective()
         ev[k][1].record(stage.stream)
     barrier()
-    wall = time.perf_counter() - wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    records_dev = stage.records.clone()
+    single_ms = sum(a.elapsed_time(b) for a, b in ev)
 
     # ---- e2e: pinned host -> H2D -> stage -> D2H records, all inside the timed region --------
     # through the host-facing PipelinedStage (two replicas: copies of batch k+1 overlap batch k)
@@ -240,13 +274,18 @@ def run_b200(args, rank, world, local_rank):
     clock_info = clocks.stop()
 
     # ---- sustained: the same step (flush + graph replay + collective) looped for >= sustain seconds -------
-    sustained = sustained_run(args, stage, step_collective, flush, barrier, local_rank)
+    # (every rank must run the SAME number of steps: with the in-graph record gather a step waits for its peers)
+    est = torch.tensor([dev_ms / K], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    sustained = sustained_run(args, pipelined, barrier, local_rank, est.item())
 
     # ---- max over ranks -----------------------------------------------------------------
-    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, sustained["ms_per_step"]], dtype=torch.float64, device=dev)
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, sustained["ms_per_step"], single_ms], dtype=torch.float64,
+                      device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms, sus_ms = tt.tolist()
+    dev_ms, e2e_ms, wall_ms, sus_ms, single_ms = tt.tolist()
     # ---- BASELINE configs[3]: hypothesis-scoring sweep, every rank scores its own 16 instances -----
     sweep = scoring_sweep(pkg, stage, dev, world, barrier) if not args.no_extra else None
     if rank != 0:
@@ -264,7 +303,11 @@ def run_b200(args, rank, world, local_rank):
                 "upload": pipe.upload_note()},
         "gpu_launches": stage.kernels_per_step * K,
         "launches_per_step": stage.kernels_per_step,
-        "wall_ms_per_step_incl_flush": wall_ms / K,
+        "wall_ms_per_step": wall_ms / K,
+        "batches_in_flight": D,
+        "single_batch": {"ms_per_step": single_ms / K, "value": total / (single_ms / 1e3),
+                         "how": "ONE batch in flight (the step's latency): L2 flushed by a 256 MB memset between "
+                                "steps, outside the per-step event pairs"},
         "clocks": clock_info,
         "record_gather": gather.how,
         "host_cores_bound": len(numa_cores) if numa_cores else None,
@@ -272,6 +315,9 @@ def run_b200(args, rank, world, local_rank):
     fp32 = fp32_peak(pkg, stage, dev)
     line["roofline"] = dominant_kernel_roofline(pkg, stage, flush)
     extra = {"sustained": sustained, "fp32_peak": fp32}
+    for g_ in gathers:
+        if g_.timed_out():
+            raise RuntimeError("a pose-record gather gave up waiting for a peer")
     if not args.no_extra:
         extra["kernels"] = kernel_table(pkg, stage, fp32, line["roofline"])
         extra["configs3_scoring_sweep"] = sweep
@@ -318,38 +364,19 @@ def parity_in_bench(cpu_result, records, cpu_result_e2e, e2e_records, upload):
     return out
 
 
-def sustained_run(args, stage, step_collective, flush, barrier, local_rank):
-    """The timed step looped back to back for >= --sustain-seconds of device time: the figure at the clocks the
-    GPU HOLDS under this load (the K-step `value` is a burst of a few ms at full boost)."""
+def sustained_run(args, pipelined, barrier, local_rank, ms_est):
+    """The timed loop (same batches in flight) run for >= --sustain-seconds of device time: the figure at the
+    clocks the GPU HOLDS under this load (the K-step `value` is a burst of ~0.1 s at full boost)."""
     barrier()
     clocks = ClockSampler(local_rank, period_ms=50)
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ms_est = 0.6
-    n = max(200, int(args.sustain_seconds * 1e3 / ms_est))
-    e0.record(stage.stream)
-    for _ in range(n):
-        with torch.cuda.stream(stage.stream):
-            flush.zero_()
-        stage.run()
-        step_collective()
-    e1.record(stage.stream)
+    n = max(200, int(args.sustain_seconds * 1e3 / max(ms_est, 0.05)))
+    total_ms = pipelined(n)
     barrier()
-    total_ms = e0.elapsed_time(e1)
-    # the flushes are inside this loop's event pair: time them alone and take them out
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stage.stream):
-        f0.record(stage.stream)
-        for _ in range(50):
-            flush.zero_()
-        f1.record(stage.stream)
-    stage.stream.synchronize()
-    flush_ms = f0.elapsed_time(f1) / 50
     info = clocks.stop()
-    return {"steps": n, "seconds": total_ms / 1e3, "ms_per_step": total_ms / n - flush_ms,
-            "ms_per_step_incl_flush": total_ms / n, "flush_ms": flush_ms, "clocks": info,
-            "how": "graph replays back to back with the L2 flush between them, one event pair around the whole "
-                   "loop, the separately timed flush subtracted"}
+    return {"steps": n, "seconds": total_ms / 1e3, "ms_per_step": total_ms / n, "clocks": info,
+            "how": "the timed loop of `value` (graph replays round-robin over the batches in flight), one event "
+                   "pair around all steps"}
 
 
 def _peaks():
@@ -725,6 +752,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-kernel table, the sweep and the microbench")
     ap.add_argument("--sustain-seconds", type=float, default=2.0)
+    ap.add_argument("--in-flight", type=int, default=3,
+                    help="batches in flight in the `value` loop (one stage replica, streams and CUDA graph each); "
+                         "1 = one batch at a time")
     ap.add_argument("--e2e-upload", default="fp16", choices=["fp16", "fp32"],
                     help="feature upload format of the host-facing path (fp16 only with the fp16 fine GEMM)")
     ap.add_argument("--record-gather", default="peer", choices=["peer", "nccl"],

@@ -45,6 +45,7 @@
 // once per block and the running minima wait in shared memory.  The SIMT kernel (coarse.cu) remains
 // for shapes this one does not take (more than 4096 model points or 256 query points).
 #include "tc_ptx.cuh"
+#include <type_traits>
 
 namespace pem {
 namespace tc {
@@ -322,29 +323,37 @@ score_tc_kernel(const float *__restrict__ R, const float *__restrict__ t, const 
                         r0 += kSRows;
                         ++tile_seq;
                     };
+                    // one chunk: wait for its MMAs, load the two 64-column halves (the second load flies under the
+                    // fold of the first), hand the buffer back as soon as both have landed, fold
                     auto take = [&](uint32_t full_bar, uint32_t parity, uint32_t empty_bar, uint32_t col) {
-                        float v[kSChunk];
+                        uint32_t lo[64], hi[64];
                         mbar_wait(full_bar, parity);
                         tc_fence_after();
-                        tmem_ld128(lane_base + col, v);     // (waits for the load)
+                        tmem_ld64_issue(lane_base + col, lo);
+                        tmem_ld64_wait(lo);
+                        tmem_ld64_issue(lane_base + col + 64u, hi);
+                        fold64(lo, m);
+                        tmem_ld64_wait(hi);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty_bar);
-#pragma unroll
-                        for (int q = 0; q < kSChunk; q += 16) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) m[k] = fminf(fminf(m[k], v[q + 2 * k]), v[q + 2 * k + 1]);
-                        }
+                        fold64(hi, m);
                     };
                     if constexpr (FIXED) {
-                        for (int tl = 0; tl < n_tiles; ++tl) {
+                        // chunk c = 2 j + part of a tile: buffer c & 3, parity c >> 2 -- constants once `part` is one
+                        auto tiles = [&](auto part_tag) {
+                            constexpr int PART = decltype(part_tag)::value;
+                            for (int tl = 0; tl < n_tiles; ++tl) {
 #pragma unroll
-                            for (int j = 0; j < kSFixedChunks / 2; ++j) {
-                                const uint32_t slot = (uint32_t)((2 * j + part) & 3);   // chunk c = 2 j + part
-                                take(full0 + 8u * slot, (uint32_t)((j >> 1) & 1), empty0 + 8u * slot, slot * kSChunk);
+                                for (int j = 0; j < kSFixedChunks / 2; ++j) {
+                                    const uint32_t slot = (uint32_t)((2 * j + PART) & 3);
+                                    take(full0 + 8u * slot, (uint32_t)((j >> 1) & 1), empty0 + 8u * slot, slot * kSChunk);
+                                }
+                                finish_tile();
                             }
-                            finish_tile();
-                        }
+                        };
+                        if (part == 0) tiles(std::integral_constant<int, 0>{});
+                        else tiles(std::integral_constant<int, 1>{});
                     } else {
                         for (int tl = 0; tl < n_tiles; ++tl) {
                             for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {

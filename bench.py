@@ -7,7 +7,7 @@ A *step* is one pass of the geometric stage (openvino-sam-6d_b200/stage.py) over
 of B synthetic instances per GPU (default B = 16, BASELINE.json configs[1]: coarse 196 / fine
 2048 points, 6000 -> 300 hypotheses, 1024 model points).  Prints ONE JSON line on rank 0.
 
-  value        instances/s, whole job, inputs resident in HBM: K steps round-robin over --in-flight (3) batches
+  value        instances/s, whole job, inputs resident in HBM: K steps round-robin over --in-flight (4) batches
                in flight (one stage replica, streams and CUDA graph per batch; the latency-bound coarse chain
                of one batch runs under the bulk kernels of the others), one CUDA-event pair around the K
                steps, max over ranks.  No L2 flush inside that region: the batches in flight are distinct
@@ -62,8 +62,8 @@ def workload_config(args, world):
         "parallelism": "instance-sharded dp%d, pose-record gather" % world,
         "l2": "no flush inside the timed region: %d batches in flight on distinct instances, each step reads 70 MB "
               "of inputs and writes 150 MB of PE groups (working set %d x ~330 MB >> 126 MB L2); "
-              "single_batch: flushed between steps" % (getattr(args, "in_flight", 3), getattr(args, "in_flight", 3)),
-        "batches_in_flight": getattr(args, "in_flight", 3),
+              "single_batch: flushed between steps" % (getattr(args, "in_flight", 4), getattr(args, "in_flight", 4)),
+        "batches_in_flight": getattr(args, "in_flight", 4),
         "fine_gemm": getattr(args, "fine_precision", "fp16") + " tcgen05 (fp32 accumulation; pose parity bars "
                      "0.1 deg / 1e-4 asserted for this mode on the bench batch, tests/test_bench_batch_gpu.py)",
     }
@@ -752,7 +752,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-kernel table, the sweep and the microbench")
     ap.add_argument("--sustain-seconds", type=float, default=2.0)
-    ap.add_argument("--in-flight", type=int, default=3,
+    ap.add_argument("--in-flight", type=int, default=4,
                     help="batches in flight in the `value` loop (one stage replica, streams and CUDA graph each); "
                          "1 = one batch at a time")
     ap.add_argument("--e2e-upload", default="fp16", choices=["fp16", "fp32"],

@@ -845,6 +845,164 @@ pe_group2_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Masked PE grouping, one WARP per centre (round 2).  pe_group2_kernel<.., MASKED> walks the candidate
+// masks with one thread per (centre, quarter tile): its bit loops diverge over 32 different centres and
+// every tile costs two CTA barriers, ~500 warp instructions per centre.  Here a warp owns a centre: lane l
+// takes the mask words of columns [l * wpl * 32, (l + 1) * wpl * 32) (one coalesced 256-byte read per centre
+// at N = 2048), re-tests its set bits exactly, and the hits are compacted in index order by one packed
+// warp scan; the neighbour rows then leave with the lanes along the neighbour axis (128-byte stores).
+// Same arithmetic, same "first nsample hits in index order, back-fill with the first, none -> 0" rule.
+// ------------------------------------------------------------------------------------
+constexpr int kPwWarps = 8;       // warps per CTA
+constexpr int kPwPerWarp = 8;     // centres per warp
+constexpr int kPwCentres = kPwWarps * kPwPerWarp;
+constexpr int kPwCand = 256;      // candidates per round of a centre (index-ordered list in shared memory)
+// kPwMaxWpl = mask words per lane (1, 2 or 4: N <= 1024, 2048, 4096), a template argument so that the
+// per-lane word arrays stay as small as the cloud needs: <= 51 registers keep five CTAs on an SM and the
+// 512 CTAs of 16 clouds x 2048 centres in ONE wave (at 64 registers they took two)
+// NS1 / NS2: the neighbour counts as compile-time constants (0 = take the run-time arguments): the PEM pair
+// (32, 64) unrolls the output loops and keeps the plane offsets in immediates.
+template <int kPwMaxWpl, int NS1, int NS2>
+__global__ void __launch_bounds__(32 * kPwWarps, kPwMaxWpl <= 2 ? 5 : 4)
+pe_group2_warp_kernel(const float *__restrict__ xyz, int N, float eps, float r2a, int ns1_rt,
+                      float *__restrict__ out1, float r2b, int ns2_rt, float *__restrict__ out2,
+                      const uint32_t *__restrict__ cmask, int W, int32_t *__restrict__ idx1,
+                      int32_t *__restrict__ idx2) {
+    extern __shared__ float4 s_dyn[];
+    const int ns1 = NS1 ? NS1 : ns1_rt, ns2 = NS2 ? NS2 : ns2_rt;
+    // the cloud, one spare entry after every lane's share of 32 * wpl points: lane l's candidates then start at
+    // bank group (l + bit) mod 8 instead of all lanes in one (their shares are a multiple of 1 KB apart).
+    // Candidate list and neighbour rows hold these PADDED positions (column + owning lane).
+    constexpr int lg = kPwMaxWpl == 1 ? 0 : kPwMaxWpl == 2 ? 1 : 2, wpl = kPwMaxWpl;  // mask words per lane
+    constexpr int share = 32 * wpl;
+    auto P = [&](int k_) { return k_ + (k_ >> (5 + lg)); };
+    auto unP = [&](int pk) { return pk - pk / (share + 1); };   // (only where indices leave the kernel)
+    float4 *s_pts = s_dyn;
+    unsigned short *rows = reinterpret_cast<unsigned short *>(s_dyn + P(N) + 1);
+    const int warp = warp_id(), lane = lane_id(), b = blockIdx.y;
+    const int row_len = ns1 + ns2;
+    unsigned short *row1 = rows + warp * row_len, *row2 = row1 + ns1;
+    unsigned short *cand = rows + kPwWarps * row_len + warp * kPwCand;
+    const float *xyz_b = xyz + (size_t)b * N * 3;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const float *p = xyz_b + 3 * (size_t)k;
+        s_pts[P(k)] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    }
+    __syncthreads();
+    const int j_begin = blockIdx.x * kPwCentres + warp * kPwPerWarp;
+    const int j_end = min(N, j_begin + kPwPerWarp);
+    const unsigned below = (1u << lane) - 1u;
+    const int pid0 = lane * share + lane;   // padded position of this lane's first column
+    // the candidate words of the warp's first centre are in flight before the loop; inside it the next
+    // centre's words are fetched before the current one is processed
+    uint32_t cw_next[kPwMaxWpl];
+    auto fetch = [&](int j) {
+        const uint32_t *mrow = cmask + ((size_t)b * N + j) * W + lane * wpl;
+#pragma unroll
+        for (int w = 0; w < kPwMaxWpl; ++w) cw_next[w] = (lane * wpl + w < W) ? __ldg(mrow + w) : 0u;
+    };
+    if (j_begin < j_end) fetch(j_begin);
+    for (int j = j_begin; j < j_end; ++j) {
+        uint32_t cw[kPwMaxWpl];
+#pragma unroll
+        for (int w = 0; w < kPwMaxWpl; ++w) cw[w] = cw_next[w];
+        if (j + 1 < j_end) fetch(j + 1);
+        const float4 c = s_pts[P(j)];
+        const float qx = __fadd_rn(c.x, eps), qy = __fadd_rn(c.y, eps), qz = __fadd_rn(c.z, eps);
+        // Lanes = candidates.  The set bits are first laid out as an index-ordered list (a lane's share of the
+        // columns is contiguous, so one scan over the lanes' counts orders them), then 32 candidates at a time
+        // go through the exact test; the hit ballots are already in index order, so a hit's slot is the running
+        // total plus the hits below its lane.  (The per-lane bit loops that remain only COPY positions: ~2 per
+        // lane; walking the masks with one lane per centre-share cost 760 warp instructions per centre.)
+        int n = 0;
+#pragma unroll
+        for (int w = 0; w < kPwMaxWpl; ++w) n += __popc(cw[w]);
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int ncand = __shfl_sync(kFull, incl, 31), first_rank = incl - n;
+        int base1 = 0, base2 = 0;
+        for (int lo = 0; lo < ncand && (base1 < ns1 || base2 < ns2); lo += kPwCand) {
+            if (ncand <= kPwCand) {  // the whole list at once (the rule)
+                unsigned short *dst = cand + first_rank;
+#pragma unroll
+                for (int w = 0; w < kPwMaxWpl; ++w) {
+                    uint32_t cm = cw[w];
+                    while (cm != 0u) {
+                        *dst++ = (unsigned short)(pid0 + w * 32 + __ffs(cm) - 1);
+                        cm &= cm - 1u;
+                    }
+                }
+            } else if (first_rank < lo + kPwCand && first_rank + n > lo) {  // ranks [lo, lo + kPwCand)
+                int rank = first_rank;
+#pragma unroll
+                for (int w = 0; w < kPwMaxWpl; ++w) {
+                    uint32_t cm = cw[w];
+                    while (cm != 0u) {
+                        const int u = __ffs(cm) - 1;
+                        cm &= cm - 1u;
+                        if (rank >= lo && rank < lo + kPwCand) cand[rank - lo] = (unsigned short)(pid0 + w * 32 + u);
+                        ++rank;
+                    }
+                }
+            }
+            __syncwarp();
+            const int cnt = min(kPwCand, ncand - lo);
+            for (int c0 = 0; c0 < cnt && (base1 < ns1 || base2 < ns2); c0 += 32) {
+                const int i = c0 + lane;
+                const bool valid = i < cnt;
+                const int pc = valid ? cand[i] : 0;
+                const float4 p = s_pts[pc];
+                const float d2 = sqdist_unfused(qx, qy, qz, p.x, p.y, p.z);
+                const bool hit1 = valid && d2 < r2a, hit2 = valid && d2 < r2b;
+                const unsigned m1 = __ballot_sync(kFull, hit1), m2 = __ballot_sync(kFull, hit2);
+                const int r1 = base1 + __popc(m1 & below), r2 = base2 + __popc(m2 & below);
+                if (hit1 && r1 < ns1) row1[r1] = (unsigned short)pc;
+                if (hit2 && r2 < ns2) row2[r2] = (unsigned short)pc;
+                base1 += __popc(m1);
+                base2 += __popc(m2);
+            }
+            __syncwarp();  // the list is rewritten by the next round
+        }
+        const int tot1 = min(base1, ns1), tot2 = min(base2, ns2);
+        // back-fill with the first hit; no hit -> point 0 (padded position 0)
+        {
+            const unsigned short f1 = tot1 ? row1[0] : (unsigned short)0, f2 = tot2 ? row2[0] : (unsigned short)0;
+            for (int l = tot1 + lane; l < ns1; l += 32) row1[l] = f1;
+            for (int l = tot2 + lane; l < ns2; l += 32) row2[l] = f2;
+        }
+        __syncwarp();
+        // outputs: lanes along the neighbour axis
+        auto emit = [&](const unsigned short *rw, int nss, float *ob, int32_t *io) {
+            if (io) {
+                int32_t *ib = io + ((size_t)b * N + j) * nss;
+                for (int l = lane; l < nss; l += 32) ib[l] = unP(rw[l]);
+            }
+            if (ob == nullptr) return;
+            const int plane = N * nss;   // (N <= 4096, nss <= 128: 6 planes fit 32-bit offsets)
+            float *o = ob + (size_t)b * 6 * plane + (size_t)j * nss + lane;
+#pragma unroll
+            for (int l = 0; l < 128; l += 32) {   // nsample <= 128
+                if (l + lane >= nss) break;
+                const float4 p = s_pts[rw[l + lane]];
+                o[l] = __fsub_rn(p.x, qx);
+                o[plane + l] = __fsub_rn(p.y, qy);
+                o[2 * plane + l] = __fsub_rn(p.z, qz);
+                o[3 * plane + l] = p.x;
+                o[4 * plane + l] = p.y;
+                o[5 * plane + l] = p.z;
+            }
+        };
+        emit(row1, ns1, out1, idx1);
+        emit(row2, ns2, out2, idx2);
+        __syncwarp();  // the rows are rewritten by the next centre
+    }
+}
+
 static size_t bq_smem_bytes(int ns) {
     return (size_t)kBqTile * sizeof(float4) + (size_t)kBqCentres * (ns + 1) * sizeof(int);
 }
@@ -1079,16 +1237,21 @@ static int pe_masked_launch(const float *xyz, int B, int N, float centre_eps, fl
     PEM_REQUIRE(B > 0 && N > 0 && nsample1 > 0 && nsample2 > 0 && B <= 65535, PEM_E_SHAPE);
     PEM_REQUIRE(nsample1 <= 128 && nsample2 <= 128 && N <= 4096, PEM_E_UNSUPPORTED);  // cloud in smem
     PEM_REQUIRE(masks_bytes >= pem_pe_masks_bytes(B, N), PEM_E_WORKSPACE);
-    const size_t n_pts = (size_t)(N + kPeTile - 1) / kPeTile * kPeTile;
-    const size_t smem = n_pts * sizeof(float4) +
-                        (size_t)kPeCentres * (nsample1 + 2 + nsample2 + 2) * sizeof(unsigned short);
-    static PemSmemCache cached(0);
-    if (int rc = pem_ensure_dyn_smem(pe_group2_kernel<true, true>, smem, &cached)) return rc;
-    pe_group2_kernel<true, true><<<dim3((N + kPeCentres - 1) / kPeCentres, B), kPeThreads, smem,
-                                  pem_cu_stream(stream)>>>(xyz, N, centre_eps, radius1 * radius1, nsample1, out1,
-                                                           radius2 * radius2, nsample2, out2,
-                                                           (const uint32_t *)masks, (N + 31) / 32, idx1, idx2);
-    return pem_launch_status();
+    const int W = (N + 31) / 32;
+    const size_t smem = (size_t)(N + 32 + 2) * sizeof(float4) +
+                        (size_t)kPwWarps * (nsample1 + nsample2 + kPwCand) * sizeof(unsigned short);
+    auto go = [&](auto kern, PemSmemCache *cache) {
+        if (int rc = pem_ensure_dyn_smem(kern, smem, cache)) return rc;
+        kern<<<dim3((N + kPwCentres - 1) / kPwCentres, B), 32 * kPwWarps, smem, pem_cu_stream(stream)>>>(
+            xyz, N, centre_eps, radius1 * radius1, nsample1, out1, radius2 * radius2, nsample2, out2,
+            (const uint32_t *)masks, W, idx1, idx2);
+        return pem_launch_status();
+    };
+    static PemSmemCache c1(0), c2(0), c2pe(0), c4(0);
+    if (W <= 32) return go(pe_group2_warp_kernel<1, 0, 0>, &c1);
+    if (W <= 64 && nsample1 == 32 && nsample2 == 64) return go(pe_group2_warp_kernel<2, 32, 64>, &c2pe);  // the PEM shape
+    if (W <= 64) return go(pe_group2_warp_kernel<2, 0, 0>, &c2);
+    return go(pe_group2_warp_kernel<4, 0, 0>, &c4);
 }
 
 extern "C" int pem_pe_group2_masked(const float *xyz, int B, int N, float centre_eps, float radius1,

@@ -78,6 +78,14 @@ def test_argument_validation_without_gpu(pkg):
     assert lib.pem_fine_fused_ex(p, p, p, p, p, 1, 8, 8, 100, 8, 0.1, 0.15, 1, p, p, p, None, None, None, None, p,
                                  1 << 30, None) == -3
     assert lib.pem_fine_fused_pass_ex(p, p, 1, 8, 8, 64, 0.1, 1, 5, p, 1 << 30, None) == -3
+    # option bits on the precision word: PEM_FINE_THREE_PASS = 0x100, PEM_FINE_STEPS_PER_TASK(n) = n << 16; others rejected
+    assert lib.pem_fine_fused_ex(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, 1 | 0x200, p, p, p, None, None, None, None,
+                                 p, 1 << 30, None) == -3
+    assert lib.pem_fine_fused_ex(p, p, p, p, p, 1, 8, 8, 64, 8, 0.1, 0.15, 1 | 0x100 | (2 << 16), p, p, p, None, None,
+                                 None, None, p, 16, None) == -4      # options accepted: stops at the workspace check
+    # the scoring kernel named by the caller: 0 auto, 1 SIMT, 2 tensor cores
+    assert lib.pem_score_hypotheses_ex(p, p, None, 1, 8, 8, p, p, 4, p, 16, p, 3, None) == -2
+    assert lib.pem_score_hypotheses_ex(p, p, None, 1, 8, 8, p, p, 300, p, 16, p, 0, None) == -3   # > 256 query points
     # instance preparation
     assert lib.pem_instance_scratch_bytes(3, 480, 640) == 3 * 480 * 640 * 4
     assert lib.pem_backproject_depth(p, 4, 4, 1.0, 1.0, 0.0, 0.0, 2, p, None) == -3     # precision is 0 or 1

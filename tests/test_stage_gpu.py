@@ -47,3 +47,37 @@ def test_stage_matches_cpu_reference(pkg, oracle, dev, cpu_result, use_graph, fi
     rec = stage.records.cpu()
     assert torch.equal(rec[:, :9], R.reshape(B, 9).cpu()) and torch.equal(rec[:, 12], s.cpu())
     assert stage.kernels_per_step > 20
+
+
+def test_pipelined_stage_with_half_precision_upload(pkg, oracle, dev):
+    """The host-facing path of bench.py's `e2e` figure: PipelinedStage(upload="fp16") takes the caller's features in
+    half precision (half the bytes on the link) and widens them on the device.  Parity is against the reference fed
+    the SAME fp16-representable features (PipelinedStage.as_uploaded); two different batches alternate over the two
+    replicas so that the per-batch background token and instance data really follow the upload."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import cpu_stage
+    B = 2           # reference shapes (the north_star bars are stated for them)
+    kw, gen = {}, {}
+    batches = [pkg.synth.make_batch(list(range(g0, g0 + B)), **gen) for g0 in (100, 200)]
+    pipe = pkg.stage.PipelinedStage(B, dev, depth=2, upload="fp16", **kw)
+    pins = [pipe.pin_inputs(b) for b in batches]
+    assert pins[0]["feats"].dtype == torch.float16
+    with pytest.raises(RuntimeError):
+        pkg.stage.PipelinedStage(B, dev, depth=1, upload="fp32", **kw).submit(pins[0])   # dtype must match the mode
+    got = []
+    for k in range(4):
+        if len(pipe.inflight) == len(pipe.stages):      # (submit() would collect -- and drop -- the oldest itself)
+            got.append(pipe.collect().clone())
+        pipe.submit(pins[k % 2])
+    while pipe.inflight:
+        got.append(pipe.collect().clone())
+    assert len(got) == 4 and torch.equal(got[0], got[2]) and torch.equal(got[1], got[3])
+    for k in range(2):
+        ref_in = pkg.stage.PipelinedStage.as_uploaded(batches[k], "fp16")
+        oR, ot, os_, _ = cpu_stage.run_stage_cpu(ref_in, faithful=False)
+        rec = got[k]
+        R, t, s = rec[:, :9].reshape(B, 3, 3), rec[:, 9:12], rec[:, 12]
+        assert oracle.rotation_angle_deg(R, oR).max().item() < 0.1
+        assert (t - ot).abs().max().item() < 1e-4
+        assert (s - os_).abs().max().item() < 2e-3

@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpem_b200.so")
+# PEM_B200_LIB: load a side build of the same sources instead (A/B timing of kernel variants, tools/ only)
+LIB_PATH = os.environ.get("PEM_B200_LIB") or os.path.join(_HERE, "libpem_b200.so")
 _lib = None
 
 c_p = ctypes.c_void_p

@@ -103,8 +103,30 @@ struct Params {
     // ragged passes (the background-column correction): strips >= strip_count[b] are skipped
     const int *strip_count;
     int strip_major;       // task order: strips outermost
-    int dev;               // timing experiments: 1 no MMAs, 2 no streamed loads, 4 no epilogue math
+    int early;             // 1: the operands are older than the predecessor grid (it only produced epilogue constants), so the
+                           // producer and the issuer start under its tail instead of parking in pdl_enter()
+    long long *trace;      // PEM_TRACE buffer (dev builds), else null
+    int dev;               // timing experiments: 1 no MMAs, 2 no streamed loads, 4 no epilogue math; on top of 1|2|4 only:
+                           // 16 no ring hand-shake, 32 no accumulator hand-shake; 64 alone: the generic loops instead
+                           // of the unrolled producer / issuer (A/B); 128 statistics pass without MUFU (x*x for 2^x),
+                           // 256 without column sums (dev builds only).  1, 2, 4, 128, 256 keep the unrolled form
 };
+
+// Device-side timeline of CTA 0 (-DPEM_DEV_KNOBS builds, tools/pass_trace.py): role r appends (tag, clock64) pairs
+// to trace[r][..]; compiled out of the shipped library.
+constexpr int kTraceLen = 512;
+#ifdef PEM_DEV_KNOBS
+#define PEM_TRACE(role, tag)                                                          \
+    do {                                                                              \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < kTraceLen) {         \
+            p.trace[((role)*kTraceLen + trace_n) * 2] = (tag);                        \
+            p.trace[((role)*kTraceLen + trace_n) * 2 + 1] = clock64();                \
+            ++trace_n;                                                                \
+        }                                                                             \
+    } while (0)
+#else
+#define PEM_TRACE(role, tag) do { } while (0)
+#endif
 
 struct Smem {
     // operand buffers first: SWIZZLE_128B needs 1024-byte alignment
@@ -153,7 +175,13 @@ __device__ __forceinline__ Task decode_task(const Params &p, int task) {
     return t;
 }
 
-template <int MODE, int EPW>
+// FAST: the single-product mode at C = 256 (four K chunks) with an EIGHT-slot ring, i.e. exactly two row steps of
+// streamed chunks: the slots, barriers and TMEM buffer of a step follow from its parity, so the producer's and the
+// issuer's K-chunk loops unroll with every shared-memory address, descriptor and barrier parity a constant plus one
+// per-step offset.  (The generic loops below cost the issuing warp ~90 dependent instructions, 460-750 clocks, per
+// K chunk -- device timeline, tools/pass_trace.py -- against 512 clocks of MMAs: the issuer, not the tensor pipe,
+// the loads or the epilogue, bounded the single-product passes.)
+template <int MODE, int EPW, bool FAST = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const Params p) {
@@ -167,8 +195,9 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id(), lane = lane_id();
     const int crank = (int)cluster_ctarank();  // 0 = leader CTA of the pair
+    [[maybe_unused]] int trace_n = 0;
     // the streamed ring: a[0..4], or b_lo[0..3] + a[0..4] (contiguous) when there is no lo operand
-    const int n_stages = p.single ? min(kMaxStages, max(2, p.ring)) : kStages;
+    const int n_stages = FAST ? 8 : p.single ? min(kMaxStages, max(2, p.ring)) : kStages;
     const uint32_t ring0 = p.single ? smem_u32(sm.b_lo[0]) + (uint32_t)(kMaxStages - n_stages) * kChunkBytes
                                     : smem_u32(sm.a[0]);
     const int n_tasks = p.B * p.n_strips * p.n_splits;
@@ -201,12 +230,102 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     cluster_sync_all();  // the peer's barriers and TMEM exist before anything targets them
-    pdl_enter();         // everything above is local; global memory is touched only below
+#ifdef PEM_DEV_KNOBS
+    long long cta_t0 = 0, cta_g0 = 0, cta_t1 = 0, cta_g1 = 0;
+    if (p.trace && threadIdx.x == 0) { cta_t0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0)); }
+#endif
+    // everything above is local; global memory is touched only below.  Params::early: the loads and MMAs of the
+    // first two row steps run while the predecessor (a finish kernel) is still writing the per-row / per-column
+    // constants that only the epilogue warps read
+    if (p.early && warp < 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else pdl_enter();
+#ifdef PEM_DEV_KNOBS
+    if (p.trace && threadIdx.x == 0) { cta_t1 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g1)); }
+#endif
 
     // Both single-issuer roles run with warp-uniform control flow (all 32 lanes loop and wait);
     // only the instruction issue is predicated on an elected lane, so addresses and
     // descriptors stay in uniform registers (no per-instruction uniformisation loops).
-    if (warp == 0) {
+    if (FAST && warp == 0) {
+        // ================================ TMA producer, unrolled ======================
+        uint32_t it = 0, b_phase = 0;  // row steps issued so far (slot set = parity, ring phase = bit 1)
+        const uint32_t full0 = smem_u32(&sm.full[0]) & kPeerBitMask, empty0 = smem_u32(&sm.empty[0]);
+        const uint32_t bfull0 = smem_u32(&sm.b_full[0]) & kPeerBitMask, bempty0 = smem_u32(&sm.b_empty[0]);
+        const uint32_t bdst0 = smem_u32(sm.b_hi[0]);
+        for (int task = task0; task < n_tasks; task += task_step) {
+            const Task t = decode_task(p, task);
+            if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;  // ragged pass: nothing there
+            const int rowB = t.b * p.Np + t.n * TN + crank * BN;
+            for (int m = t.m0; m < t.m1; ++m, ++it) {
+                const int rowA = t.b * p.Mp + m * TM + crank * BM;
+                const uint32_t half = it & 1u, ph = (it >> 1) & 1u;
+                const uint32_t dst = ring0 + half * (4u * kChunkBytes);
+                if (elect_one()) {  // one lane walks the whole step: waits, expect_tx and the bulk loads
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        if (m == t.m0) {  // replace chunk kc of the resident strip
+                            mbar_wait(bempty0 + 8u * kc, b_phase ^ 1);
+                            if (crank == 0) mbar_expect_tx(bfull0 + 8u * kc, 2u * kChunkBytes);
+                            tma_load_2d_pair(&tmB, bfull0 + 8u * kc, bdst0 + (uint32_t)kc * kChunkBytes, kc * BK, rowB);
+                        }
+                        mbar_wait(empty0 + half * 32u + 8u * kc, ph ^ 1);
+                        const uint32_t bar = full0 + half * 32u + 8u * kc;
+#ifdef PEM_DEV_KNOBS
+                        if (p.dev & 2) { if (crank == 0) mbar_arrive(bar); continue; }  // probe: no streamed loads
+#endif
+                        if (crank == 0) mbar_expect_tx(bar, 2u * kChunkBytes);
+                        tma_load_2d_pair(&tmA, bar, dst + (uint32_t)kc * kChunkBytes, kc * BK, rowA);
+                    }
+                }
+                __syncwarp();
+            }
+            b_phase ^= 1;
+        }
+    } else if (FAST && warp == 1) {
+        // ================================ MMA issuer (leader CTA), unrolled ===========
+        if (crank == 0) {
+            uint32_t it = 0, b_phase = 0;
+            const uint32_t a_lo0 = (ring0 >> 4) | (1u << 16), b_lo0 = (smem_u32(sm.b_hi[0]) >> 4) | (1u << 16);
+            const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+            const uint32_t bfull0 = smem_u32(&sm.b_full[0]), bempty0 = smem_u32(&sm.b_empty[0]);
+            const uint32_t tfull0 = smem_u32(&sm.tmem_full[0]), tempty0 = smem_u32(&sm.tmem_empty[0]);
+            constexpr uint32_t idesc = make_idesc_f16(TM, TN);
+            for (int task = task0; task < n_tasks; task += task_step) {
+                const Task t = decode_task(p, task);
+                if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;
+                for (int m = t.m0; m < t.m1; ++m, ++it) {
+                    const uint32_t half = it & 1u, ph = (it >> 1) & 1u;
+                    const bool first = m == t.m0, last = m == t.m1 - 1;
+                    mbar_wait(tempty0 + 8u * half, ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + half * (uint32_t)TN;
+                    const uint32_t a_lo = a_lo0 + half * (4u * kChunkBytes >> 4);
+                    if (elect_one()) {  // one lane walks the whole step: waits, MMAs and commits
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            if (first) mbar_wait(bfull0 + 8u * kc, b_phase);
+                            mbar_wait(full0 + half * 32u + 8u * kc, ph);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes per K = 16 step: +2 in the address field
+                                const uint32_t ao = a_lo + (uint32_t)(kc * (kChunkBytes >> 4) + 2 * k);
+                                const uint32_t bo = b_lo0 + (uint32_t)(kc * (kChunkBytes >> 4) + 2 * k);
+#ifdef PEM_DEV_KNOBS
+                                if (p.dev & 1) continue;  // probe: no MMAs
+#endif
+                                if (kc == 0 && k == 0) tc_mma_f16_pair_lo<false>(d, ao, bo, idesc);
+                                else tc_mma_f16_pair_lo<true>(d, ao, bo, idesc);
+                            }
+                            tc_commit_pair(empty0 + half * 32u + 8u * kc);  // frees the slot once these retire
+                            if (last) tc_commit_pair(bempty0 + 8u * kc);     // chunk kc of the strip may be replaced
+                            if (kc == 3) tc_commit_pair(tfull0 + 8u * half); // accumulator ready
+                        }
+                    }
+                    __syncwarp();
+                }
+                b_phase ^= 1;
+            }
+        }
+    } else if (warp == 0) {
         // ================================ TMA producer ================================
         // Every completion is counted on the LEADER's full barriers (it alone arms them, for
         // both CTAs' bytes); a peer completion that lands before the leader's expect_tx only
@@ -217,8 +336,10 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const Task t = decode_task(p, task);
             if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;  // ragged pass: nothing there
             const int rowB = t.b * p.Np + t.n * TN + crank * BN;
+            PEM_TRACE(0, 1);
             for (int m = t.m0; m < t.m1; ++m) {
                 const int rowA = t.b * p.Mp + m * TM + crank * BM;
+                PEM_TRACE(0, 2);
                 for (int kc = 0; kc < p.KC; ++kc) {
                     if (m == t.m0) {  // replace chunk kc of the resident strip
                         mbar_wait(smem_u32(&sm.b_empty[kc]), b_phase ^ 1);
@@ -233,11 +354,11 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __syncwarp();
                     }
                     for (int hl = 0; hl < n_hl; ++hl) {
-                        mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+                        if (!(p.dev & 16)) mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&sm.full[stage]);
                             if (p.dev & 2) {  // timing experiment: no streamed loads
-                                if (crank == 0) mbar_arrive(bar);
+                                if (crank == 0 && !(p.dev & 16)) mbar_arrive(bar);
                             } else {
                                 if (crank == 0) mbar_expect_tx(bar, 2u * kChunkBytes);
                                 tma_load_2d_pair(&tmA, bar & kPeerBitMask, ring0 + (uint32_t)stage * kChunkBytes, kc * BK,
@@ -263,14 +384,17 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const Task t = decode_task(p, task);
                 if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;
                 for (int m = t.m0; m < t.m1; ++m) {
-                    mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
+                    PEM_TRACE(1, 10);
+                    if (!(p.dev & 32)) mbar_wait(smem_u32(&sm.tmem_empty[acc]), acc_phase ^ 1);
+                    PEM_TRACE(1, 11);
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(acc * TN);
                     for (int kc = 0; kc < p.KC; ++kc) {
                         if (m == t.m0) mbar_wait(smem_u32(&sm.b_full[kc]), b_phase);
                         const uint64_t bh = desc(smem_u32(sm.b_hi[kc])), bl = desc(smem_u32(sm.b_lo[kc]));
                         // A_hi chunk: A_hi*B_hi + A_hi*B_lo (single: the only product)
-                        mbar_wait(smem_u32(&sm.full[stage]), phase);
+                        if (!(p.dev & 16)) mbar_wait(smem_u32(&sm.full[stage]), phase);
+                        PEM_TRACE(1, 12 + kc);
                         tc_fence_after();
                         uint64_t ad = desc(ring0 + (uint32_t)stage * kChunkBytes);
                         if (elect_one()) {
@@ -280,10 +404,10 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tc_mma_bf16_pair(d, ad + 2 * k, bh + 2 * k, kIdesc, (kc | k) != 0);
                                 if (n_hl == 2) tc_mma_bf16_pair(d, ad + 2 * k, bl + 2 * k, kIdesc, 1);
                             }
-                            tc_commit_pair(smem_u32(&sm.empty[stage]));  // frees the slot once these retire
+                            if (!(p.dev & 16)) tc_commit_pair(smem_u32(&sm.empty[stage]));  // frees the slot once these retire
                             if (n_hl == 1) {
                                 if (m == t.m1 - 1) tc_commit_pair(smem_u32(&sm.b_empty[kc]));
-                                if (kc == p.KC - 1) tc_commit_pair(smem_u32(&sm.tmem_full[acc]));
+                                if (kc == p.KC - 1 && !(p.dev & 32)) tc_commit_pair(smem_u32(&sm.tmem_full[acc]));
                             }
                         }
                         __syncwarp();
@@ -327,6 +451,8 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const Task t = decode_task(p, task);
             if (p.strip_count && t.n >= __ldg(p.strip_count + t.b)) continue;
             const int b = t.b, n = t.n;
+            [[maybe_unused]] const int trole = warp == 2 ? 2 : 3;
+            if (warp == 2 || warp == 1 + EPW) PEM_TRACE(trole, 40);
             const int j0 = n * TN + half * WC;     // first column of this warp
             const int ncols = min(WC, p.Cn - j0);  // valid columns (<= 0: none)
             // Column reductions.  kStats / kLabel keep one accumulator per column in registers across the
@@ -369,16 +495,17 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint64_t a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
                 const uint64_t K1 = pack2(kc1, kc1), K2X = pack2(kc2x, kc2x), NROW = pack2(-rowc, -rowc),
                                NC2 = pack2(-2.0f * kc2, -2.0f * kc2);
-                mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
+                if (warp == 2 || warp == 1 + EPW) PEM_TRACE(trole, 30);
+                if (!(p.dev & 32)) mbar_wait(smem_u32(&sm.tmem_full[acc]), acc_phase);
+                if (warp == 2 || warp == 1 + EPW) PEM_TRACE(trole, 31);
                 tc_fence_after();
-                // columns per TMEM load: 16 where 128 column accumulators already fill the registers
-                constexpr int CW = COLREG ? 16 : 32;
-#pragma unroll
-                for (int c = 0; c < WC / CW; ++c) {
-                    if (p.dev & 4) break;
-                    float v[CW];
-                    tmem_ld(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                (uint32_t)(acc * TN + half * WC + c * CW), v);
+                // columns per TMEM load: 16 where 128 column accumulators already fill the registers, and in the FAST
+                // form, which keeps the next chunk's load in flight under the arithmetic of the current one
+                constexpr int CW = (COLREG || FAST) ? 16 : 32;
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TN + half * WC);
+                float v[CW];  // the chunk being worked on
+                auto chunk_m = [&](const int c, auto mask_tag) {  // (c is a constant after unrolling)
+                    [[maybe_unused]] constexpr bool MASK = decltype(mask_tag)::value;  // kStats: the strip has padded columns
                     if (MODE == kStore) {
                         if (row_ok) {
                             float *dst = p.atten + ((size_t)b * (p.R + p.off) + gi + p.off) * (p.Cn + p.off) +
@@ -391,14 +518,17 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // two pairs at a time: the adds do not wait on each other.  MASK: the last strip's
                         // padded columns contribute nothing (a separate copy: predicated-off selects would
                         // still take issue slots on every other strip)
-                        auto stats_chunk = [&](auto mask_tag) {
-                            constexpr bool MASK = decltype(mask_tag)::value;
+                        {
 #pragma unroll
                             for (int q = 0; q < CW; q += 4) {
                                 float e0, e1, e2, e3;
                                 unpack2(fma2(pack2(v[q], v[q + 1]), K1, NROW), e0, e1);
                                 unpack2(fma2(pack2(v[q + 2], v[q + 3]), K1, NROW), e2, e3);
-                                e0 = ex2(e0); e1 = ex2(e1); e2 = ex2(e2); e3 = ex2(e3);
+#ifdef PEM_DEV_KNOBS
+                                if (p.dev & 128) { e0 *= e0; e1 *= e1; e2 *= e2; e3 *= e3; }  // probe: no MUFU
+                                else
+#endif
+                                { e0 = ex2(e0); e1 = ex2(e1); e2 = ex2(e2); e3 = ex2(e3); }
                                 if (MASK) {
                                     if (c * CW + q >= ncols) e0 = 0.f;
                                     if (c * CW + q + 1 >= ncols) e1 = 0.f;
@@ -408,12 +538,13 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const uint64_t p01 = pack2(e0, e1), p23 = pack2(e2, e3);
                                 a0 = add2(a0, p01);
                                 a1 = add2(a1, p23);
+#ifdef PEM_DEV_KNOBS
+                                if (p.dev & 256) continue;  // probe: no column sums
+#endif
                                 colacc2[(c * CW + q) / 2] = add2(colacc2[(c * CW + q) / 2], p01);
                                 colacc2[(c * CW + q) / 2 + 1] = add2(colacc2[(c * CW + q) / 2 + 1], p23);
                             }
-                        };
-                        if (ncols >= WC) stats_chunk(std::false_type{});
-                        else stats_chunk(std::true_type{});
+                        }
                     }
                     if (LAB) {
 #pragma unroll
@@ -466,13 +597,54 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             m = shift_in_sign(m, d2);
                             m = shift_in_sign(m, d3);
                         }
-                        cmask[c] |= m;
+                        if (CW == 32) cmask[c] |= m;
+                        else cmask[c / 2] |= m << (16 * (1 - (c & 1)));  // 16-column chunks: column q of the chunk at bit 15 - q
                     }
-                }
+                };
+                auto chunk = [&](const int c) {
+                    if (MODE == kStats && ncols < WC) chunk_m(c, std::true_type{});
+                    else chunk_m(c, std::false_type{});
+                };
                 // accumulator fully read: hand the TMEM buffer back to the MMA warp of the leader
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(smem_u32(&sm.tmem_empty[acc]), 0);
+                auto hand_back = [&]() {
+                    if (warp == 2 || warp == 1 + EPW) PEM_TRACE(trole, 32);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0 && !(p.dev & 32)) mbar_arrive_remote(smem_u32(&sm.tmem_empty[acc]), 0);
+                };
+                if constexpr (FAST && !COLREG) {
+                    // Software pipeline over the four 16-column chunks of this warp: wait for chunk c, put the load of
+                    // chunk c + 1 in flight, then do the arithmetic of chunk c; the buffer goes back as soon as the last
+                    // chunk has landed in registers.  Worth 2 us on the label + weighted-sum pass and 4 us on a full
+                    // weighted-sum pass.  Not for the passes that keep one accumulator per column (COLREG): 64 of them
+                    // leave no room for a second chunk, and eight pipelined 8-column chunks measured slower (43.5 us)
+                    // than four plain 16-column ones (40 us).
+                    constexpr int NCH = WC / CW;
+                    if (!(p.dev & 4)) {
+                        uint32_t r[2][CW];
+                        tmem_ld_issue(taddr0, r[0]);
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            tmem_ld_wait(r[c & 1]);
+                            if (c + 1 < NCH) tmem_ld_issue(taddr0 + (uint32_t)((c + 1) * CW), r[(c + 1) & 1]);
+                            else hand_back();
+#pragma unroll
+                            for (int q = 0; q < CW; ++q) v[q] = __uint_as_float(r[c & 1][q]);
+                            chunk(c);
+                        }
+                    } else {
+                        hand_back();
+                    }
+                } else {
+                    if (!(p.dev & 4)) {
+#pragma unroll
+                        for (int c = 0; c < WC / CW; ++c) {
+                            tmem_ld(taddr0 + (uint32_t)(c * CW), v);
+                            chunk(c);
+                        }
+                    }
+                    hand_back();
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // per-(row, half-strip) partials: consecutive lanes = consecutive rows
                 const size_t pr = ((size_t)b * NPW * p.n_strips + NPW * n + half);
@@ -485,6 +657,7 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // fold the column accumulators across the 32 lanes, then across the 4 quadrants;
             // every (row split, CTA of the pair) leaves its own plane
+            if (warp == 2 || warp == 1 + EPW) PEM_TRACE(trole, 41);
             if (MODE == kStats || LAB) {
 #pragma unroll
                 for (int c = 0; c < WC / 32; ++c) {
@@ -512,11 +685,19 @@ fine_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             epi_barrier<EPT>();  // shared per-task constants / colred are reused by the next task
+            if (warp == 2 || warp == 1 + EPW) PEM_TRACE(trole, 42);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+#ifdef PEM_DEV_KNOBS
+    if (p.trace && threadIdx.x == 0) {  // per-CTA span: (clock, globaltimer) before / after the dependency wait and at the end
+        long long *q = p.trace + 4 * kTraceLen * 2 + 6 * blockIdx.x, g2;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2));
+        q[0] = cta_t0; q[1] = cta_g0; q[2] = cta_t1; q[3] = cta_g1; q[4] = clock64(); q[5] = g2;
+    }
+#endif
     cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM
     if (warp == 1) {
         tc_fence_after();
@@ -1127,20 +1308,30 @@ static void launch_prep(const Params &p, int B, int C, cudaStream_t st, const fl
     else go(tc_prep_kernel<2>);
 }
 
-template <int MODE, int EPW>
+template <int MODE, int EPW, bool FAST = false>
 static int launch_pass_w(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
     constexpr int kThreads = 64 + 32 * EPW;
     const size_t smem = sizeof(Smem) + 1024;
     static PemSmemCache cached(0);
-    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE, EPW>, smem, &cached)) return rc;
+    if (int rc = pem_ensure_dyn_smem(fine_tc_kernel<MODE, EPW, FAST>, smem, &cached)) return rc;
     const int n_tasks = p.B * p.n_strips * p.n_splits;
     const int pairs = min(max(1, num_sms() / 2), n_tasks);  // one cluster of two CTAs per SM pair
-    pem_launch_pdl(fine_tc_kernel<MODE, EPW>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, p);
+    pem_launch_pdl(fine_tc_kernel<MODE, EPW, FAST>, dim3(2 * pairs), dim3(kThreads), smem, st, tmA, tmB, p);
     return pem_launch_status();
 }
+// the unrolled form of the kernel (see fine_tc_kernel): single product, C = 256, 16 epilogue warps; the
+// role probes of the development build (16, 32, 64) keep the generic loops
+static bool fast_form(const Params &p) {
+    return p.single && p.KC == 4 && epw_of(p) == 16 && (p.dev & (16 | 32 | 64)) == 0;
+}
+
 template <int MODE>
 static int launch_pass(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, cudaStream_t st) {
-    if (MODE != kStore && epw_of(p) == 16) return launch_pass_w<MODE, MODE == kStore ? 8 : 16>(tmA, tmB, p, st);
+    if (MODE != kStore && epw_of(p) == 16) {
+        // the unrolled producer / issuer (see fine_tc_kernel): single product, C = 256; probes keep the generic loops
+        if (fast_form(p)) return launch_pass_w<MODE, MODE == kStore ? 8 : 16, MODE != kStore>(tmA, tmB, p, st);
+        return launch_pass_w<MODE, MODE == kStore ? 8 : 16>(tmA, tmB, p, st);
+    }
     return launch_pass_w<MODE, 8>(tmA, tmB, p, st);
 }
 
@@ -1154,6 +1345,8 @@ using namespace pem::tc;
 extern "C" void pem_dev_set_fine_steps_per_task(int v) { g_dev_steps_per_task = v; }
 extern "C" void pem_dev_set_fine_epi_warps(int v) { g_epi_warps_single = v == 8 ? 8 : 16; }
 extern "C" void pem_dev_set_fine_ring(int v) { g_ring_single = v < 2 ? 2 : v > kMaxStages ? kMaxStages : v; }
+static long long *g_dev_trace = nullptr;
+extern "C" void pem_dev_set_fine_trace(long long *buf) { g_dev_trace = buf; }  // 4 roles x kTraceLen x (tag, clock)
 #endif
 
 // fine.cu
@@ -1252,7 +1445,9 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
         p.rowpart4 = w.rowpart;
         p.bg_b = w.bg_b;
         p.lbg = w.lbg;
+        p.early = 1;  // the predecessor (tc_finish_stats_kernel) does not touch the operands
         if (int rc = launch_pass<kLabelW>(tmA, tmB, p, st)) return rc;
+        p.early = 0;
         const int n_part_m = n_part;
         pem_launch_pdl(tc_finish_label_kernel, dim3((mx + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
             w.rowmax, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part_m,
@@ -1273,6 +1468,7 @@ extern "C" int pem_fine_fused_ex(const float *f1, const float *f2, const float *
     } else {
         // pass 2: foreground labels
         p.rowmaxpart = w.rowpart;
+        p.early = 1;  // the predecessors (finish kernels) do not touch the operands
         if (int rc = launch_pass<kLabel>(tmA, tmB, p, st)) return rc;
         pem_launch_pdl(tc_finish_label_kernel, dim3((mx + kFinishItems - 1) / kFinishItems, B), dim3(256), 0, st, 
             w.rowpart, w.colpart, w.bg_a, w.bg_b, w.lbg, w.inv_colsum, pts2, p.R, p.Cn, p.Mp, p.Np, n_part,
@@ -1314,7 +1510,10 @@ extern "C" int pem_dev_fine_pass(const float *f1, const float *f2, int B, int N1
     CUtensorMap tmA, tmB;
     if (int rc = make_operand_map(&tmA, w.A, (size_t)2 * B * p.Mp, C)) return rc;
     if (int rc = make_operand_map(&tmB, w.Bm, (size_t)2 * B * p.Np, C)) return rc;
-    p.dev = flags & 7;  // (bit 3: the single-product fp16 mode; `prep` must have run in the same mode)
+#ifdef PEM_DEV_KNOBS
+    p.trace = g_dev_trace;
+#endif
+    p.dev = flags & ~8;  // (bit 3: the single-product fp16 mode; `prep` must have run in the same mode)
     p.rowpart = p.rowmaxpart = p.rowpart4 = w.rowpart;
     p.colpart = w.colpart;
     p.lrs = w.lrs;

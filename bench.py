@@ -476,7 +476,7 @@ def dominant_kernel_roofline(pkg, stage, flush):
     single = stage.fine_precision == 1
     nprod = 1.0 if single else 3.0
     traffic, traffic_src = None, None
-    for name in ("r2_fine_tc_fp16_ncu_summary.json", "r1_fine_tc_fp16_ncu_summary.json") if single else \
+    for name in ("r2b_fine_tc_fp16_ncu_summary.json", "r2_fine_tc_fp16_ncu_summary.json", "r1_fine_tc_fp16_ncu_summary.json") if single else \
             ("r2_fine_tc_ncu_summary.json", "r1_fine_tc_ncu_summary.json"):
         try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel
             with open(os.path.join(ROOT, "profiles", name)) as f:

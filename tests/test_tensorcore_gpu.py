@@ -47,7 +47,11 @@ def test_fine_fused(pkg, oracle, dev, ids, n_dense, feat_dim, precision):
 
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("B,N1,N2,C,spt", [(2, 700, 300, 128, 0), (1, 1300, 1537, 64, 0), (3, 256, 257, 256, 1),
-                                           (1, 1300, 600, 192, 4), (2, 1, 5, 64, 0)])
+                                           (1, 1300, 600, 192, 4), (2, 1, 5, 64, 0),
+                                           # C = 256: in fp16 mode the unrolled producer / issuer over the eight-slot ring
+                                           # (slot set = parity of the running row step): ragged rows and columns, odd
+                                           # step counts per task with several tasks per CTA pair (80 tasks on 74 pairs)
+                                           (2, 1300, 1537, 256, 0), (10, 700, 2040, 256, 3), (5, 300, 2048, 256, 1)])
 def test_fine_fused_ragged_shapes_and_task_splits(pkg, oracle, dev, B, N1, N2, C, spt, precision):
     """N1 != N2, sizes that are not multiples of the 256-wide tiles, every row-steps-per-task
     setting (0 = the host's choice): correlated random features so that the assignment is not flat."""

@@ -76,7 +76,8 @@ def test_fine_fused_ragged_shapes_and_task_splits(pkg, oracle, dev, B, N1, N2, C
         assert (st["pred"].cpu() - ost["pred"]).abs().max().item() < PRED_TOL[precision]
         assert oracle.rotation_angle_deg(R.cpu(), oR).max().item() < 0.1
         assert (t.cpu() - ot).abs().max().item() < 1e-4
-        assert (s.cpu() - os_).abs().max().item() < 2e-3
+        # the score counts points within dis_thres: steps of 1 / N1, two borderline points on the small clouds
+        assert (s.cpu() - os_).abs().max().item() < max(2e-3, 2.1 / N1)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

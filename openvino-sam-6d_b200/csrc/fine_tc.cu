@@ -44,6 +44,10 @@
 //     chunk): the next task's chunk kc is requested as soon as the last step of the current
 //     task is done with chunk kc, so strip loads hide behind the remaining MMAs and tasks can
 //     be short (steps per task is chosen on the host to balance the pairs).
+//   (fp16 mode at C = 256 runs the FAST form of the two single-issuer roles below: eight-slot ring = two row steps,
+//   every slot, barrier, parity and descriptor a constant plus one per-step offset, one elected lane walking a whole
+//   step; the generic loops serve the split-bf16 mode and other C.  The issuing warp's instruction chain, not the
+//   tensor pipe, bounded the generic form: tools/pass_trace.py, profiles/r2b_fine_tc_experiments.md.)
 //   warp 0      TMA producer (both CTAs; completions are signalled on the LEADER's mbarriers).
 //   warp 1      TMEM allocator; in the leader CTA (cluster rank 0) the single-thread tcgen05.mma
 //               issuer.  tcgen05.commit multicasts slot-free / accumulator-ready / chunk-free
